@@ -1,0 +1,225 @@
+/* fovpt_exact.h -- the parity-critical arithmetic of the foveated path tracer, written once
+ * with explicitly rounded operations so that an sm_100a kernel and a host compiler produce the
+ * SAME BITS.  Everything whose result the parity contract calls "bit-exact" lives here:
+ *
+ *   - the seed / jitter integer RNG          (reference cuda/random.h:34-59,101-104)
+ *   - the shading RNG                        (reference PT_sv5_/maths.h:170-210)
+ *   - launch index -> pixel, ring test       (reference PT_sv5_/deviceProgram.cu:432-440)
+ *   - the pinhole camera ray                 (reference PT_sv5_/deviceProgram.cu:479-492,
+ *                                             sutil/vec_math.h:541-561 for dot/normalize)
+ *   - the ray/triangle test that replaces OptiX's closed-source one (no reference source:
+ *     this header IS the specification; see DESIGN.md "traversal semantics")
+ *
+ * Rules: every float operation goes through FX_* (single IEEE-754 round-to-nearest-even
+ * operation, never contracted).  On the device these are the __f*_rn intrinsics, which nvcc
+ * never fuses; on the host they are plain operators and the including translation unit must
+ * be compiled with -ffp-contract=off and without -ffast-math.
+ *
+ * The product (csrc/) owns this header; oracle/ includes it, never the other way round.
+ */
+#ifndef FOVPT_EXACT_H
+#define FOVPT_EXACT_H
+
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define FX_HD __host__ __device__ __forceinline__
+#else
+#define FX_HD static inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define FX_MUL(a, b) __fmul_rn((a), (b))
+#define FX_ADD(a, b) __fadd_rn((a), (b))
+#define FX_SUB(a, b) __fsub_rn((a), (b))
+#define FX_FMA(a, b, c) __fmaf_rn((a), (b), (c))
+#define FX_RCP(a) __frcp_rn((a))
+#define FX_DIV(a, b) __fdiv_rn((a), (b))
+#define FX_SQRT(a) __fsqrt_rn((a))
+#define FX_U2F(a) __uint2float_rn((a))
+#else
+#define FX_MUL(a, b) ((float)(a) * (float)(b))
+#define FX_ADD(a, b) ((float)(a) + (float)(b))
+#define FX_SUB(a, b) ((float)(a) - (float)(b))
+#define FX_FMA(a, b, c) fmaf((a), (b), (c))
+#define FX_RCP(a) (1.0f / (float)(a))
+#define FX_DIV(a, b) ((float)(a) / (float)(b))
+#define FX_SQRT(a) sqrtf((a))
+#define FX_U2F(a) ((float)(uint32_t)(a))
+#endif
+
+typedef struct { float x, y, z; } fx_vec3;
+
+/* ------------------------------------------------------------------ integer RNG */
+
+/* 4-round TEA hash of (launch linear index, subframe) -> per-launch-index seed. */
+FX_HD uint32_t fx_tea4(uint32_t val0, uint32_t val1)
+{
+    uint32_t v0 = val0, v1 = val1, s0 = 0u;
+    for (int n = 0; n < 4; ++n) {
+        s0 += 0x9e3779b9u;
+        v0 += ((v1 << 4) + 0xa341316cu) ^ (v1 + s0) ^ ((v1 >> 5) + 0xc8013ea4u);
+        v1 += ((v0 << 4) + 0xad90777du) ^ (v0 + s0) ^ ((v0 >> 5) + 0x7e95761eu);
+    }
+    return v0;
+}
+
+/* one LCG step; returns the new state (the low 24 bits are the sample). */
+FX_HD uint32_t fx_lcg_next(uint32_t s) { return 1664525u * s + 1013904223u; }
+
+/* jitter sample in [0,1): 24 low bits / 2^24 -- exact in binary32. */
+FX_HD float fx_rnd(uint32_t* s)
+{
+    *s = fx_lcg_next(*s);
+    return FX_DIV(FX_U2F(*s & 0x00FFFFFFu), 16777216.0f);
+}
+
+/* seed after k samples: each sample advances the LCG twice (two jitter draws). */
+FX_HD uint32_t fx_seed_after(uint32_t seed0, uint32_t k)
+{
+    for (uint32_t i = 0; i < 2u * k; ++i) seed0 = fx_lcg_next(seed0);
+    return seed0;
+}
+
+typedef struct { uint32_t s1, s2; } fx_rng;
+
+FX_HD fx_rng fx_rng_init(uint32_t seed)
+{
+    fx_rng r;
+    r.s1 = 315645664u + seed;     /* int arithmetic in the reference wraps the same way */
+    r.s2 = r.s1 ^ 0x13ab45feu;
+    return r;
+}
+
+FX_HD uint32_t fx_rng_u32(fx_rng* r)
+{
+    r->s1 = (r->s2 ^ ((r->s1 << 5) | (r->s1 >> 27))) ^ (r->s1 * r->s2);
+    r->s2 = r->s1 ^ ((r->s2 << 12) | (r->s2 >> 20));
+    return r->s1;
+}
+
+/* uniform float: value * (1/2^32) clamped to [0, 0.999999].  (float)0xffffffff == 2^32. */
+FX_HD float fx_rng_f(fx_rng* r)
+{
+    float v = FX_MUL(FX_U2F(fx_rng_u32(r)), 2.3283064365386963e-10f);
+    return fmaxf(0.0f, fminf(v, 0.999999f));
+}
+
+/* ------------------------------------------------------------------ foveation index math */
+
+/* launch index -> pixel coordinate (unsigned, wraps exactly like the reference). */
+FX_HD void fx_launch_to_pixel(uint32_t lx, uint32_t ly, uint32_t factor_x, uint32_t factor_y,
+                              uint32_t off_x, uint32_t off_y, uint32_t* px, uint32_t* py)
+{
+    *px = lx * factor_x + off_x;
+    *py = ly * factor_y + off_y;
+}
+
+/* distance of the pixel from the gaze point, as the reference computes it: uint -> float
+ * conversion of both, difference, Euclidean length with z = 0. */
+FX_HD float fx_gaze_range(uint32_t px, uint32_t py, uint32_t cx, uint32_t cy)
+{
+    float dx = FX_SUB(FX_U2F(px), FX_U2F(cx));
+    float dy = FX_SUB(FX_U2F(py), FX_U2F(cy));
+    float dz = 0.0f;
+    return FX_SQRT(FX_ADD(FX_ADD(FX_MUL(dx, dx), FX_MUL(dy, dy)), FX_MUL(dz, dz)));
+}
+
+FX_HD int fx_in_ring(float range, float r_inner, float r_outer)
+{
+    return !(range < r_inner || range > r_outer);
+}
+
+/* ------------------------------------------------------------------ camera ray */
+
+FX_HD float fx_dot3(fx_vec3 a, fx_vec3 b)
+{
+    return FX_ADD(FX_ADD(FX_MUL(a.x, b.x), FX_MUL(a.y, b.y)), FX_MUL(a.z, b.z));
+}
+
+FX_HD fx_vec3 fx_normalize3(fx_vec3 v)
+{
+    float inv = FX_DIV(1.0f, FX_SQRT(fx_dot3(v, v)));
+    fx_vec3 r;
+    r.x = FX_MUL(v.x, inv); r.y = FX_MUL(v.y, inv); r.z = FX_MUL(v.z, inv);
+    return r;
+}
+
+/* d = 2*((pix + jitter)/(w,h)) - 1 ; dir = normalize(d.x*U + d.y*V + W) */
+FX_HD fx_vec3 fx_camera_dir(uint32_t px, uint32_t py, float jx, float jy, int w, int h,
+                            fx_vec3 U, fx_vec3 V, fx_vec3 W)
+{
+    float dx = FX_SUB(FX_MUL(2.0f, FX_DIV(FX_ADD(FX_U2F(px), jx), (float)w)), 1.0f);
+    float dy = FX_SUB(FX_MUL(2.0f, FX_DIV(FX_ADD(FX_U2F(py), jy), (float)h)), 1.0f);
+    fx_vec3 s;
+    s.x = FX_ADD(FX_ADD(FX_MUL(dx, U.x), FX_MUL(dy, V.x)), W.x);
+    s.y = FX_ADD(FX_ADD(FX_MUL(dx, U.y), FX_MUL(dy, V.y)), W.y);
+    s.z = FX_ADD(FX_ADD(FX_MUL(dx, U.z), FX_MUL(dy, V.z)), W.z);
+    return fx_normalize3(s);
+}
+
+/* ------------------------------------------------------------------ ray / triangle */
+
+/* Triangle record as stored on the device: v0 and the two edges, computed ONCE (by
+ * fx_make_tri, one exact subtraction per component) so that both sides test the same numbers. */
+typedef struct { fx_vec3 v0, e1, e2; } fx_tri;
+
+FX_HD fx_tri fx_make_tri(fx_vec3 a, fx_vec3 b, fx_vec3 c)
+{
+    fx_tri t;
+    t.v0 = a;
+    t.e1.x = FX_SUB(b.x, a.x); t.e1.y = FX_SUB(b.y, a.y); t.e1.z = FX_SUB(b.z, a.z);
+    t.e2.x = FX_SUB(c.x, a.x); t.e2.y = FX_SUB(c.y, a.y); t.e2.z = FX_SUB(c.z, a.z);
+    return t;
+}
+
+FX_HD fx_vec3 fx_cross3(fx_vec3 a, fx_vec3 b)
+{
+    fx_vec3 r;
+    r.x = FX_FMA(a.y, b.z, -FX_MUL(a.z, b.y));
+    r.y = FX_FMA(a.z, b.x, -FX_MUL(a.x, b.z));
+    r.z = FX_FMA(a.x, b.y, -FX_MUL(a.y, b.x));
+    return r;
+}
+
+FX_HD float fx_dot3_fma(fx_vec3 a, fx_vec3 b)
+{
+    return FX_FMA(a.z, b.z, FX_FMA(a.y, b.y, FX_MUL(a.x, b.x)));
+}
+
+/* Moeller-Trumbore with a fixed operation sequence.
+ *   returns 0: no intersection.
+ *   returns +1: hit, ray sees the front face (vertices counter-clockwise from the ray origin,
+ *               i.e. dot(cross(e1,e2), dir) < 0  <=>  det > 0) -- OptiX's front-face rule.
+ *   returns -1: hit on the back face.
+ * (u,v) are the barycentric weights of vertex 1 and vertex 2 (optixGetTriangleBarycentrics
+ * convention, used at deviceProgram.cu:656-661).  The caller applies the open interval
+ * tmin < t < tmax.  */
+FX_HD int fx_ray_tri(fx_vec3 o, fx_vec3 d, const fx_tri tr, float* t_out, float* u_out, float* v_out)
+{
+    fx_vec3 p = fx_cross3(d, tr.e2);
+    float det = fx_dot3_fma(tr.e1, p);
+    if (det == 0.0f) return 0;
+    float inv = FX_RCP(det);
+    fx_vec3 tv;
+    tv.x = FX_SUB(o.x, tr.v0.x); tv.y = FX_SUB(o.y, tr.v0.y); tv.z = FX_SUB(o.z, tr.v0.z);
+    float u = FX_MUL(fx_dot3_fma(tv, p), inv);
+    if (!(u >= 0.0f && u <= 1.0f)) return 0;
+    fx_vec3 q = fx_cross3(tv, tr.e1);
+    float v = FX_MUL(fx_dot3_fma(d, q), inv);
+    if (!(v >= 0.0f && FX_ADD(u, v) <= 1.0f)) return 0;
+    float t = FX_MUL(fx_dot3_fma(tr.e2, q), inv);
+    if (!(t == t)) return 0;
+    *t_out = t; *u_out = u; *v_out = v;
+    return det > 0.0f ? 1 : -1;
+}
+
+/* Closest-hit ordering: smaller t wins; equal t -> smaller global triangle id wins.  This makes
+ * the result independent of BVH shape and traversal order. */
+FX_HD int fx_hit_better(float t, uint32_t id, float best_t, uint32_t best_id)
+{
+    return (t < best_t) || (t == best_t && id < best_id);
+}
+
+#endif /* FOVPT_EXACT_H */

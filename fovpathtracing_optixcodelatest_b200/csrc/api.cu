@@ -1,0 +1,715 @@
+// api.cu -- the C ABI of libfovpt (include/fovpt.h): context, scene ingest, probe, frame buffers and
+// the frame scheduler that strings the wavefront kernels together.  Each entry point names, in
+// fovpt.h, the reference host function it stands in for (PT_sv5_/SimplePathtracer.cpp).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/fovpt.h"
+#include "bvh_build.h"
+#include "wavefront_launch.h"
+
+using namespace fovpt;
+
+namespace {
+
+struct HostMesh {
+    std::vector<float> vtx; std::vector<uint32_t> idx; std::vector<float> tc;
+    MaterialBlob mat; int texture_id;
+};
+struct HostTex { int w, h; std::vector<uint32_t> px; };
+
+struct EventPair { cudaEvent_t a, b; int kind; };
+
+}  // namespace
+
+struct fovpt_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    fovpt_config cfg;
+    int n_sm = 148;
+    LaunchCfg L;
+
+    // scene (host staging until commit)
+    std::vector<HostMesh> meshes;
+    std::vector<HostTex> textures;
+    // scene (device)
+    BuiltBvh bvh;
+    SceneDev scene{};
+    float* d_vtx = nullptr; uint32_t* d_idx = nullptr; uint32_t* d_tri_mesh = nullptr; float2* d_tc = nullptr;
+    MaterialBlob* d_mat = nullptr; int2* d_mesh_tex = nullptr; int4* d_tex_info = nullptr; uint32_t* d_texels = nullptr;
+    bool committed = false;
+
+    // probe
+    float4* p_data = nullptr; float *p_pdfX = nullptr, *p_cdfX = nullptr, *p_pdfY = nullptr, *p_cdfY = nullptr;
+
+    // frame buffers owned by the library (fovpt_resize)
+    int fb_w = 0, fb_h = 0;
+    float4* fb_accum = nullptr; uint32_t* fb_frame = nullptr;
+    uint32_t* last_frame_ptr = nullptr; float4* last_accum_ptr = nullptr; size_t last_npix = 0;
+
+    // wavefront storage
+    size_t path_cap = 0;
+    PathState ps{};
+    Queues q{};
+    size_t li_cap = 0; float4* li_backplate = nullptr; float4* li_color = nullptr; uint8_t* needed = nullptr;
+    size_t px_cap = 0; uint32_t* owner_map = nullptr;
+    std::vector<unsigned char> owner_key;      // what the cached owner map was computed for
+    DevStats* d_stats = nullptr;
+    unsigned char* h_pinned = nullptr; size_t h_pinned_sz = 0;
+
+    // partition
+    uint8_t* d_tile_owner = nullptr; int tile_size = 0, tiles_x = 0, tiles_y = 0, rank = 0;
+
+    // stats
+    uint64_t launches = 0, frames = 0;
+    float build_ms = 0.f;
+    cudaEvent_t ev_frame0 = nullptr, ev_frame1 = nullptr;
+    std::vector<EventPair> ev_pool; size_t ev_used = 0;
+    float last_ms[6] = {0, 0, 0, 0, 0, 0};     // frame, raygen, extend, shade, shadow, resolve
+    bool frame_timed = false;
+};
+
+namespace {
+
+enum { K_RAYGEN = 1, K_EXTEND = 2, K_SHADE = 3, K_SHADOW = 4, K_RESOLVE = 5 };
+
+int fail(fovpt_ctx* c, const std::string& m) { if (c) c->err = m; return 1; }
+int cuda_fail(fovpt_ctx* c, cudaError_t e, const char* what)
+{
+    return fail(c, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CU(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return cuda_fail(c, e__, #call); } while (0)
+
+template <typename T> cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, (n ? n : 1) * sizeof(T)); }
+
+struct Timed {       // records a CUDA-event pair around one kernel launch on the context stream
+    fovpt_ctx* c; EventPair* e;
+    Timed(fovpt_ctx* c_, int kind) : c(c_), e(nullptr)
+    {
+        if (c->ev_used == c->ev_pool.size()) {
+            EventPair p; cudaEventCreate(&p.a); cudaEventCreate(&p.b); p.kind = 0; c->ev_pool.push_back(p);
+        }
+        e = &c->ev_pool[c->ev_used++];
+        e->kind = kind;
+        cudaEventRecord(e->a, c->stream);
+    }
+    ~Timed() { cudaEventRecord(e->b, c->stream); c->launches++; }
+};
+
+void free_scene(fovpt_ctx* c)
+{
+    free_bvh(&c->bvh);
+    cudaFree(c->d_vtx); cudaFree(c->d_idx); cudaFree(c->d_tri_mesh); cudaFree(c->d_tc); cudaFree(c->d_mat);
+    cudaFree(c->d_mesh_tex); cudaFree(c->d_tex_info); cudaFree(c->d_texels);
+    c->d_vtx = nullptr; c->d_idx = nullptr; c->d_tri_mesh = nullptr; c->d_tc = nullptr; c->d_mat = nullptr;
+    c->d_mesh_tex = nullptr; c->d_tex_info = nullptr; c->d_texels = nullptr;
+    c->committed = false;
+}
+
+void free_paths(fovpt_ctx* c)
+{
+    cudaFree(c->ps.ray_o); cudaFree(c->ps.ray_d); cudaFree(c->ps.hit); cudaFree(c->ps.thr); cudaFree(c->ps.rng);
+    cudaFree(c->ps.direct); cudaFree(c->ps.indirect); cudaFree(c->ps.alpha); cudaFree(c->ps.shw_d); cudaFree(c->ps.pend);
+    cudaFree(c->q.cur); cudaFree(c->q.next); cudaFree(c->q.shadow);
+    c->ps = PathState{}; c->q.cur = c->q.next = c->q.shadow = nullptr; c->path_cap = 0;
+}
+
+int ensure_paths(fovpt_ctx* c, size_t n)
+{
+    if (n <= c->path_cap) return 0;
+    free_paths(c);
+    CU(dmalloc(&c->ps.ray_o, n)); CU(dmalloc(&c->ps.ray_d, n)); CU(dmalloc(&c->ps.hit, n)); CU(dmalloc(&c->ps.thr, n));
+    CU(dmalloc(&c->ps.rng, n)); CU(dmalloc(&c->ps.direct, n)); CU(dmalloc(&c->ps.indirect, n)); CU(dmalloc(&c->ps.alpha, n));
+    CU(dmalloc(&c->ps.shw_d, n)); CU(dmalloc(&c->ps.pend, n));
+    CU(dmalloc(&c->q.cur, n)); CU(dmalloc(&c->q.next, n)); CU(dmalloc(&c->q.shadow, n));
+    c->path_cap = n;
+    return 0;
+}
+
+int ensure_li(fovpt_ctx* c, size_t n)
+{
+    if (n <= c->li_cap) return 0;
+    cudaFree(c->li_backplate); cudaFree(c->li_color); cudaFree(c->needed);
+    CU(dmalloc(&c->li_backplate, n)); CU(dmalloc(&c->li_color, n)); CU(dmalloc(&c->needed, n));
+    c->li_cap = n; c->owner_key.clear();
+    return 0;
+}
+
+int ensure_px(fovpt_ctx* c, size_t n)
+{
+    if (n <= c->px_cap) return 0;
+    cudaFree(c->owner_map);
+    CU(dmalloc(&c->owner_map, n));
+    c->px_cap = n; c->owner_key.clear();
+    return 0;
+}
+
+int ensure_pinned(fovpt_ctx* c, size_t n)
+{
+    if (n <= c->h_pinned_sz) return 0;
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    c->h_pinned = nullptr; c->h_pinned_sz = 0;
+    CU(cudaMallocHost((void**)&c->h_pinned, n));
+    c->h_pinned_sz = n;
+    return 0;
+}
+
+// One pass of the frame schedule, host side (SimplePathtracer.cpp:137-209)
+struct PassHost { unsigned lw, lh, factor; int fill; float r_inner, r_outer; unsigned spp, off_x, off_y, redraw, subframe; };
+
+void fill_frame(fovpt_ctx* c, const LaunchParamsBlob& lp, const std::vector<PassHost>& passes, FrameDev* F, size_t* total_li)
+{
+    memset(F, 0, sizeof(*F));
+    F->w = lp.frame.size_x; F->h = lp.frame.size_y;
+    F->cx = lp.frame.c_x; F->cy = lp.frame.c_y;
+    memcpy(F->eye, lp.camera.eye, 12); memcpy(F->U, lp.camera.U, 12); memcpy(F->V, lp.camera.V, 12); memcpy(F->W, lp.camera.W, 12);
+    F->probe = lp.probe;
+    F->accum = lp.frame.accum_buffer; F->frame = lp.frame.frame_buffer;
+    F->npass = (int)passes.size();
+    size_t li = 0;
+    for (size_t p = 0; p < passes.size(); ++p) {
+        const PassHost& h = passes[p];
+        PassDev& d = F->pass[p];
+        d.lw = h.lw; d.lh = h.lh; d.factor = h.factor; d.fill = (unsigned)h.fill; d.spp = h.spp; d.redraw = h.redraw; d.subframe = h.subframe;
+        d.uoff_x = h.off_x; d.uoff_y = h.off_y; d.off_x = (int)h.off_x; d.off_y = (int)h.off_y;
+        d.r_inner = h.r_inner; d.r_outer = h.r_outer;
+        d.pid_base = 0; d.li_base = (unsigned)li;
+        li += (size_t)h.lw * h.lh;
+    }
+    *total_li = li;
+    F->max_depth = c->cfg.max_depth; F->tmin = c->cfg.tmin; F->tmax = c->cfg.tmax; F->exposure = c->cfg.exposure;
+    F->accumulate = c->cfg.accumulate; F->skip_wasted = c->cfg.skip_wasted_trace;
+    F->tile_owner = c->d_tile_owner; F->tile_size = c->tile_size; F->tiles_x = c->tiles_x; F->tiles_y = c->tiles_y; F->rank = c->rank;
+}
+
+// runs the passes of one frame through the wavefront; asynchronous.
+int run_frame(fovpt_ctx* c, const LaunchParamsBlob& lp, const std::vector<PassHost>& passes)
+{
+    if (!c->committed) return fail(c, "scene not committed");
+    if (!lp.probe.data) return fail(c, "LaunchParams.probe is empty (call fovpt_probe_upload / setProbe first)");
+    if (!lp.frame.accum_buffer || !lp.frame.frame_buffer) return fail(c, "LaunchParams.frame buffers are null (call fovpt_resize first)");
+    if (passes.empty() || passes.size() > (size_t)kMaxPasses) return fail(c, "bad pass count");
+    for (auto& p : passes) {
+        if (p.spp == 0 || p.spp > 4096) return fail(c, "samples_per_launch out of range");
+        if ((size_t)p.lw * p.lh >= (1u << 28)) return fail(c, "launch too large");
+        if (p.factor == 0 || p.fill <= 0) return fail(c, "factor / fillSize must be positive");
+    }
+    cudaSetDevice(c->device);
+    FrameDev F; size_t total_li = 0;
+    fill_frame(c, lp, passes, &F, &total_li);
+    const size_t npix = (size_t)F.w * F.h;
+    if (ensure_li(c, total_li) || ensure_px(c, npix)) return 1;
+
+    c->ev_used = 0;
+    cudaEventRecord(c->ev_frame0, c->stream);
+
+    // owner map: recomputed only when the frame geometry / gaze / partition changes
+    std::vector<unsigned char> key(sizeof(int) * 4 + sizeof(PassDev) * kMaxPasses + sizeof(void*) + 5 * sizeof(int));
+    {
+        unsigned char* k = key.data();
+        int head[4] = {F.w, F.h, (int)F.cx, (int)F.cy};
+        memcpy(k, head, sizeof(head)); k += sizeof(head);
+        PassDev geo[kMaxPasses]; memset(geo, 0, sizeof(geo));
+        for (int p = 0; p < F.npass; ++p) { geo[p] = F.pass[p]; geo[p].spp = 0; geo[p].redraw = 0; geo[p].subframe = 0; }
+        memcpy(k, geo, sizeof(geo)); k += sizeof(geo);
+        const void* to = F.tile_owner; memcpy(k, &to, sizeof(void*)); k += sizeof(void*);
+        int tail[5] = {F.tile_size, F.tiles_x, F.tiles_y, F.rank, F.npass};
+        memcpy(k, tail, sizeof(tail));
+    }
+    if (key != c->owner_key) {
+        CU(cudaMemsetAsync(c->needed, 0, total_li, c->stream));
+        { Timed t(c, K_RESOLVE); launch_owner_map(c->L, F, c->owner_map, c->needed); }
+        c->owner_key = key;
+    }
+
+    // chunking: at most path budget paths in flight
+    const size_t budget = (size_t)48 << 20;
+    struct Chunk { int pass; unsigned row0, row1; unsigned pid_base; };
+    std::vector<std::vector<Chunk>> groups;
+    {
+        std::vector<Chunk> cur; size_t used = 0;
+        for (int p = 0; p < F.npass; ++p) {
+            const PassDev& P = F.pass[p];
+            const size_t per_row = (size_t)P.lw * P.spp;
+            unsigned row = 0;
+            while (row < P.lh) {
+                size_t room = budget > used ? budget - used : 0;
+                unsigned rows = (unsigned)std::min<size_t>(P.lh - row, per_row ? room / per_row : P.lh);
+                if (rows == 0) {
+                    if (cur.empty()) rows = 1;      // a single row larger than the budget: take it alone
+                    else { groups.push_back(cur); cur.clear(); used = 0; continue; }
+                }
+                cur.push_back({p, row, row + rows, (unsigned)used});
+                used += per_row * rows; row += rows;
+            }
+        }
+        if (!cur.empty()) groups.push_back(cur);
+    }
+    size_t max_paths = 0;
+    for (auto& g : groups) { size_t n = 0; for (auto& ch : g) n += (size_t)(ch.row1 - ch.row0) * F.pass[ch.pass].lw * F.pass[ch.pass].spp; max_paths = std::max(max_paths, n); }
+    if (max_paths >= 0xfffffff0ull) return fail(c, "path batch exceeds 32-bit ids");
+    if (ensure_paths(c, max_paths)) return 1;
+
+    const int iters = c->cfg.max_depth + 1 + (c->scene.any_catcher ? 4 : 0);
+    for (auto& g : groups) {
+        CU(cudaMemsetAsync(c->q.counts, 0, 4 * sizeof(uint32_t), c->stream));
+        for (auto& ch : g) {
+            Timed t(c, K_RAYGEN);
+            launch_raygen(c->L, F, ch.pass, ch.row0, ch.row1, ch.pid_base, c->needed, c->ps, c->q, c->li_backplate, c->d_stats);
+        }
+        for (int it = 0; it < iters; ++it) {
+            { Timed t(c, K_EXTEND); launch_extend(c->L, c->scene, c->ps, c->q, c->cfg.tmin, c->cfg.tmax, c->d_stats); }
+            { Timed t(c, K_SHADE); launch_shade(c->L, F, c->scene, c->ps, c->q, c->cfg.fast_math != 0); }
+            { Timed t(c, K_SHADOW); launch_shadow(c->L, c->scene, c->ps, c->q, c->cfg.tmin, c->cfg.tmax, c->d_stats); }
+            std::swap(c->q.cur, c->q.next);
+            { Timed t(c, 0); launch_swap(c->L, c->q.counts); }
+        }
+        for (auto& ch : g) {
+            Timed t(c, K_RESOLVE);
+            launch_resolve_li(c->L, F, ch.pass, ch.row0, ch.row1, ch.pid_base, c->needed, c->ps, c->li_backplate, c->li_color);
+        }
+    }
+    { Timed t(c, K_RESOLVE); launch_resolve_px(c->L, F, c->owner_map, c->li_color, c->cfg.fast_math != 0); }
+    cudaEventRecord(c->ev_frame1, c->stream);
+    c->frame_timed = true;
+    c->frames++;
+    c->last_frame_ptr = F.frame; c->last_accum_ptr = F.accum; c->last_npix = npix;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+void collect_times(fovpt_ctx* c)
+{
+    if (!c->frame_timed) return;
+    cudaEventSynchronize(c->ev_frame1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev_frame0, c->ev_frame1);
+    for (int i = 0; i < 6; ++i) c->last_ms[i] = 0.f;
+    c->last_ms[0] = ms;
+    for (size_t i = 0; i < c->ev_used; ++i) {
+        EventPair& e = c->ev_pool[i];
+        if (e.kind <= 0 || e.kind > 5) continue;
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, e.a, e.b) == cudaSuccess) c->last_ms[e.kind] += t;
+    }
+    c->frame_timed = false;
+}
+
+std::vector<PassHost> schedule(const fovpt_config& cfg, const LaunchParamsBlob& lp)
+{
+    std::vector<PassHost> v;
+    const int w = lp.frame.size_x, h = lp.frame.size_y;
+    const unsigned sub = lp.frame.subframe_index;
+    const bool ext = cfg.seed_all_passes_with_subframe != 0;
+    if (!cfg.foveated) {     // FOV_OFF block, SimplePathtracer.cpp:85-131
+        v.push_back({(unsigned)w, (unsigned)h, 1u, 1, 0.f, 1000000000.f, (unsigned)cfg.spp_uniform, 0u, 0u, 0u, ext ? sub : 0u});
+        return v;
+    }
+    const int ri = cfg.inner_radius, ro = cfg.outer_radius;
+    const unsigned cx = lp.frame.c_x, cy = lp.frame.c_y;
+    // periphery :137-157
+    v.push_back({(unsigned)(w / 4), (unsigned)(h / 4), 4u, 4, (float)ro, 1000000000.f, (unsigned)cfg.spp_periphery, 0u, 0u, 0u, sub});
+    // mid ring :160-187 (launch dims are the float r_outer truncated)
+    const float r2 = (float)(ro + 2);
+    v.push_back({(unsigned)r2, (unsigned)r2, 2u, 2, (float)ri, r2, (unsigned)cfg.spp_mid, cx - (unsigned)(ro + 2), cy - (unsigned)(ro + 2),
+                 ext ? 0u : 1u, ext ? sub : 0u});
+    // fovea :189-209
+    const float r3 = (float)(ri + 1);
+    v.push_back({(unsigned)(r3 * 2), (unsigned)(r3 * 2), 1u, 1, 0.f, r3, (unsigned)cfg.spp_fovea, cx - (unsigned)(ri + 1), cy - (unsigned)(ri + 1),
+                 ext ? 0u : 1u, ext ? sub : 0u});
+    return v;
+}
+
+}  // namespace
+
+// ====================================================================== C ABI
+extern "C" {
+
+void fovpt_default_config(fovpt_config* k)
+{
+    memset(k, 0, sizeof(*k));
+    k->max_depth = 4; k->tmin = 0.01f; k->tmax = 1e16f; k->exposure = 16.0f; k->accumulate = 0; k->foveated = 1;
+    k->inner_radius = 74; k->outer_radius = 241; k->spp_periphery = 8; k->spp_mid = 16; k->spp_fovea = 32; k->spp_uniform = 4;
+    k->seed_all_passes_with_subframe = 0; k->skip_wasted_trace = 1; k->fast_math = 0;
+}
+
+int fovpt_create(fovpt_ctx** out, int device, void* stream)
+{
+    if (!out) return 1;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return 2;   // "no CUDA capable devices", SimplePathtracer.cpp:318-321
+    fovpt_ctx* c = new fovpt_ctx();
+    c->device = device;
+    fovpt_default_config(&c->cfg);
+    if (cudaSetDevice(device) != cudaSuccess) { delete c; return 3; }
+    cudaFree(0);
+    if (stream) c->stream = (cudaStream_t)stream;
+    else { if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return 4; } c->own_stream = true; }
+    cudaDeviceProp prop;
+    cudaGetDeviceProperties(&prop, device);
+    c->n_sm = prop.multiProcessorCount;
+    int be = 8, bs = 4;
+    query_occupancy(&be, &bs);
+    c->L.stream = c->stream;
+    c->L.grid_trace = c->n_sm * (be > 0 ? be : 8);
+    c->L.grid_shade = c->n_sm * (bs > 0 ? bs : 4);
+    c->L.grid_light = c->n_sm * 8;
+    if (dmalloc(&c->q.counts, 4) != cudaSuccess || dmalloc(&c->d_stats, 1) != cudaSuccess) { delete c; return 5; }
+    cudaMemset(c->q.counts, 0, 16); cudaMemset(c->d_stats, 0, sizeof(DevStats));
+    cudaEventCreate(&c->ev_frame0); cudaEventCreate(&c->ev_frame1);
+    *out = c;
+    return 0;
+}
+
+int fovpt_destroy(fovpt_ctx* c)
+{
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_scene(c); free_paths(c);
+    cudaFree(c->p_data); cudaFree(c->p_pdfX); cudaFree(c->p_cdfX); cudaFree(c->p_pdfY); cudaFree(c->p_cdfY);
+    cudaFree(c->fb_accum); cudaFree(c->fb_frame); cudaFree(c->li_backplate); cudaFree(c->li_color); cudaFree(c->needed);
+    cudaFree(c->owner_map); cudaFree(c->q.counts); cudaFree(c->d_stats); cudaFree(c->d_tile_owner);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    for (auto& e : c->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    cudaEventDestroy(c->ev_frame0); cudaEventDestroy(c->ev_frame1);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return 0;
+}
+
+const char* fovpt_last_error(fovpt_ctx* c) { return c ? c->err.c_str() : "null context"; }
+void* fovpt_stream(fovpt_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int fovpt_set_config(fovpt_ctx* c, const fovpt_config* k)
+{
+    if (!c || !k) return 1;
+    if (k->max_depth < 0 || k->max_depth > 200) return fail(c, "max_depth out of range");
+    if (k->foveated && (k->inner_radius < 0 || k->outer_radius < k->inner_radius)) return fail(c, "bad radii");
+    if (k->spp_periphery <= 0 || k->spp_mid <= 0 || k->spp_fovea <= 0 || k->spp_uniform <= 0) return fail(c, "spp must be positive");
+    c->cfg = *k;
+    return 0;
+}
+int fovpt_get_config(fovpt_ctx* c, fovpt_config* k) { if (!c || !k) return 1; *k = c->cfg; return 0; }
+
+int fovpt_scene_begin(fovpt_ctx* c)
+{
+    if (!c) return 1;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->meshes.clear(); c->textures.clear();
+    free_scene(c);
+    return 0;
+}
+
+int fovpt_scene_add_texture(fovpt_ctx* c, const uint32_t* rgba8, int w, int h)
+{
+    if (!c || !rgba8 || w <= 0 || h <= 0) { fail(c, "bad texture"); return -1; }
+    HostTex t; t.w = w; t.h = h; t.px.assign(rgba8, rgba8 + (size_t)w * h);
+    c->textures.push_back(std::move(t));
+    return (int)c->textures.size() - 1;
+}
+
+int fovpt_scene_add_mesh(fovpt_ctx* c, const float* vtx, size_t nvtx, const uint32_t* idx, size_t ntri,
+                         const float* tc, const void* material104, int texture_id)
+{
+    if (!c || !vtx || !idx || !material104) { fail(c, "null mesh argument"); return -1; }
+    for (size_t i = 0; i < 3 * ntri; ++i)
+        if (idx[i] >= nvtx) { fail(c, "mesh index out of range (see SURVEY A.9: one usemtl per shape)"); return -1; }
+    for (size_t i = 0; i < 3 * nvtx; ++i)
+        if (!std::isfinite(vtx[i])) { fail(c, "non-finite vertex"); return -1; }
+    HostMesh m;
+    m.vtx.assign(vtx, vtx + 3 * nvtx); m.idx.assign(idx, idx + 3 * ntri);
+    if (tc) m.tc.assign(tc, tc + 2 * nvtx);
+    memcpy(&m.mat, material104, sizeof(MaterialBlob));
+    m.texture_id = texture_id;
+    c->meshes.push_back(std::move(m));
+    return (int)c->meshes.size() - 1;
+}
+
+int fovpt_scene_commit(fovpt_ctx* c, uint64_t* traversable_out)
+{
+    if (!c) return 1;
+    cudaSetDevice(c->device);
+    free_scene(c);
+    size_t nv = 0, nt = 0;
+    for (auto& m : c->meshes) { nv += m.vtx.size() / 3; nt += m.idx.size() / 3; }
+    if (nt >= (1u << 29)) return fail(c, "too many triangles");
+    std::vector<float> vtx; vtx.reserve(3 * nv);
+    std::vector<uint32_t> idx; idx.reserve(3 * nt);
+    std::vector<uint32_t> tri_mesh; tri_mesh.reserve(nt);
+    std::vector<float> tc(2 * nv, 0.f);
+    std::vector<MaterialBlob> mats; std::vector<int2> mesh_tex;
+    int any_catcher = 0;
+    size_t vbase = 0;
+    for (size_t mi = 0; mi < c->meshes.size(); ++mi) {
+        HostMesh& m = c->meshes[mi];
+        vtx.insert(vtx.end(), m.vtx.begin(), m.vtx.end());
+        for (uint32_t i : m.idx) idx.push_back(i + (uint32_t)vbase);
+        tri_mesh.insert(tri_mesh.end(), m.idx.size() / 3, (uint32_t)mi);
+        if (!m.tc.empty()) memcpy(&tc[2 * vbase], m.tc.data(), m.tc.size() * 4);
+        mats.push_back(m.mat);
+        const bool has_tex = m.texture_id >= 0 && m.texture_id < (int)c->textures.size();
+        mesh_tex.push_back(make_int2(has_tex ? m.texture_id : -1, m.tc.empty() ? 0 : 1));
+        if (m.mat.flags & kMaterialShadowCatcher) any_catcher = 1;
+        vbase += m.vtx.size() / 3;
+    }
+    std::vector<int4> tex_info; std::vector<uint32_t> texels;
+    for (auto& t : c->textures) {
+        tex_info.push_back(make_int4((int)texels.size(), t.w, t.h, 0));
+        texels.insert(texels.end(), t.px.begin(), t.px.end());
+    }
+    CU(dmalloc(&c->d_vtx, vtx.size())); CU(dmalloc(&c->d_idx, idx.size())); CU(dmalloc(&c->d_tri_mesh, tri_mesh.size()));
+    CU(dmalloc(&c->d_tc, nv)); CU(dmalloc(&c->d_mat, mats.size())); CU(dmalloc(&c->d_mesh_tex, mesh_tex.size()));
+    CU(dmalloc(&c->d_tex_info, tex_info.size())); CU(dmalloc(&c->d_texels, texels.size()));
+    CU(cudaMemcpy(c->d_vtx, vtx.data(), vtx.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_idx, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_tri_mesh, tri_mesh.data(), tri_mesh.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_tc, tc.data(), tc.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_mat, mats.data(), mats.size() * sizeof(MaterialBlob), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_mesh_tex, mesh_tex.data(), mesh_tex.size() * sizeof(int2), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_tex_info, tex_info.data(), tex_info.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_texels, texels.data(), texels.size() * 4, cudaMemcpyHostToDevice));
+
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, c->stream);
+    cudaError_t be = build_bvh(c->d_vtx, c->d_idx, (uint32_t)nt, 4, c->stream, &c->bvh, &c->launches);
+    cudaEventRecord(e1, c->stream);
+    if (be != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return cuda_fail(c, be, "build_bvh"); }
+    cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&c->build_ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (c->bvh.max_depth > (uint32_t)kStackSize) return fail(c, "BVH deeper than the traversal stack");
+
+    c->scene.bvh.nodes = c->bvh.nodes; c->scene.bvh.tris = c->bvh.tris;
+    c->scene.bvh.n_nodes = c->bvh.n_nodes; c->scene.bvh.n_tris = c->bvh.n_tris;
+    c->scene.tri_mesh = c->d_tri_mesh; c->scene.tri_vidx = c->d_idx; c->scene.texcoords = c->d_tc;
+    c->scene.materials = c->d_mat; c->scene.mesh_tex = c->d_mesh_tex; c->scene.tex_info = c->d_tex_info; c->scene.texels = c->d_texels;
+    c->scene.any_catcher = any_catcher;
+    c->committed = true;
+    if (traversable_out) *traversable_out = (uint64_t)(uintptr_t)c->bvh.nodes | 1ull;
+    return 0;
+}
+
+int fovpt_probe_upload(fovpt_ctx* c, int w, int h, const float* rgba, const float* pdfX, const float* cdfX,
+                       const float* pdfY, const float* cdfY, const float offset[3], void* probe_out64)
+{
+    if (!c) return 1;
+    if (w <= 0 || h <= 0 || !rgba || !pdfX || !cdfX || !pdfY || !cdfY || !probe_out64) return fail(c, "Probe Data is not valid");   // Probe.h:104-105
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->p_data); cudaFree(c->p_pdfX); cudaFree(c->p_cdfX); cudaFree(c->p_pdfY); cudaFree(c->p_cdfY);
+    const size_t n = (size_t)w * h;
+    CU(dmalloc(&c->p_data, n)); CU(dmalloc(&c->p_pdfX, n)); CU(dmalloc(&c->p_cdfX, n)); CU(dmalloc(&c->p_pdfY, (size_t)h)); CU(dmalloc(&c->p_cdfY, (size_t)h));
+    CU(cudaMemcpy(c->p_data, rgba, n * 16, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->p_pdfX, pdfX, n * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->p_cdfX, cdfX, n * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->p_pdfY, pdfY, (size_t)h * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->p_cdfY, cdfY, (size_t)h * 4, cudaMemcpyHostToDevice));
+    ProbeBlob pb; memset(&pb, 0, sizeof(pb));
+    pb.width = w; pb.height = h; pb.data = c->p_data;
+    if (offset) memcpy(pb.offset, offset, 12);
+    pb.pdfValuesX = c->p_pdfX; pb.cdfValuesX = c->p_cdfX; pb.pdfValuesY = c->p_pdfY; pb.cdfValuesY = c->p_cdfY;
+    memcpy(probe_out64, &pb, sizeof(pb));
+    return 0;
+}
+
+int fovpt_resize(fovpt_ctx* c, int w, int h, void** accum_out, void** frame_out)
+{
+    if (!c) return 1;
+    if (w <= 0 || h <= 0) return fail(c, "bad frame size");
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->fb_accum); cudaFree(c->fb_frame);
+    c->fb_accum = nullptr; c->fb_frame = nullptr;
+    const size_t n = (size_t)w * h;
+    CU(dmalloc(&c->fb_accum, n)); CU(dmalloc(&c->fb_frame, n));
+    CU(cudaMemset(c->fb_accum, 0, n * 16)); CU(cudaMemset(c->fb_frame, 0, n * 4));
+    c->fb_w = w; c->fb_h = h;
+    c->last_frame_ptr = c->fb_frame; c->last_accum_ptr = c->fb_accum; c->last_npix = n;
+    if (accum_out) *accum_out = c->fb_accum;
+    if (frame_out) *frame_out = c->fb_frame;
+    return 0;
+}
+
+int fovpt_launch(fovpt_ctx* c, const void* lp248, size_t size, unsigned lw, unsigned lh)
+{
+    if (!c) return 1;
+    if (!lp248 || size != sizeof(LaunchParamsBlob)) return fail(c, "launch params must be the 248-byte LaunchParams");
+    LaunchParamsBlob lp; memcpy(&lp, lp248, sizeof(lp));
+    if (lp.frame.size_x <= 0 || lp.frame.size_y <= 0) return fail(c, "frame.size not set");
+    if (lp.frame.factor_x != lp.frame.factor_y) return fail(c, "anisotropic factor not supported");
+    if (lw == 0 || lh == 0) return 0;
+    std::vector<PassHost> p;
+    p.push_back({lw, lh, lp.frame.factor_x, lp.frame.fillSize, lp.frame.r_inner, lp.frame.r_outer, lp.samples_per_launch,
+                 lp.frame.offset_x, lp.frame.offset_y, lp.frame.redraw, lp.frame.subframe_index});
+    return run_frame(c, lp, p);
+}
+
+int fovpt_render_frame(fovpt_ctx* c, void* lp248)
+{
+    if (!c) return 1;
+    if (!lp248) return fail(c, "null launch params");
+    LaunchParamsBlob* lp = (LaunchParamsBlob*)lp248;
+    if (lp->frame.size_x == 0) return 0;                  // SimplePathtracer.cpp:81-82
+    std::vector<PassHost> p = schedule(c->cfg, *lp);
+    LaunchParamsBlob tmp; memcpy(&tmp, lp, sizeof(tmp));
+    int rc = run_frame(c, tmp, p);
+    if (rc) return rc;
+    // what render() leaves behind in the host copy of the params (:137-211)
+    const PassHost& last = p.back();
+    lp->frame.factor_x = lp->frame.factor_y = last.factor; lp->frame.factor_z = 1;
+    lp->frame.fillSize = last.fill; lp->frame.r_inner = last.r_inner; lp->frame.r_outer = last.r_outer;
+    lp->samples_per_launch = last.spp; lp->frame.offset_x = last.off_x; lp->frame.offset_y = last.off_y; lp->frame.redraw = last.redraw;
+    lp->frame.subframe_index = lp->frame.subframe_index + 1;
+    return 0;
+}
+
+int fovpt_sync(fovpt_ctx* c)
+{
+    if (!c) return 1;
+    cudaSetDevice(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    collect_times(c);
+    return 0;
+}
+
+int fovpt_download(fovpt_ctx* c, uint32_t* dst, size_t npix)
+{
+    if (!c || !dst) return 1;
+    if (!c->last_frame_ptr || npix > c->last_npix) return fail(c, "no frame buffer of that size");
+    cudaSetDevice(c->device);
+    if (ensure_pinned(c, npix * 4)) return 1;
+    CU(cudaMemcpyAsync(c->h_pinned, c->last_frame_ptr, npix * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    memcpy(dst, c->h_pinned, npix * 4);
+    collect_times(c);
+    return 0;
+}
+
+int fovpt_download_accum(fovpt_ctx* c, float* dst, size_t npix)
+{
+    if (!c || !dst) return 1;
+    if (!c->last_accum_ptr || npix > c->last_npix) return fail(c, "no accumulation buffer of that size");
+    cudaSetDevice(c->device);
+    CU(cudaMemcpyAsync(dst, c->last_accum_ptr, npix * 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    collect_times(c);
+    return 0;
+}
+
+int fovpt_trace(fovpt_ctx* c, const float* rays, size_t n, int mode, int32_t* tri, float* tuv)
+{
+    if (!c || !rays || !tri) return 1;
+    if (!c->committed) return fail(c, "scene not committed");
+    if (mode != 0 && mode != 1) return fail(c, "mode must be 0 (closest) or 1 (any)");
+    if (n == 0) return 0;
+    cudaSetDevice(c->device);
+    float* d_r = nullptr; int32_t* d_t = nullptr; float* d_tuv = nullptr;
+    CU(dmalloc(&d_r, 8 * n)); CU(dmalloc(&d_t, n)); CU(dmalloc(&d_tuv, 3 * n));
+    CU(cudaMemcpyAsync(d_r, rays, 32 * n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemsetAsync(d_tuv, 0, 12 * n, c->stream));
+    launch_trace_query(c->L, c->scene, d_r, n, mode, d_t, d_tuv);
+    c->launches++;
+    CU(cudaMemcpyAsync(tri, d_t, 4 * n, cudaMemcpyDeviceToHost, c->stream));
+    if (tuv) CU(cudaMemcpyAsync(tuv, d_tuv, 12 * n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    cudaFree(d_r); cudaFree(d_t); cudaFree(d_tuv);
+    return 0;
+}
+
+int fovpt_primary_hits(fovpt_ctx* c, const void* lp248, unsigned lw, unsigned lh, int32_t* tri, float* tuv, float* dir)
+{
+    if (!c || !lp248 || !tri || !tuv || !dir) return 1;
+    if (!c->committed) return fail(c, "scene not committed");
+    LaunchParamsBlob lp; memcpy(&lp, lp248, sizeof(lp));
+    std::vector<PassHost> p;
+    p.push_back({lw, lh, lp.frame.factor_x, lp.frame.fillSize, lp.frame.r_inner, lp.frame.r_outer, lp.samples_per_launch,
+                 lp.frame.offset_x, lp.frame.offset_y, lp.frame.redraw, lp.frame.subframe_index});
+    FrameDev F; size_t total_li = 0;
+    fill_frame(c, lp, p, &F, &total_li);
+    cudaSetDevice(c->device);
+    const size_t n = (size_t)lw * lh;
+    int32_t* d_t = nullptr; float* d_tuv = nullptr; float* d_dir = nullptr;
+    CU(dmalloc(&d_t, n)); CU(dmalloc(&d_tuv, 3 * n)); CU(dmalloc(&d_dir, 3 * n));
+    CU(cudaMemsetAsync(d_tuv, 0, 12 * n, c->stream)); CU(cudaMemsetAsync(d_dir, 0, 12 * n, c->stream));
+    launch_primary_hits(c->L, F, c->scene, d_t, d_tuv, d_dir);
+    c->launches++;
+    CU(cudaMemcpyAsync(tri, d_t, 4 * n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(tuv, d_tuv, 12 * n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(dir, d_dir, 12 * n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    cudaFree(d_t); cudaFree(d_tuv); cudaFree(d_dir);
+    return 0;
+}
+
+int fovpt_set_tile_owner(fovpt_ctx* c, int tile_size, int tiles_x, int tiles_y, const uint8_t* owner, int rank)
+{
+    if (!c) return 1;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_tile_owner); c->d_tile_owner = nullptr;
+    c->owner_key.clear();
+    if (!owner) { c->tile_size = c->tiles_x = c->tiles_y = 0; c->rank = 0; return 0; }
+    if (tile_size <= 0 || tiles_x <= 0 || tiles_y <= 0) return fail(c, "bad tile grid");
+    CU(dmalloc(&c->d_tile_owner, (size_t)tiles_x * tiles_y));
+    CU(cudaMemcpy(c->d_tile_owner, owner, (size_t)tiles_x * tiles_y, cudaMemcpyHostToDevice));
+    c->tile_size = tile_size; c->tiles_x = tiles_x; c->tiles_y = tiles_y; c->rank = rank;
+    return 0;
+}
+
+int fovpt_get_stats(fovpt_ctx* c, fovpt_stats* s)
+{
+    if (!c || !s) return 1;
+    cudaSetDevice(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    collect_times(c);
+    DevStats d;
+    CU(cudaMemcpy(&d, c->d_stats, sizeof(d), cudaMemcpyDeviceToHost));
+    memset(s, 0, sizeof(*s));
+    s->samples = d.samples; s->radiance_rays = d.radiance_rays; s->shadow_rays = d.shadow_rays;
+    s->kernel_launches = c->launches; s->frames = c->frames;
+    s->bvh_nodes = c->bvh.n_nodes; s->bvh_tris = c->bvh.n_tris; s->bvh_build_ms = c->build_ms;
+    s->last_frame_ms = c->last_ms[0]; s->last_raygen_ms = c->last_ms[K_RAYGEN]; s->last_extend_ms = c->last_ms[K_EXTEND];
+    s->last_shade_ms = c->last_ms[K_SHADE]; s->last_shadow_ms = c->last_ms[K_SHADOW]; s->last_resolve_ms = c->last_ms[K_RESOLVE];
+    return 0;
+}
+
+int fovpt_reset_stats(fovpt_ctx* c)
+{
+    if (!c) return 1;
+    cudaSetDevice(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemset(c->d_stats, 0, sizeof(DevStats)));
+    c->launches = 0; c->frames = 0;
+    return 0;
+}
+
+int fovpt_bvh_info(fovpt_ctx* c, uint64_t* n_nodes, uint64_t* n_tris)
+{
+    if (!c || !c->committed) return 1;
+    if (n_nodes) *n_nodes = c->bvh.n_nodes;
+    if (n_tris) *n_tris = c->bvh.n_tris;
+    return 0;
+}
+
+int fovpt_bvh_read(fovpt_ctx* c, void* nodes64, uint32_t* sorted_tri_ids)
+{
+    if (!c || !c->committed) return 1;
+    cudaSetDevice(c->device);
+    if (nodes64 && c->bvh.n_nodes) CU(cudaMemcpy(nodes64, c->bvh.nodes, (size_t)c->bvh.n_nodes * 64, cudaMemcpyDeviceToHost));
+    if (sorted_tri_ids && c->bvh.n_tris) CU(cudaMemcpy(sorted_tri_ids, c->bvh.sorted_ids, (size_t)c->bvh.n_tris * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+}  // extern "C"

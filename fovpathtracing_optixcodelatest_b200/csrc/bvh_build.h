@@ -1,0 +1,24 @@
+// bvh_build.h -- host entry of the on-device BVH builder (bvh_build.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace fovpt {
+
+struct BuiltBvh {
+    const float4*   nodes = nullptr;       // 4 x float4 per inner node (layout: bvh.cuh)
+    const float4*   tris = nullptr;        // 3 x float4 per triangle, leaf order
+    const float4*   tri_rec = nullptr;     // 3 x float4 per triangle, global-id order
+    const uint32_t* sorted_ids = nullptr;  // leaf slot -> global triangle id
+    uint32_t        n_nodes = 0, n_tris = 0, max_depth = 0;
+    float           pad = 0.f;
+    float           bounds[6] = {0, 0, 0, 0, 0, 0};
+};
+
+// d_vtx: float3 soup of all meshes; d_idx: uint3 per triangle, already rebased to the soup.
+// Synchronises the stream (the caller is a one-off setup path, like optixAccelBuild + SYNC).
+cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, uint32_t ntri, int leaf_max, cudaStream_t st,
+                      BuiltBvh* out, uint64_t* launches);
+void free_bvh(BuiltBvh* b);
+
+}  // namespace fovpt

@@ -1,0 +1,438 @@
+// wavefront.cu -- the sm_100a kernels that replace the reference's OptiX device programs
+// (PT_sv5_/deviceProgram.cu): __raygen__renderFrame (:392-617) is split into k_raygen +
+// k_resolve_li + k_resolve_px, optixTrace(RADIANCE) (:196-222) is k_extend, __closesthit__radiance
+// / __miss__radiance (:619-732, :253-282) are k_shade, optixTrace(OCCLUSION) + its three programs
+// (:224-300) are k_shadow.  All kernels are persistent grid-stride loops over device-resident
+// queues, so a whole frame is enqueued without a host round trip.
+#include <cooperative_groups.h>
+
+#include "shade.cuh"
+#include "wavefront.cuh"
+#include "wavefront_launch.h"
+
+namespace cg = cooperative_groups;
+
+namespace fovpt {
+
+// ------------------------------------------------------------------ small device helpers
+__device__ __forceinline__ uint32_t queue_push(uint32_t* counter)
+{
+    cg::coalesced_group g = cg::coalesced_threads();
+    uint32_t base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(counter, g.size());
+    return g.shfl(base, 0) + g.thread_rank();
+}
+
+__device__ __forceinline__ bool li_active(const FrameDev& F, const PassDev& P, unsigned lx, unsigned ly, uint32_t* px, uint32_t* py)
+{
+    fx_launch_to_pixel(lx, ly, P.factor, P.factor, P.uoff_x, P.uoff_y, px, py);       // deviceProgram.cu:433
+    const float range = fx_gaze_range(*px, *py, F.cx, F.cy);                          // :435
+    return fx_in_ring(range, P.r_inner, P.r_outer) != 0;                              // :437
+}
+
+__device__ __forceinline__ long long floor_div(long long a, long long b) { long long q = a / b; return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q; }
+__device__ __forceinline__ long long ceil_div(long long a, long long b) { return -floor_div(-a, b); }
+
+// launch coordinates (one axis) whose splat reaches destination coordinate X of an n-wide frame:
+// px0 = l*factor + off, writes px0 .. px0+fill-1, clamped to [0, n-1] (deviceProgram.cu:546-556)
+__device__ __forceinline__ void splat_candidates(int X, int n, const PassDev& P, int off, unsigned ldim, int* lo, int* hi)
+{
+    long long h = floor_div((long long)X - off, (long long)P.factor);
+    long long l = ceil_div((long long)X - ((long long)P.fill - 1) - off, (long long)P.factor);
+    if (X == n - 1) h = (long long)ldim - 1;     // everything beyond the frame clamps onto the border
+    if (l < 0) l = 0;
+    if (h > (long long)ldim - 1) h = (long long)ldim - 1;
+    *lo = (int)l; *hi = (int)h;
+}
+
+// The launch index of pass P whose write to pixel (X,Y) survives: the row-major LAST active
+// writer (sequential semantics of one launch; only border pixels ever have more than one).
+__device__ __forceinline__ uint32_t pass_owner(const FrameDev& F, const PassDev& P, int X, int Y)
+{
+    int lox, hix, loy, hiy;
+    splat_candidates(X, F.w, P, P.off_x, P.lw, &lox, &hix);
+    splat_candidates(Y, F.h, P, P.off_y, P.lh, &loy, &hiy);
+    for (int ly = hiy; ly >= loy; --ly)
+        for (int lx = hix; lx >= lox; --lx) {
+            uint32_t px, py;
+            if (li_active(F, P, (unsigned)lx, (unsigned)ly, &px, &py)) return (uint32_t)ly * P.lw + (uint32_t)lx;
+        }
+    return kNoOwner;
+}
+
+__device__ __forceinline__ bool tile_is_mine(const FrameDev& F, int X, int Y)
+{
+    if (!F.tile_owner) return true;
+    const int tx = X / F.tile_size, ty = Y / F.tile_size;
+    return F.tile_owner[ty * F.tiles_x + tx] == (uint8_t)F.rank;
+}
+
+// ------------------------------------------------------------------ k_owner_map
+// Each frame pixel is owned by exactly one (pass, launch index): the last pass that writes it
+// (passes overdraw in order, SimplePathtracer.cpp:137-209) and within it the row-major last writer.
+__global__ void k_owner_map(FrameDev F, uint32_t* __restrict__ owner_map, uint8_t* __restrict__ needed)
+{
+    const size_t npix = (size_t)F.w * F.h;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+        const int X = (int)(i % F.w), Y = (int)(i / F.w);
+        uint32_t own = kNoOwner;
+        if (tile_is_mine(F, X, Y)) {
+            for (int p = F.npass - 1; p >= 0; --p) {
+                const uint32_t li = pass_owner(F, F.pass[p], X, Y);
+                if (li != kNoOwner) { own = ((uint32_t)p << 28) | li; needed[F.pass[p].li_base + li] = 1; break; }
+            }
+        }
+        owner_map[i] = own;
+    }
+}
+
+// ------------------------------------------------------------------ camera
+struct CamRay { float3 dir; uint32_t px, py; };
+
+__device__ __forceinline__ float3 camera_dir(const FrameDev& F, uint32_t px, uint32_t py, float jx, float jy)
+{
+    const fx_vec3 U = {F.U[0], F.U[1], F.U[2]}, V = {F.V[0], F.V[1], F.V[2]}, W = {F.W[0], F.W[1], F.W[2]};
+    const fx_vec3 d = fx_camera_dir(px, py, jx, jy, F.w, F.h, U, V, W);                 // :483-491
+    return make_float3(d.x, d.y, d.z);
+}
+
+// ------------------------------------------------------------------ k_raygen
+// chunk = rows [row0,row1) of one pass.  One thread per (launch index, sample).
+__global__ void k_raygen(FrameDev F, int pass, unsigned row0, unsigned row1, unsigned chunk_pid_base,
+                         const uint8_t* __restrict__ needed, PathState ps, Queues q, float4* __restrict__ li_backplate,
+                         DevStats* __restrict__ stats)
+{
+    const PassDev P = F.pass[pass];
+    const size_t total = (size_t)(row1 - row0) * P.lw * P.spp;
+    unsigned long long started = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned k = (unsigned)(i % P.spp);
+        const size_t lloc = i / P.spp;
+        const unsigned lx = (unsigned)(lloc % P.lw), ly = row0 + (unsigned)(lloc / P.lw);
+        const uint32_t li = ly * P.lw + lx;
+        if (!needed[P.li_base + li]) continue;
+        uint32_t px, py;
+        fx_launch_to_pixel(lx, ly, P.factor, P.factor, P.uoff_x, P.uoff_y, &px, &py);
+        uint32_t seed = fx_tea4(ly * (unsigned)F.w + lx, P.subframe);                    // :411
+        seed = fx_seed_after(seed, k);
+        const fx_rng rng = fx_rng_init(seed);                                           // :464 (before the jitter draws)
+        const float jx = fx_rnd(&seed);                                                 // :479, x first
+        const float jy = fx_rnd(&seed);
+        const float3 dir = camera_dir(F, px, py, jx, jy);
+        const uint32_t pid = chunk_pid_base + (uint32_t)i;
+        ps.ray_o[pid] = make_float4(F.eye[0], F.eye[1], F.eye[2], 0.f);
+        ps.ray_d[pid] = make_float4(dir.x, dir.y, dir.z, 0.f);
+        ps.thr[pid] = make_float4(1.f, 1.f, 1.f, 1.f);                                   // throughput 1, rayEta 1 (:467-468)
+        ps.rng[pid] = make_uint2(rng.s1, rng.s2);
+        ps.direct[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ps.indirect[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ps.alpha[pid] = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
+        if (k == P.spp - 1) {                                                           // backplate of the LAST sample (:495)
+            const float4 bp = probe_eval(F.probe, probe_dir_to_uv(dir));
+            li_backplate[P.li_base + li] = bp;
+        }
+        q.cur[queue_push(&q.counts[0])] = pid;
+        ++started;
+    }
+    // block-level count of started samples
+    for (int o = 16; o > 0; o >>= 1) started += __shfl_xor_sync(0xffffffffu, started, o);
+    if ((threadIdx.x & 31) == 0 && started) atomicAdd(&stats->samples, started);
+}
+
+// ------------------------------------------------------------------ k_extend  (closest hit)
+__global__ void __launch_bounds__(128) k_extend(SceneDev S, PathState ps, Queues q, float tmin, float tmax, DevStats* __restrict__ stats)
+{
+    const uint32_t n = q.counts[0];
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats->radiance_rays, (unsigned long long)n);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t pid = q.cur[i];
+        const float4 o = ps.ray_o[pid], d = ps.ray_d[pid];
+        HitRec h;
+        const bool ok = trace_closest(S.bvh, make_float3(o.x, o.y, o.z), make_float3(d.x, d.y, d.z), tmin, tmax, h);
+        ps.hit[pid] = ok ? make_float4(h.t, h.u, h.v, __int_as_float((int)h.k)) : make_float4(0.f, 0.f, 0.f, __int_as_float((int)kNoHit));
+    }
+}
+
+// ------------------------------------------------------------------ k_shadow  (any hit, back faces culled)
+__global__ void __launch_bounds__(128) k_shadow(SceneDev S, PathState ps, Queues q, float tmin, float tmax, DevStats* __restrict__ stats)
+{
+    const uint32_t n = q.counts[2];
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats->shadow_rays, (unsigned long long)n);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t pid = q.shadow[i];
+        const float4 o = ps.ray_o[pid], d = ps.shw_d[pid];
+        const bool occluded = trace_any_front(S.bvh, make_float3(o.x, o.y, o.z), make_float3(d.x, d.y, d.z), tmin, tmax);
+        const float4 pe = ps.pend[pid];
+        const uint32_t mode = (uint32_t)__float_as_int(pe.w);
+        if ((mode & 1u) == 0u) {
+            if (!occluded) {                                   // SampleLights, :323-341
+                float4* dst = (mode & 2u) ? ps.direct : ps.indirect;
+                float4 a = dst[pid];
+                a.x += pe.x; a.y += pe.y; a.z += pe.z;
+                dst[pid] = a;
+            }
+        } else if (occluded) {                                 // SampleShadow on a shadow catcher, :367-384
+            float4 a = ps.alpha[pid];
+            a.x += pe.x; a.y += pe.y; a.z += pe.z;
+            ps.alpha[pid] = a;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ k_shade  (closest-hit / miss program)
+template <bool FAST>
+__global__ void __launch_bounds__(128) k_shade(FrameDev F, SceneDev S, PathState ps, Queues q)
+{
+    const uint32_t n = q.counts[0];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t pid = q.cur[i];
+        const float4 h4 = ps.hit[pid];
+        const uint32_t slot = (uint32_t)__float_as_int(h4.w);
+        if (slot == kNoHit) continue;                            // __miss__radiance: DONE, adds nothing (:253-282)
+        const float4 ro4 = ps.ray_o[pid], rd4 = ps.ray_d[pid];
+        const float3 ro = f3(ro4.x, ro4.y, ro4.z), rd = f3(rd4.x, rd4.y, rd4.z);
+        const float4* tp = S.bvh.tris + 3 * (size_t)slot;
+        const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
+        const uint32_t gid = (uint32_t)__float_as_int(ta.w);
+        // geometric normal, flipped toward the viewer (:632-634); e1,e2 are exactly v1-v0, v2-v0
+        const float3 n0 = unit3<FAST>(cross3(f3(tb.x, tb.y, tb.z), f3(tc.x, tc.y, tc.z)));
+        const float3 wo = -rd;
+        const float3 N = n0 * copysignf(1.0f, dot3(wo, n0));
+        const float3 P = ro + h4.x * rd;                         // :636-638
+        const uint32_t mesh = __ldg(&S.tri_mesh[gid]);
+        const MaterialBlob* M = S.materials + mesh;
+        const int mflags = __ldg(&M->flags);
+        float4 al = ps.alpha[pid];
+        uint32_t st = (uint32_t)__float_as_int(al.w);
+        const uint32_t depth = st & kDepthMask;
+        const bool secondary = (st & kFlagSecondary) != 0;
+        const bool catcher = (mflags & kMaterialShadowCatcher) != 0;
+        if (catcher && secondary) {                              // pass-through, --depth then ++depth (:646-651, :529)
+            ps.ray_o[pid] = make_float4(P.x, P.y, P.z, 0.f);
+            q.next[queue_push(&q.counts[1])] = pid;
+            continue;
+        }
+        BsdfParams bp;
+        bp.color = f3(__ldg(&M->color[0]), __ldg(&M->color[1]), __ldg(&M->color[2]));
+        bp.metallic = __ldg(&M->metallic); bp.subsurface = __ldg(&M->subsurface); bp.specular = __ldg(&M->specular);
+        bp.roughness = __ldg(&M->roughness); bp.specularTint = __ldg(&M->specularTint); bp.clearcoat = __ldg(&M->clearcoat);
+        bp.clearcoatGloss = __ldg(&M->clearcoatGloss); bp.transmission = __ldg(&M->transmission);
+        float3 albedo = bp.color;
+        const int2 mt = __ldg(&S.mesh_tex[mesh]);
+        if (mt.x >= 0 && mt.y) {                                 // :655-665
+            const uint32_t* vi = S.tri_vidx + 3 * (size_t)gid;
+            const float2 t0 = __ldg(&S.texcoords[vi[0]]), t1 = __ldg(&S.texcoords[vi[1]]), t2 = __ldg(&S.texcoords[vi[2]]);
+            const float u = h4.y, v = h4.z, w0 = 1.f - u - v;
+            const int4 ti = __ldg(&S.tex_info[mt.x]);
+            albedo = texture_bilinear(S.texels + ti.x, ti.y, ti.z, w0 * t0.x + u * t1.x + v * t2.x, w0 * t0.y + u * t1.y + v * t2.y);
+        }
+        const float4 th4 = ps.thr[pid];
+        float3 T = f3(th4.x, th4.y, th4.z);
+        float ray_eta = th4.w;
+        float out_eta = 1.0f;                                    // :673-683
+        if (ray_eta == 1.0f) {
+            const float eta = __ldg(&M->eta);
+            out_eta = eta == 0.f ? 2.f / (1.f - sqrtf(0.08f * bp.specular)) - 1.f : eta;
+        }
+        const uint2 r2 = ps.rng[pid];
+        fx_rng rng; rng.s1 = r2.x; rng.s2 = r2.y;
+
+        // next-event estimation: one probe sample, balance heuristic (:303-344 / :347-387)
+        float3 wi, sky; float sky_pdf;
+        probe_sample<FAST>(F.probe, rng, wi, sky, sky_pdf);
+        float3 pending = f3(0.f);
+        {
+            const float pdfb = bsdf_pdf<FAST>(bp, ray_eta, out_eta, N, wo, wi);
+            if (pdfb > 0.f) {
+                const float wgt = 0.5f * sky_pdf / (0.5f * pdfb + 0.5f * sky_pdf);
+                if (wgt > 0.f) {
+                    const float3 f = bsdf_eval<FAST>(bp, albedo, ray_eta, out_eta, N, wo, wi);
+                    pending = T * ((wgt * sky * f * fabsf(dot3(wi, N))) * Mth<FAST>::rcp(sky_pdf));
+                }
+            }
+        }
+        if (!catcher) { al.x = al.y = al.z = 1.0f; st |= kFlagAlphaOne; }   // :689
+        float3 E = f3(0.f);
+        if (!secondary) E = f3(__ldg(&M->emission[0]), __ldg(&M->emission[1]), __ldg(&M->emission[2]));   // :696-698
+
+        float3 tu, tv, L = f3(0.f);
+        tangent_frame<FAST>(N, tu, tv);
+        const float pdf = bsdf_sample<FAST>(bp, ray_eta, out_eta, tu, tv, N, wo, rng, L);
+        const bool done = !(pdf > 0.f);                          // :708-711
+        const bool commit = !done && (int)depth < F.max_depth;   // radiance of this segment counts (:515-527)
+        if (!done) {
+            const float3 f = bsdf_eval<FAST>(bp, albedo, ray_eta, out_eta, N, wo, L);
+            if (dot3(L, N) <= 0.f) ray_eta = out_eta;            // :717-721
+            T = T * ((f * fabsf(dot3(N, L))) * Mth<FAST>::rcp(pdf));   // :724
+        }
+        const bool has_pending = pending.x != 0.f || pending.y != 0.f || pending.z != 0.f;
+        const bool shadow = catcher ? has_pending : (commit && has_pending);
+        // !secondary implies depth == 0 (depth only advances together with the secondary flag), so the
+        // emission term lands in directLight exactly once; the NEE term is added by k_shadow.
+        if (commit && depth == 0) ps.direct[pid] = make_float4(E.x, E.y, E.z, 0.f);
+        if (shadow || commit) ps.ray_o[pid] = make_float4(P.x, P.y, P.z, 0.f);
+        if (shadow) {
+            ps.shw_d[pid] = make_float4(wi.x, wi.y, wi.z, 0.f);
+            const uint32_t mode = (catcher ? 1u : 0u) | (depth == 0 ? 2u : 0u);
+            ps.pend[pid] = make_float4(pending.x, pending.y, pending.z, __int_as_float((int)mode));
+            q.shadow[queue_push(&q.counts[2])] = pid;
+        }
+        bool cont = commit;
+        if (commit) {
+            st = (st & ~kDepthMask) | ((depth + 1) & kDepthMask) | kFlagSecondary;
+            // the (max_depth+1)-th segment only ever sets alpha; skip it when alpha is already 1
+            if (F.skip_wasted && (int)(depth + 1) >= F.max_depth && (st & kFlagAlphaOne) && !S.any_catcher) cont = false;
+        }
+        al.w = __int_as_float((int)st);
+        ps.alpha[pid] = al;
+        if (cont) {
+            ps.ray_d[pid] = make_float4(L.x, L.y, L.z, 0.f);
+            ps.thr[pid] = make_float4(T.x, T.y, T.z, ray_eta);
+            ps.rng[pid] = make_uint2(rng.s1, rng.s2);
+            q.next[queue_push(&q.counts[1])] = pid;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ k_resolve_li
+// per launch index: sum its spp samples in order, apply the backplate/alpha composite (:536-560)
+__global__ void k_resolve_li(FrameDev F, int pass, unsigned row0, unsigned row1, unsigned chunk_pid_base,
+                             const uint8_t* __restrict__ needed, PathState ps, const float4* __restrict__ li_backplate,
+                             float4* __restrict__ li_color)
+{
+    const PassDev P = F.pass[pass];
+    const size_t total = (size_t)(row1 - row0) * P.lw;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t li = row0 * P.lw + (uint32_t)i;
+        if (!needed[P.li_base + li]) continue;
+        float3 result = f3(0.f), alpha = f3(0.f);
+        const uint32_t pid0 = chunk_pid_base + (uint32_t)i * P.spp;
+        for (unsigned k = 0; k < P.spp; ++k) {
+            const float4 d = ps.direct[pid0 + k], in = ps.indirect[pid0 + k], a = ps.alpha[pid0 + k];
+            result = result + (f3(d.x, d.y, d.z) + f3(in.x, in.y, in.z));
+            alpha = alpha + f3(a.x, a.y, a.z);
+        }
+        const float sppf = (float)P.spp;
+        const float inv = 1.0f / sppf;
+        alpha = alpha * inv;
+        const float4 bp = li_backplate[P.li_base + li];
+        const float3 color = (f3(bp.x, bp.y, bp.z) * sppf) * (f3(1.f) - alpha) + result;
+        const float3 acc = color * inv;
+        li_color[P.li_base + li] = make_float4(acc.x, acc.y, acc.z, 1.0f);
+    }
+}
+
+// ------------------------------------------------------------------ k_resolve_px
+// per owned pixel: fetch its owner's colour, optional accumulation lerp, exposure + Reinhard + sRGB8 (:558-600)
+template <bool FAST>
+__global__ void k_resolve_px(FrameDev F, const uint32_t* __restrict__ owner_map, const float4* __restrict__ li_color)
+{
+    const size_t npix = (size_t)F.w * F.h;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t own = owner_map[i];
+        if (own == kNoOwner) continue;
+        const PassDev& P = F.pass[own >> 28];
+        const float4 c = li_color[P.li_base + (own & 0x0fffffffu)];
+        float3 acc = f3(c.x, c.y, c.z);
+        if (F.accumulate && P.subframe > 0 && !P.redraw) {       // PT_sv4_vmv2/deviceProgram.cu:545-553
+            acc = f3(fmaxf(0.f, fminf(acc.x, 10.f)), fmaxf(0.f, fminf(acc.y, 10.f)), fmaxf(0.f, fminf(acc.z, 10.f)));
+            const float a = 1.0f / (float)(P.subframe + 1);
+            const float4 prev = F.accum[i];
+            acc = mix3(f3(prev.x, prev.y, prev.z), acc, a);
+        }
+        F.accum[i] = make_float4(acc.x, acc.y, acc.z, 1.0f);
+        F.frame[i] = tonemap_rgba8<FAST>(acc, F.exposure);
+    }
+}
+
+// ------------------------------------------------------------------ debug / query kernels
+__global__ void k_primary_hits(FrameDev F, SceneDev S, int32_t* __restrict__ tri, float* __restrict__ tuv, float* __restrict__ dir)
+{
+    const PassDev P = F.pass[0];
+    const size_t total = (size_t)P.lw * P.lh;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const unsigned lx = (unsigned)(i % P.lw), ly = (unsigned)(i / P.lw);
+        uint32_t px, py;
+        if (!li_active(F, P, lx, ly, &px, &py)) { tri[i] = -2; continue; }
+        uint32_t seed = fx_tea4(ly * (unsigned)F.w + lx, P.subframe);
+        const float jx = fx_rnd(&seed), jy = fx_rnd(&seed);
+        const float3 d = camera_dir(F, px, py, jx, jy);
+        HitRec h;
+        const bool ok = trace_closest(S.bvh, make_float3(F.eye[0], F.eye[1], F.eye[2]), d, F.tmin, F.tmax, h);
+        tri[i] = ok ? (int32_t)h.gid : -1;
+        tuv[3 * i] = ok ? h.t : 0.f; tuv[3 * i + 1] = ok ? h.u : 0.f; tuv[3 * i + 2] = ok ? h.v : 0.f;
+        dir[3 * i] = d.x; dir[3 * i + 1] = d.y; dir[3 * i + 2] = d.z;
+    }
+}
+
+__global__ void k_trace_query(SceneDev S, const float* __restrict__ rays, size_t n, int mode, int32_t* __restrict__ tri, float* __restrict__ tuv)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float* r = rays + 8 * i;
+        const float3 o = make_float3(r[0], r[1], r[2]), d = make_float3(r[4], r[5], r[6]);
+        if (mode == 0) {
+            HitRec h;
+            const bool ok = trace_closest(S.bvh, o, d, r[3], r[7], h);
+            tri[i] = ok ? (int32_t)h.gid : -1;
+            tuv[3 * i] = ok ? h.t : 0.f; tuv[3 * i + 1] = ok ? h.u : 0.f; tuv[3 * i + 2] = ok ? h.v : 0.f;
+        } else {
+            tri[i] = trace_any_front(S.bvh, o, d, r[3], r[7]) ? 1 : 0;
+        }
+    }
+}
+
+__global__ void k_swap_counts(uint32_t* counts)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) { counts[0] = counts[1]; counts[1] = 0; counts[2] = 0; }
+}
+
+// ------------------------------------------------------------------ launch wrappers (host)
+void launch_owner_map(const LaunchCfg& L, const FrameDev& F, uint32_t* owner_map, uint8_t* needed)
+{
+    k_owner_map<<<L.grid_light, 256, 0, L.stream>>>(F, owner_map, needed);
+}
+void launch_raygen(const LaunchCfg& L, const FrameDev& F, int pass, unsigned row0, unsigned row1, unsigned pid_base,
+                   const uint8_t* needed, const PathState& ps, const Queues& q, float4* li_backplate, DevStats* stats)
+{
+    k_raygen<<<L.grid_light, 256, 0, L.stream>>>(F, pass, row0, row1, pid_base, needed, ps, q, li_backplate, stats);
+}
+void launch_extend(const LaunchCfg& L, const SceneDev& S, const PathState& ps, const Queues& q, float tmin, float tmax, DevStats* stats)
+{
+    k_extend<<<L.grid_trace, 128, 0, L.stream>>>(S, ps, q, tmin, tmax, stats);
+}
+void launch_shadow(const LaunchCfg& L, const SceneDev& S, const PathState& ps, const Queues& q, float tmin, float tmax, DevStats* stats)
+{
+    k_shadow<<<L.grid_trace, 128, 0, L.stream>>>(S, ps, q, tmin, tmax, stats);
+}
+void launch_shade(const LaunchCfg& L, const FrameDev& F, const SceneDev& S, const PathState& ps, const Queues& q, bool fast)
+{
+    if (fast) k_shade<true><<<L.grid_shade, 128, 0, L.stream>>>(F, S, ps, q);
+    else k_shade<false><<<L.grid_shade, 128, 0, L.stream>>>(F, S, ps, q);
+}
+void launch_swap(const LaunchCfg& L, uint32_t* counts) { k_swap_counts<<<1, 32, 0, L.stream>>>(counts); }
+void launch_resolve_li(const LaunchCfg& L, const FrameDev& F, int pass, unsigned row0, unsigned row1, unsigned pid_base,
+                       const uint8_t* needed, const PathState& ps, const float4* li_backplate, float4* li_color)
+{
+    k_resolve_li<<<L.grid_light, 256, 0, L.stream>>>(F, pass, row0, row1, pid_base, needed, ps, li_backplate, li_color);
+}
+void launch_resolve_px(const LaunchCfg& L, const FrameDev& F, const uint32_t* owner_map, const float4* li_color, bool fast)
+{
+    if (fast) k_resolve_px<true><<<L.grid_light, 256, 0, L.stream>>>(F, owner_map, li_color);
+    else k_resolve_px<false><<<L.grid_light, 256, 0, L.stream>>>(F, owner_map, li_color);
+}
+void launch_primary_hits(const LaunchCfg& L, const FrameDev& F, const SceneDev& S, int32_t* tri, float* tuv, float* dir)
+{
+    k_primary_hits<<<L.grid_trace, 128, 0, L.stream>>>(F, S, tri, tuv, dir);
+}
+void launch_trace_query(const LaunchCfg& L, const SceneDev& S, const float* rays, size_t n, int mode, int32_t* tri, float* tuv)
+{
+    k_trace_query<<<L.grid_trace, 128, 0, L.stream>>>(S, rays, n, mode, tri, tuv);
+}
+
+void query_occupancy(int* extend_blocks_per_sm, int* shade_blocks_per_sm)
+{
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(extend_blocks_per_sm, k_extend, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(shade_blocks_per_sm, k_shade<false>, 128, 0);
+}
+
+}  // namespace fovpt

@@ -1,0 +1,89 @@
+// wavefront.cuh -- device-side data model of the wavefront path tracer (kernels: wavefront.cu).
+//
+// One camera path ("sample", one iteration of reference deviceProgram.cu:448-539) owns slot `pid`
+// in a set of SoA arrays; queues of pids connect the stages:
+//
+//   k_owner_map -> k_raygen -> [ k_extend -> k_shade -> k_shadow ] x (max_depth+1) -> k_resolve_li -> k_resolve_px
+//
+// pid = pass.pid_base + li * pass.spp + k, with li the row-major launch index of the pass
+// (optixGetLaunchIndex) and k the sample number, so the spp samples of one launch index are
+// adjacent and can be summed in the reference's order by k_resolve_li.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "bvh.cuh"
+#include "fovpt_layout.h"
+
+namespace fovpt {
+
+constexpr uint32_t kNoHit = 0xffffffffu;
+constexpr uint32_t kNoOwner = 0xffffffffu;
+constexpr int kMaxPasses = 3;
+
+// path flag bits (stored as int bits in alpha.w)
+constexpr uint32_t kFlagSecondary = 1u << 8;   // RAY_STATE_FLAGS_SECONDARY_RAY
+constexpr uint32_t kFlagAlphaOne = 1u << 9;    // prd.alpha was set to 1 by a non-catcher hit
+constexpr uint32_t kDepthMask = 0xffu;
+
+struct PathState {              // SoA, capacity = paths of the largest batch
+    float4* ray_o;              // origin.xyz
+    float4* ray_d;              // direction.xyz
+    float4* hit;                // t, u, v, bits(sorted triangle slot | kNoHit)
+    float4* thr;                // pathThroughput.xyz, rayEta
+    uint2*  rng;                // Random state (maths.h:170-227)
+    float4* direct;             // directLight.xyz
+    float4* indirect;           // indirectLight.xyz
+    float4* alpha;              // alpha.xyz, bits(depth | flags)
+    float4* shw_d;              // NEE direction.xyz
+    float4* pend;               // throughput * NEE value, bits(mode): bit0 catcher (add to alpha when occluded), bit1 primary
+};
+
+struct SceneDev {
+    DeviceBvh           bvh;
+    const uint32_t*     tri_mesh;     // global triangle id -> mesh id
+    const uint32_t*     tri_vidx;     // 3 global vertex indices per global triangle
+    const float2*       texcoords;    // per global vertex (zero where the mesh has none)
+    const MaterialBlob* materials;    // per mesh
+    const int2*         mesh_tex;     // per mesh: (texture id or -1, has texcoords)
+    const int4*         tex_info;     // per texture: (texel offset, w, h, 0)
+    const uint32_t*     texels;
+    int                 any_catcher;
+};
+
+struct PassDev {
+    unsigned lw, lh, factor, fill, spp, redraw, subframe;
+    int      off_x, off_y;            // offset as a signed number (uint2 offset wraps)
+    unsigned uoff_x, uoff_y;          // the same offset, raw
+    float    r_inner, r_outer;
+    unsigned pid_base, li_base;
+};
+
+struct FrameDev {
+    int       w, h;
+    unsigned  cx, cy;
+    float     eye[3], U[3], V[3], W[3];
+    ProbeBlob probe;
+    float4*   accum;
+    uint32_t* frame;
+    int       npass;
+    PassDev   pass[kMaxPasses];
+    // config
+    int   max_depth;
+    float tmin, tmax, exposure;
+    int   accumulate, skip_wasted;
+    // partition
+    const uint8_t* tile_owner;
+    int   tile_size, tiles_x, tiles_y, rank;
+};
+
+struct Queues {
+    uint32_t* cur;
+    uint32_t* next;
+    uint32_t* shadow;
+    uint32_t* counts;   // [0] cur [1] next [2] shadow
+};
+
+struct DevStats { unsigned long long samples, radiance_rays, shadow_rays; };
+
+}  // namespace fovpt

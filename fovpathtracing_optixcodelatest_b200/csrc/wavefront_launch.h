@@ -1,0 +1,32 @@
+// wavefront_launch.h -- host-callable wrappers around the kernels of wavefront.cu.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "wavefront.cuh"
+
+namespace fovpt {
+
+struct LaunchCfg {
+    cudaStream_t stream;
+    int grid_trace;   // persistent grid of the traversal kernels  (SMs x resident CTAs)
+    int grid_shade;   // persistent grid of the shading kernel
+    int grid_light;   // grid of the light-weight per-pixel / per-launch-index kernels
+};
+
+void launch_owner_map(const LaunchCfg&, const FrameDev&, uint32_t* owner_map, uint8_t* needed);
+void launch_raygen(const LaunchCfg&, const FrameDev&, int pass, unsigned row0, unsigned row1, unsigned pid_base,
+                   const uint8_t* needed, const PathState&, const Queues&, float4* li_backplate, DevStats*);
+void launch_extend(const LaunchCfg&, const SceneDev&, const PathState&, const Queues&, float tmin, float tmax, DevStats*);
+void launch_shadow(const LaunchCfg&, const SceneDev&, const PathState&, const Queues&, float tmin, float tmax, DevStats*);
+void launch_shade(const LaunchCfg&, const FrameDev&, const SceneDev&, const PathState&, const Queues&, bool fast);
+void launch_swap(const LaunchCfg&, uint32_t* counts);
+void launch_resolve_li(const LaunchCfg&, const FrameDev&, int pass, unsigned row0, unsigned row1, unsigned pid_base,
+                       const uint8_t* needed, const PathState&, const float4* li_backplate, float4* li_color);
+void launch_resolve_px(const LaunchCfg&, const FrameDev&, const uint32_t* owner_map, const float4* li_color, bool fast);
+void launch_primary_hits(const LaunchCfg&, const FrameDev&, const SceneDev&, int32_t* tri, float* tuv, float* dir);
+void launch_trace_query(const LaunchCfg&, const SceneDev&, const float* rays, size_t n, int mode, int32_t* tri, float* tuv);
+void query_occupancy(int* extend_blocks_per_sm, int* shade_blocks_per_sm);
+
+}  // namespace fovpt

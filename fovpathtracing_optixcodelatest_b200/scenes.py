@@ -109,7 +109,7 @@ def _block(p0, p1, p2, p3, height):
 
 
 def cornell_box(disney_half=True) -> Scene:
-    """Cornell box in the classic 555-unit frame.  9 meshes, 36 triangles.
+    """Cornell box in the classic 555-unit frame.  9 meshes, 34 triangles.
 
     ``disney_half``: odd meshes keep the reference's default Disney ``Material()`` parameters
     (only Kd/Ke overwritten, exactly what ``loadOBJ`` does, Model.cpp:190-191); even meshes are the
@@ -222,3 +222,213 @@ def checker_texture(size=256, a=(200, 190, 170), b=(120, 95, 80), cells=8, seed=
         out |= ch << (8 * c)
     out |= np.uint32(255) << 24
     return out
+
+
+# ----------------------------------------------------------------------------- procedural meshes
+
+def _grid(origin, du, dv, nu, nv, disp=None, uv_scale=(1.0, 1.0)):
+    """(nu x nv) quads spanning origin + s*du + t*dv, s,t in [0,1]; optional displacement along the
+    normal disp(s,t).  Triangles are counter-clockwise seen from the side cross(du,dv) points to."""
+    o = np.asarray(origin, np.float64); du = np.asarray(du, np.float64); dv = np.asarray(dv, np.float64)
+    s = np.linspace(0.0, 1.0, nu + 1); t = np.linspace(0.0, 1.0, nv + 1)
+    S, T = np.meshgrid(s, t, indexing="xy")
+    P = o[None, None, :] + S[..., None] * du + T[..., None] * dv
+    if disp is not None:
+        n = np.cross(du, dv); n = n / np.linalg.norm(n)
+        P = P + disp(S, T)[..., None] * n
+    vtx = P.reshape(-1, 3).astype(np.float32)
+    tc = np.stack([S * uv_scale[0], T * uv_scale[1]], -1).reshape(-1, 2).astype(np.float32)
+    ii, jj = np.meshgrid(np.arange(nu), np.arange(nv), indexing="xy")
+    a = (jj * (nu + 1) + ii).reshape(-1); b = a + 1; c = a + (nu + 1) + 1; d = a + (nu + 1)
+    idx = np.concatenate([np.stack([a, b, c], 1), np.stack([a, c, d], 1)]).astype(np.uint32)
+    return vtx, idx, tc
+
+
+def _lathe(profile_r, profile_y, center, nseg, uv_scale=(4.0, 4.0)):
+    """surface of revolution around +y through `center`; profile from bottom to top; outward normals."""
+    r = np.asarray(profile_r, np.float64); y = np.asarray(profile_y, np.float64)
+    ang = np.linspace(0.0, 2 * math.pi, nseg + 1)
+    A, R = np.meshgrid(ang, r, indexing="xy")
+    Y = np.broadcast_to(y[:, None], A.shape)
+    P = np.stack([center[0] + R * np.cos(A), center[1] + Y, center[2] - R * np.sin(A)], -1)
+    vtx = P.reshape(-1, 3).astype(np.float32)
+    nr = len(r) - 1
+    S = A / (2 * math.pi); T = np.broadcast_to(np.linspace(0, 1, len(r))[:, None], A.shape)
+    tc = np.stack([S * uv_scale[0], T * uv_scale[1]], -1).reshape(-1, 2).astype(np.float32)
+    ii, jj = np.meshgrid(np.arange(nseg), np.arange(nr), indexing="xy")
+    a = (jj * (nseg + 1) + ii).reshape(-1); b = a + 1; c = a + (nseg + 1) + 1; d = a + (nseg + 1)
+    idx = np.concatenate([np.stack([a, b, c], 1), np.stack([a, c, d], 1)]).astype(np.uint32)
+    return vtx, idx, tc
+
+
+def _icosphere(level):
+    t = (1.0 + 5 ** 0.5) / 2
+    v = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t), (0, 1, -t),
+         (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]
+    f = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6), (7, 1, 8),
+         (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10), (8, 6, 7), (9, 8, 1)]
+    v = np.array(v, np.float64); v /= np.linalg.norm(v, axis=1, keepdims=True)
+    f = np.array(f, np.int64)
+    for _ in range(level):
+        edges = np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]])
+        key = np.sort(edges, axis=1)
+        uniq, inv = np.unique(key, axis=0, return_inverse=True)
+        mid = v[uniq[:, 0]] + v[uniq[:, 1]]; mid /= np.linalg.norm(mid, axis=1, keepdims=True)
+        base = len(v); v = np.concatenate([v, mid])
+        n = len(f); m01 = base + inv[:n]; m12 = base + inv[n:2 * n]; m20 = base + inv[2 * n:]
+        f = np.concatenate([np.stack([f[:, 0], m01, m20], 1), np.stack([f[:, 1], m12, m01], 1),
+                            np.stack([f[:, 2], m20, m12], 1), np.stack([m01, m12, m20], 1)])
+    return v, f
+
+
+def _value_noise3(p, seed, freq):
+    """cheap deterministic lattice noise in [-1,1] evaluated at points p (n,3)."""
+    q = p * freq
+    i = np.floor(q).astype(np.int64); fr = q - i
+    fr = fr * fr * (3 - 2 * fr)
+
+    def h(ix, iy, iz):
+        n = (ix * 73856093) ^ (iy * 19349663) ^ (iz * 83492791) ^ (seed * 2654435761)
+        n = (n ^ (n >> 13)) * 1274126177
+        return ((n ^ (n >> 16)) & 0xffff) / 32767.5 - 1.0
+
+    out = 0.0
+    for dx in (0, 1):
+        for dy in (0, 1):
+            for dz in (0, 1):
+                w = (fr[:, 0] if dx else 1 - fr[:, 0]) * (fr[:, 1] if dy else 1 - fr[:, 1]) * (fr[:, 2] if dz else 1 - fr[:, 2])
+                out = out + w * h(i[:, 0] + dx, i[:, 1] + dy, i[:, 2] + dz)
+    return out
+
+
+def _disney(color, **kw):
+    m = Material.default()        # what loadOBJ leaves: reference defaults + Kd, Ke = 0
+    m.color.set(color); m.emission.set((0.0, 0.0, 0.0))
+    for k, v in kw.items():
+        setattr(m, k, v)
+    return m
+
+
+def atrium(seed=1, detail=1.0) -> Scene:
+    """Procedural "Sponza-class" atrium (C3/C4): a two-storey colonnaded hall with an open roof,
+    arches, galleries, hanging drapes, vases and a displaced sculpture; ~262k triangles at detail=1.
+    Extents follow Crytek Sponza (x in [-1900,1800], y in [0,1500], z in [-1100,1100]) so that the
+    reference camera preset (main.cpp:240-254) stands inside the hall looking down its long axis."""
+    rng = np.random.default_rng(seed)
+    sc = Scene(name="atrium")
+    sc.textures.append(checker_texture(256, (205, 190, 165), (150, 128, 105), 16, seed))      # 0 stone tiles
+    sc.textures.append(checker_texture(256, (190, 170, 150), (170, 150, 128), 32, seed + 1))  # 1 brick
+    x0, x1, z0, z1, H = -1900.0, 1800.0, -1100.0, 1100.0, 1500.0
+    D = lambda n: max(2, int(round(n * detail)))
+
+    def add(name, v, i, mat, tc=None, tex=-1):
+        sc.meshes.append(Mesh(name, np.asarray(v, np.float32), np.asarray(i, np.uint32), mat,
+                              None if tc is None else np.asarray(tc, np.float32), tex))
+
+    stone = _disney((0.78, 0.74, 0.66))
+    brick = _disney((0.72, 0.66, 0.58), roughness=0.9)
+    # floor: tiles with shallow grout relief, normal +y
+    v, i, tc = _grid((x0, 0, z1), (x1 - x0, 0, 0), (0, 0, z0 - z1), D(180), D(108),
+                     lambda S, T: 2.0 * np.cos(S * 2 * math.pi * 42) * np.cos(T * 2 * math.pi * 25), (21.0, 12.5))
+    add("floor", v, i, stone, tc, 0)
+    # four walls, normals pointing inward, brick relief
+    relief = lambda S, T: 3.0 * np.sin(S * 2 * math.pi * 60) * np.sin(T * 2 * math.pi * 30)
+    v, i, tc = _grid((x0, 0, z0), (x1 - x0, 0, 0), (0, H, 0), D(112), D(44), relief, (24.0, 10.0)); add("wall_north", v, i, brick, tc, 1)
+    v, i, tc = _grid((x1, 0, z1), (x0 - x1, 0, 0), (0, H, 0), D(112), D(44), relief, (24.0, 10.0)); add("wall_south", v, i, brick, tc, 1)
+    v, i, tc = _grid((x0, 0, z1), (0, 0, z0 - z1), (0, H, 0), D(72), D(44), relief, (14.0, 10.0)); add("wall_west", v, i, brick, tc, 1)
+    v, i, tc = _grid((x1, 0, z0), (0, 0, z1 - z0), (0, H, 0), D(72), D(44), relief, (14.0, 10.0)); add("wall_east", v, i, brick, tc, 1)
+    # colonnades: two rows, two storeys
+    col_x = np.linspace(x0 + 250.0, x1 - 250.0, 10)
+    storeys = ((0.0, 620.0), (680.0, 1250.0))
+    for si, (yb, yt) in enumerate(storeys):
+        hgt = yt - yb
+        prof_t = np.linspace(0.0, 1.0, D(26))
+        base_r = 58.0 - 6.0 * si
+        # entasis + base + capital flare + fluting handled by radial ripple
+        prof_r = base_r * (1.0 - 0.12 * prof_t) + 22.0 * np.exp(-((prof_t - 0.0) / 0.05) ** 2) + 26.0 * np.exp(-((prof_t - 1.0) / 0.06) ** 2)
+        for zi, zc in enumerate((-430.0, 430.0)):
+            for ci, xc in enumerate(col_x):
+                v, i, tc = _lathe(prof_r, prof_t * hgt, (xc, yb, zc), D(30))
+                ang = np.arctan2(-(v[:, 2] - zc), v[:, 0] - xc)
+                ripple = 1.0 + 0.03 * np.cos(ang * 12)
+                v[:, 0] = xc + (v[:, 0] - xc) * ripple; v[:, 2] = zc + (v[:, 2] - zc) * ripple
+                hue = 0.70 + 0.08 * rng.random()
+                add(f"column_{si}_{zi}_{ci}", v, i, _disney((hue, hue * 0.96, hue * 0.88)), tc, -1)
+        # arches between neighbouring columns: half tori in the x-y plane
+        for zi, zc in enumerate((-430.0, 430.0)):
+            parts = []
+            for ci in range(len(col_x) - 1):
+                xa, xb = col_x[ci], col_x[ci + 1]
+                R = 0.5 * (xb - xa) - 40.0; rr = 34.0
+                nu, nv = D(24), D(14)
+                u = np.linspace(0.0, math.pi, nu + 1); w = np.linspace(0.0, 2 * math.pi, nv + 1)
+                Uu, Ww = np.meshgrid(u, w, indexing="xy")
+                cx_ = 0.5 * (xa + xb); cy_ = yt - R * 0.55
+                X = cx_ - (R + rr * np.cos(Ww)) * np.cos(Uu)
+                Y = cy_ + (R + rr * np.cos(Ww)) * np.sin(Uu) * 0.55
+                Z = zc + rr * np.sin(Ww)
+                P = np.stack([X, Y, Z], -1).reshape(-1, 3)
+                ii, jj = np.meshgrid(np.arange(nu), np.arange(nv), indexing="xy")
+                a = (jj * (nu + 1) + ii).reshape(-1); b = a + 1; c = a + (nu + 1) + 1; d = a + (nu + 1)
+                parts.append((P, np.concatenate([np.stack([a, b, c], 1), np.stack([a, c, d], 1)])))
+            v, i = _merge(parts)
+            add(f"arches_{si}_{zi}", v, i, _disney((0.80, 0.76, 0.68)))
+    # gallery slabs (upper floor) between colonnade and wall, top and underside
+    for zi, (za, zb) in enumerate(((z0, -380.0), (380.0, z1))):
+        v, i, tc = _grid((x0, 650.0, zb), (x1 - x0, 0, 0), (0, 0, za - zb), D(128), D(16), None, (20.0, 4.0)); add(f"gallery_top_{zi}", v, i, stone, tc, 0)
+        v, i, tc = _grid((x0, 620.0, za), (x1 - x0, 0, 0), (0, 0, zb - za), D(128), D(16), None, (20.0, 4.0)); add(f"gallery_bottom_{zi}", v, i, stone, tc, 0)
+        # roof over the gallery (normal down), the nave stays open to the sky
+        v, i, tc = _grid((x0, 1290.0, za), (x1 - x0, 0, 0), (0, 0, zb - za), D(96), D(14), None, (20.0, 4.0)); add(f"roof_{zi}", v, i, _disney((0.55, 0.42, 0.33)), tc, -1)
+    # hanging drapes across the nave, folded cloth; two-sided by construction (single sheet)
+    cloth = ((0.75, 0.08, 0.06), (0.10, 0.45, 0.14), (0.12, 0.16, 0.62), (0.78, 0.62, 0.10), (0.55, 0.10, 0.45), (0.85, 0.85, 0.80))
+    for k, xc in enumerate(np.linspace(x0 + 600.0, x1 - 500.0, 6)):
+        ph = rng.random() * 6.28
+        fold = lambda S, T, ph=ph: 38.0 * np.sin(S * 2 * math.pi * 9 + ph) * (0.35 + 0.65 * T) + 25.0 * np.sin(T * 7.0 + ph)
+        v, i, tc = _grid((xc, 1180.0, -330.0), (0, 0, 660.0), (0, -520.0, 0), D(66), D(62), fold, (6.0, 6.0))
+        add(f"drape_{k}", v, i, _disney(cloth[k % len(cloth)], roughness=0.8, metallic=0.1, transmission=0.0), tc, -1)
+    # vases along the nave (smooth metallic / clearcoat materials)
+    vt = np.linspace(0.0, 1.0, D(34))
+    vr = 30.0 + 55.0 * np.sin(vt * math.pi) ** 1.5 * (1.0 - 0.45 * vt) + 18.0 * np.exp(-((vt - 1.0) / 0.08) ** 2)
+    for k, xc in enumerate(np.linspace(x0 + 450.0, x1 - 450.0, 8)):
+        zc = -250.0 if k % 2 == 0 else 250.0
+        v, i, tc = _lathe(vr, vt * 190.0, (xc, 0.0, zc), D(30))
+        m = _disney((0.25 + 0.5 * rng.random(), 0.3 + 0.4 * rng.random(), 0.3 + 0.5 * rng.random()),
+                    roughness=0.25 + 0.3 * rng.random(), metallic=0.8 if k % 3 == 0 else 0.2, clearcoat=1.0 if k % 3 == 1 else 0.0,
+                    transmission=0.0 if k % 4 else 0.9)
+        add(f"vase_{k}", v, i, m, tc, -1)
+    # sculpture at the far end: displaced icosphere on a plinth
+    lvl = 5 if detail >= 0.99 else max(2, int(round(5 + math.log2(max(detail, 1e-3)))))
+    sv, sf = _icosphere(lvl)
+    disp = 1.0 + 0.22 * _value_noise3(sv, seed, 2.3) + 0.08 * _value_noise3(sv, seed + 7, 6.1)
+    sv = sv * disp[:, None] * 170.0 + np.array([1250.0, 330.0, 0.0])
+    add("sculpture", sv, sf, _disney((0.82, 0.78, 0.70), roughness=0.55))
+    parts = [_quad((1130, 160, 120), (1370, 160, 120), (1370, 160, -120), (1130, 160, -120))]
+    for (ax, az), (bx, bz) in (((1130, 120), (1370, 120)), ((1370, 120), (1370, -120)), ((1370, -120), (1130, -120)), ((1130, -120), (1130, 120))):
+        parts.append(_quad((ax, 0, az), (bx, 0, bz), (bx, 160, bz), (ax, 160, az)))
+    v, i = _merge(parts)
+    add("plinth", v, i, stone)
+    return sc
+
+
+def displaced_grid(n_tris=10_000_000, seed=3, extent=4000.0) -> Scene:
+    """C5: one height-field mesh with ~n_tris triangles (fractal sine terrain), split into bands so
+    that no single mesh is absurdly large; deterministic."""
+    n = int(math.ceil(math.sqrt(n_tris / 2.0)))
+    rng = np.random.default_rng(seed)
+    ph = rng.random(8) * 6.28
+    sc = Scene(name=f"grid{n_tris}")
+    bands = max(1, n // 512)
+    rows = np.linspace(0, n, bands + 1).astype(int)
+    for b in range(bands):
+        r0, r1 = rows[b], rows[b + 1]
+        s = np.linspace(0.0, 1.0, n + 1, dtype=np.float64); t = np.linspace(r0 / n, r1 / n, r1 - r0 + 1, dtype=np.float64)
+        S, T = np.meshgrid(s, t, indexing="xy")
+        Hh = sum((180.0 / (k + 1)) * np.sin(S * (k + 1) * 9.0 + ph[k]) * np.cos(T * (k + 1) * 7.0 + ph[(k + 3) % 8]) for k in range(5))
+        P = np.stack([(S - 0.5) * extent, Hh, (0.5 - T) * extent], -1).reshape(-1, 3).astype(np.float32)
+        nu, nv = n, r1 - r0
+        ii, jj = np.meshgrid(np.arange(nu), np.arange(nv), indexing="xy")
+        a = (jj * (nu + 1) + ii).reshape(-1); bb = a + 1; c = a + (nu + 1) + 1; d = a + (nu + 1)
+        idx = np.concatenate([np.stack([a, bb, c], 1), np.stack([a, c, d], 1)]).astype(np.uint32)
+        col = (0.35 + 0.4 * rng.random(), 0.45 + 0.3 * rng.random(), 0.3 + 0.3 * rng.random())
+        sc.meshes.append(Mesh(f"band_{b}", P, idx, _disney(col)))
+    return sc

@@ -587,10 +587,18 @@ int fovpt_download(fovpt_ctx* c, uint32_t* dst, size_t npix)
     if (!c || !dst) return 1;
     if (!c->last_frame_ptr || npix > c->last_npix) return fail(c, "no frame buffer of that size");
     cudaSetDevice(c->device);
-    if (ensure_pinned(c, npix * 4)) return 1;
-    CU(cudaMemcpyAsync(c->h_pinned, c->last_frame_ptr, npix * 4, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    memcpy(dst, c->h_pinned, npix * 4);
+    cudaPointerAttributes pa;
+    const bool dst_pinned = cudaPointerGetAttributes(&pa, dst) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (dst_pinned) {                                     // caller's buffer is page-locked: DMA straight into it
+        CU(cudaMemcpyAsync(dst, c->last_frame_ptr, npix * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    } else {                                              // pageable: stage through the context's pinned buffer
+        if (ensure_pinned(c, npix * 4)) return 1;
+        CU(cudaMemcpyAsync(c->h_pinned, c->last_frame_ptr, npix * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        memcpy(dst, c->h_pinned, npix * 4);
+    }
     collect_times(c);
     return 0;
 }

@@ -45,6 +45,11 @@ class Scene:
     def n_tris(self):
         return int(sum(len(m.idx) for m in self.meshes))
 
+    def add(self, vtx, idx, material, texcoord=None, texture_id=-1, name=""):
+        self.meshes.append(Mesh(name or f"mesh{len(self.meshes)}", np.ascontiguousarray(vtx, np.float32).reshape(-1, 3),
+                                np.ascontiguousarray(idx, np.uint32).reshape(-1, 3), material, texcoord, texture_id))
+        return len(self.meshes) - 1
+
 
 @dataclass
 class CameraSpec:

@@ -198,6 +198,7 @@ class Oracle:
         lp.camera.eye.set(eye); lp.camera.U.set(U); lp.camera.V.set(V); lp.camera.W.set(W)
         lp.viewport_x, lp.viewport_y = w, h
         lp.white = 1.0
+        lp._keep = (accum, frame)          # the blob holds raw pointers into these arrays
         return lp, accum, frame
 
     def launch(self, lp, lw, lh, opts):

@@ -257,7 +257,7 @@ int run_frame(fovpt_ctx* c, const LaunchParamsBlob& lp, const std::vector<PassHo
 
     const int iters = c->cfg.max_depth + 1 + (c->scene.any_catcher ? 4 : 0);
     for (auto& g : groups) {
-        CU(cudaMemsetAsync(c->q.counts, 0, 4 * sizeof(uint32_t), c->stream));
+        CU(cudaMemsetAsync(c->q.counts, 0, 8 * sizeof(uint32_t), c->stream));
         for (auto& ch : g) {
             Timed t(c, K_RAYGEN);
             launch_raygen(c->L, F, ch.pass, ch.row0, ch.row1, ch.pid_base, c->needed, c->ps, c->q, c->li_backplate, c->d_stats);
@@ -361,8 +361,8 @@ int fovpt_create(fovpt_ctx** out, int device, void* stream)
     c->L.grid_trace = c->n_sm * (be > 0 ? be : 8);
     c->L.grid_shade = c->n_sm * (bs > 0 ? bs : 4);
     c->L.grid_light = c->n_sm * 8;
-    if (dmalloc(&c->q.counts, 4) != cudaSuccess || dmalloc(&c->d_stats, 1) != cudaSuccess) { delete c; return 5; }
-    cudaMemset(c->q.counts, 0, 16); cudaMemset(c->d_stats, 0, sizeof(DevStats));
+    if (dmalloc(&c->q.counts, 8) != cudaSuccess || dmalloc(&c->d_stats, 1) != cudaSuccess) { delete c; return 5; }
+    cudaMemset(c->q.counts, 0, 32); cudaMemset(c->d_stats, 0, sizeof(DevStats));
     cudaEventCreate(&c->ev_frame0); cudaEventCreate(&c->ev_frame1);
     *out = c;
     return 0;
@@ -486,7 +486,7 @@ int fovpt_scene_commit(fovpt_ctx* c, uint64_t* traversable_out)
     cudaEventSynchronize(e1);
     cudaEventElapsedTime(&c->build_ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    if (c->bvh.max_depth > (uint32_t)kStackSize) return fail(c, "BVH deeper than the traversal stack");
+    if (3 * c->bvh.max_depth + 1 > (uint32_t)kStackSize) return fail(c, "BVH deeper than the traversal stack allows (3 deferred children per level)");
 
     c->scene.bvh.nodes = c->bvh.nodes; c->scene.bvh.tris = c->bvh.tris;
     c->scene.bvh.n_nodes = c->bvh.n_nodes; c->scene.bvh.n_tris = c->bvh.n_tris;
@@ -618,7 +618,7 @@ int fovpt_trace(fovpt_ctx* c, const float* rays, size_t n, int mode, int32_t* tr
 {
     if (!c || !rays || !tri) return 1;
     if (!c->committed) return fail(c, "scene not committed");
-    if (mode != 0 && mode != 1) return fail(c, "mode must be 0 (closest) or 1 (any)");
+    if (mode < 0 || mode > 3) return fail(c, "mode must be 0 (closest), 1 (any), 2/3 (the same with visit counters in tuv)");
     if (n == 0) return 0;
     cudaSetDevice(c->device);
     float* d_r = nullptr; int32_t* d_t = nullptr; float* d_tuv = nullptr;
@@ -715,7 +715,7 @@ int fovpt_bvh_read(fovpt_ctx* c, void* nodes64, uint32_t* sorted_tri_ids)
 {
     if (!c || !c->committed) return 1;
     cudaSetDevice(c->device);
-    if (nodes64 && c->bvh.n_nodes) CU(cudaMemcpy(nodes64, c->bvh.nodes, (size_t)c->bvh.n_nodes * 64, cudaMemcpyDeviceToHost));
+    if (nodes64 && c->bvh.n_nodes) CU(cudaMemcpy(nodes64, c->bvh.nodes, (size_t)c->bvh.n_nodes * 128, cudaMemcpyDeviceToHost));
     if (sorted_tri_ids && c->bvh.n_tris) CU(cudaMemcpy(sorted_tri_ids, c->bvh.sorted_ids, (size_t)c->bvh.n_tris * 4, cudaMemcpyDeviceToHost));
     return 0;
 }

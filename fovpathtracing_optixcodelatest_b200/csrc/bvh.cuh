@@ -1,16 +1,18 @@
-// bvh.cuh -- device BVH layout and the two traversal routines that replace optixTrace
+// bvh.cuh -- device BVH layout and the traversal state machine that replaces optixTrace
 // (reference call sites: PT_sv5_/deviceProgram.cu:196-222 radiance / :224-248 occlusion).
 //
-// Layout in HBM (all 32-byte aligned, read through the read-only path):
-//   nodes : 64 B per inner node = 4 x float4
-//             n0 = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)
-//             n1 = (c1.lo.x, c1.hi.x, c1.lo.y, c1.hi.y)
-//             n2 = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)
-//             n3 = (child0, child1, -, -) as int bits; child >= 0: inner node index,
-//                  child < 0: leaf, ~child = (first_sorted_tri << 2) | (count - 1), count in 1..4
+// Layout in HBM (all 32-byte aligned, read through the read-only path with 256-bit loads):
+//   nodes : 128 B per 4-wide inner node = 8 x float4, structure-of-arrays over the 4 child slots
+//             q0 = lo.x[0..3]   q1 = hi.x[0..3]   q2 = lo.y[0..3]   q3 = hi.y[0..3]
+//             q4 = lo.z[0..3]   q5 = hi.z[0..3]   q6 = child[0..3] (int bits)   q7 = 0
+//           child >= 0 : index of an inner node;  child < 0 : leaf,
+//           ~child = (first_sorted_tri << 2) | (count - 1), count in 1..4;
+//           an unused slot has lo = hi = +inf on every axis: its slab interval is empty for every ray
+//           with finite tmax, so it can never be entered.
 //   tris  : 48 B per triangle in leaf (Morton) order = 3 x float4
 //             (v0.xyz, bits(global id)), (e1.xyz, 0), (e2.xyz, 0)      [fx_make_tri of fovpt_exact.h]
-// Algorithmic bytes per ray: 64 per node visit + 48 per triangle test + 48 (ray in, hit out).
+// Algorithmic bytes per ray are counted on the oracle's canonical binary tree:
+// 64 per node visit + 48 per triangle test + 48 (ray in, hit out); see DESIGN.md section 5.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -26,28 +28,26 @@ struct DeviceBvh {
     uint32_t      n_tris = 0;
 };
 
-constexpr int kStackSize = 96;
+constexpr int kStackSize = 96;          // entries; scene commit refuses trees deeper than kStackSize / 3
+constexpr int kDone = 0x7fffffff;       // `cur` of a finished ray (never a valid node index)
 
 struct HitRec { float t, u, v; uint32_t k; uint32_t gid; };   // k = sorted triangle slot, gid = global id
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 
-// slab test of one child box against the ray (origin folded into ood = o * idir).  Boxes are
-// padded at build time (bvh_build.cu), which is what makes the fma form conservative.
-__device__ __forceinline__ void slab2(const float4 n0, const float4 n1, const float4 n2, const float3 idir, const float3 ood,
-                                      float tmin, float tmax, float& tn0, float& tf0, float& tn1, float& tf1)
+struct f8 { float4 a, b; };
+// one 256-bit read-only load (LDG.E.256.CONSTANT); p must be 32-byte aligned
+__device__ __forceinline__ f8 ldg256(const float4* p)
 {
-    float c0lox = fmaf(n0.x, idir.x, -ood.x), c0hix = fmaf(n0.y, idir.x, -ood.x);
-    float c0loy = fmaf(n0.z, idir.y, -ood.y), c0hiy = fmaf(n0.w, idir.y, -ood.y);
-    float c0loz = fmaf(n2.x, idir.z, -ood.z), c0hiz = fmaf(n2.y, idir.z, -ood.z);
-    float c1lox = fmaf(n1.x, idir.x, -ood.x), c1hix = fmaf(n1.y, idir.x, -ood.x);
-    float c1loy = fmaf(n1.z, idir.y, -ood.y), c1hiy = fmaf(n1.w, idir.y, -ood.y);
-    float c1loz = fmaf(n2.z, idir.z, -ood.z), c1hiz = fmaf(n2.w, idir.z, -ood.z);
-    tn0 = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), tmin));
-    tf0 = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fminf(fmaxf(c0loz, c0hiz), tmax));
-    tn1 = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), tmin));
-    tf1 = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fminf(fmaxf(c1loz, c1hiz), tmax));
+    f8 r;
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
+                 : "l"(p));
+    return r;
 }
+
+__device__ __forceinline__ uint32_t leaf_count(int child) { return (((uint32_t)~child) & 3u) + 1u; }
+__device__ __forceinline__ uint32_t leaf_first(int child) { return ((uint32_t)~child) >> 2; }
 
 __device__ __forceinline__ float safe_rcp(float d)
 {
@@ -57,42 +57,116 @@ __device__ __forceinline__ float safe_rcp(float d)
     return 1.0f / ad;
 }
 
-// closest hit: min t in (tmin, tmax), ties -> smallest global triangle id (fx_hit_better).
-__device__ __forceinline__ bool trace_closest(const DeviceBvh& bvh, float3 o, float3 d, float tmin, float tmax, HitRec& out)
+// slab test of one child box (origin folded into ood = o * idir).  Boxes are padded at build time
+// (bvh_build.cu), which is what makes the fma form conservative with respect to fx_ray_tri.
+__device__ __forceinline__ void slab(float lox, float hix, float loy, float hiy, float loz, float hiz, const float3 idir, const float3 ood,
+                                     float tmin, float tlimit, float& tn, float& tf)
 {
-    float best_t = __int_as_float(0x7f800000);   // +inf
-    uint32_t best_gid = 0xffffffffu, best_k = 0;
-    float best_u = 0.f, best_v = 0.f;
-    if (bvh.n_tris == 0) return false;
-    const float3 idir = make_float3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
-    const float3 ood = make_float3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
-    const fx_vec3 O = {o.x, o.y, o.z}, D = {d.x, d.y, d.z};
-    int stack[kStackSize];
-    int sp = 0;
-    int cur = 0;
-    for (;;) {
-        while (cur >= 0) {
-            const float4* np = bvh.nodes + 4 * (size_t)cur;
-            const float4 n0 = ldg4(np), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3);
-            float tn0, tf0, tn1, tf1;
-            slab2(n0, n1, n2, idir, ood, tmin, fminf(tmax, best_t), tn0, tf0, tn1, tf1);
-            const bool h0 = tn0 <= tf0, h1 = tn1 <= tf1;
-            const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
-            if (h0 && h1) {
-                const bool swap = tn1 < tn0;
-                cur = swap ? c1 : c0;
-                if (sp < kStackSize) stack[sp++] = swap ? c0 : c1;
-            } else if (h0) cur = c0;
-            else if (h1) cur = c1;
-            else {
-                if (sp == 0) goto done;
-                cur = stack[--sp];
-            }
+    const float ax = fmaf(lox, idir.x, -ood.x), bx = fmaf(hix, idir.x, -ood.x);
+    const float ay = fmaf(loy, idir.y, -ood.y), by = fmaf(hiy, idir.y, -ood.y);
+    const float az = fmaf(loz, idir.z, -ood.z), bz = fmaf(hiz, idir.z, -ood.z);
+    tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
+    tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tlimit));
+}
+
+__device__ __forceinline__ void cswap(int& a, int& b) { const int lo = min(a, b), hi = max(a, b); a = lo; b = hi; }
+
+// One ray's traversal as a resumable state machine.  A ray is always in one of three states:
+//   at_node()  : `cur` is an inner node  -> node_step() tests its 4 child boxes (branch-free)
+//   at_leaf()  : `cur` is a leaf         -> leaf_step() tests its 1..4 triangles
+//   done()     : finished
+// Kernels run 32 rays per warp, execute per iteration the step kind that the majority of lanes is
+// waiting for, and replace finished rays from the stage queue (wavefront.cu k_trace).
+//   ANY = false : closest hit, min t in (tmin, tmax), ties -> smallest global triangle id
+//                 (fx_hit_better), so the result does not depend on tree shape or visiting order.
+//   ANY = true  : true iff some FRONT-facing triangle intersects (tmin, tmax)
+//                 (OPTIX_RAY_FLAG_CULL_BACK_FACING_TRIANGLES + payload-setting any-hit,
+//                 reference deviceProgram.cu:242,284-300); stops at the first one.
+// The stack lives in the caller's local array: closest-hit entries are (child, bits(t_near)) so that
+// entries that fell behind the current best hit are dropped when popped, without touching the node.
+template <bool ANY>
+struct Traversal {
+    float3 o, d, idir, ood;
+    float tmin, tmax;
+    float best_t, best_u, best_v;
+    uint32_t best_gid, best_k;
+    int cur, sp;
+
+    __device__ __forceinline__ void begin(float3 o_, float3 d_, float tmin_, float tmax_)
+    {
+        o = o_; d = d_; tmin = tmin_; tmax = fminf(tmax_, 3.0e38f);      // finite: unused child slots sit at +inf
+        idir = make_float3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
+        ood = make_float3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
+        best_t = __int_as_float(0x7f800000); best_u = best_v = 0.f; best_gid = 0xffffffffu; best_k = 0;
+        cur = 0; sp = 0;
+    }
+    __device__ __forceinline__ bool found() const { return best_gid != 0xffffffffu; }
+    __device__ __forceinline__ bool done() const { return cur == kDone; }
+    __device__ __forceinline__ bool at_node() const { return cur >= 0 && cur != kDone; }
+    __device__ __forceinline__ bool at_leaf() const { return cur < 0; }
+
+    __device__ __forceinline__ void pop(const int2* stack)
+    {
+        if (ANY) { cur = sp > 0 ? stack[--sp].x : kDone; return; }
+        // drop entries whose near distance is already beyond the best hit (strictly: equal t can still win on id)
+        cur = kDone;
+        while (sp > 0) {
+            const int2 e = stack[--sp];
+            if (__int_as_float(e.y) <= best_t) { cur = e.x; break; }
         }
-        {   // leaf
-            const uint32_t enc = (uint32_t)~cur;
-            const uint32_t first = enc >> 2, count = (enc & 3u) + 1u;
-            for (uint32_t i = 0; i < count; ++i) {
+    }
+
+    __device__ __forceinline__ void node_step(const DeviceBvh& bvh, int2* stack)
+    {
+        const float4* np = bvh.nodes + 8 * (size_t)cur;
+        const f8 X = ldg256(np), Y = ldg256(np + 2), Z = ldg256(np + 4);
+        const float4 C = ldg4(np + 6);
+        const float tlimit = ANY ? tmax : fminf(tmax, best_t);
+        float tn0, tn1, tn2, tn3, tf0, tf1, tf2, tf3;
+        slab(X.a.x, X.b.x, Y.a.x, Y.b.x, Z.a.x, Z.b.x, idir, ood, tmin, tlimit, tn0, tf0);
+        slab(X.a.y, X.b.y, Y.a.y, Y.b.y, Z.a.y, Z.b.y, idir, ood, tmin, tlimit, tn1, tf1);
+        slab(X.a.z, X.b.z, Y.a.z, Y.b.z, Z.a.z, Z.b.z, idir, ood, tmin, tlimit, tn2, tf2);
+        slab(X.a.w, X.b.w, Y.a.w, Y.b.w, Z.a.w, Z.b.w, idir, ood, tmin, tlimit, tn3, tf3);
+        const int c0 = __float_as_int(C.x), c1 = __float_as_int(C.y), c2 = __float_as_int(C.z), c3 = __float_as_int(C.w);
+        if (ANY) {
+            // order is irrelevant for occlusion: enter the first hit child, push the others
+            const bool h0 = tn0 <= tf0, h1 = tn1 <= tf1, h2 = tn2 <= tf2, h3 = tn3 <= tf3;
+            int next = kDone;
+            if (h3) { next = c3; }
+            if (h2) { if (next != kDone) stack[sp++] = make_int2(next, 0); next = c2; }
+            if (h1) { if (next != kDone) stack[sp++] = make_int2(next, 0); next = c1; }
+            if (h0) { if (next != kDone) stack[sp++] = make_int2(next, 0); next = c0; }
+            if (next != kDone) cur = next; else pop(stack);
+        } else {
+            // sort the (up to 4) hit children by entry distance with a 5-exchange network on integer keys:
+            // key = bits(t_near) with the slot number in the two low mantissa bits (t_near >= tmin > 0, so
+            // the bit pattern orders like the float), misses = INT_MAX.
+            const int kMiss = 0x7fffffff;
+            int k0 = tn0 <= tf0 ? ((__float_as_int(fmaxf(tn0, 0.f)) & ~3) | 0) : kMiss;
+            int k1 = tn1 <= tf1 ? ((__float_as_int(fmaxf(tn1, 0.f)) & ~3) | 1) : kMiss;
+            int k2 = tn2 <= tf2 ? ((__float_as_int(fmaxf(tn2, 0.f)) & ~3) | 2) : kMiss;
+            int k3 = tn3 <= tf3 ? ((__float_as_int(fmaxf(tn3, 0.f)) & ~3) | 3) : kMiss;
+            cswap(k0, k1); cswap(k2, k3); cswap(k0, k2); cswap(k1, k3); cswap(k1, k2);
+#define FOVPT_CHILD(k) (((k) & 2) ? (((k) & 1) ? c3 : c2) : (((k) & 1) ? c1 : c0))
+            // far to near, so that the nearest of the deferred children is on top; clearing the key's low
+            // bits only makes the stored distance a hair smaller, which keeps the pop-time cull conservative
+            if (k3 != kMiss) stack[sp++] = make_int2(FOVPT_CHILD(k3), k3 & ~3);
+            if (k2 != kMiss) stack[sp++] = make_int2(FOVPT_CHILD(k2), k2 & ~3);
+            if (k1 != kMiss) stack[sp++] = make_int2(FOVPT_CHILD(k1), k1 & ~3);
+            if (k0 != kMiss) cur = FOVPT_CHILD(k0); else pop(stack);
+#undef FOVPT_CHILD
+        }
+    }
+
+    // `nmax` = largest triangle count among the lanes of this warp that execute the step together
+    // (keeps the loop trip count warp-uniform; each lane predicates on its own count)
+    __device__ __forceinline__ void leaf_step(const DeviceBvh& bvh, const int2* stack, uint32_t nmax)
+    {
+        const uint32_t first = leaf_first(cur), count = leaf_count(cur);
+        const fx_vec3 O = {o.x, o.y, o.z}, D = {d.x, d.y, d.z};
+        bool occluded = false;
+        for (uint32_t i = 0; i < nmax; ++i) {
+            if (i < count) {
                 const float4* tp = bvh.tris + 3 * (size_t)(first + i);
                 const float4 a = ldg4(tp), b = ldg4(tp + 1), c = ldg4(tp + 2);
                 fx_tri tr;
@@ -100,66 +174,51 @@ __device__ __forceinline__ bool trace_closest(const DeviceBvh& bvh, float3 o, fl
                 tr.e1.x = b.x; tr.e1.y = b.y; tr.e1.z = b.z;
                 tr.e2.x = c.x; tr.e2.y = c.y; tr.e2.z = c.z;
                 float t, u, v;
-                if (fx_ray_tri(O, D, tr, &t, &u, &v) == 0) continue;
-                if (!(t > tmin && t < tmax)) continue;
-                const uint32_t gid = (uint32_t)__float_as_int(a.w);
-                if (fx_hit_better(t, gid, best_t, best_gid)) { best_t = t; best_gid = gid; best_k = first + i; best_u = u; best_v = v; }
+                const int side = fx_ray_tri_nb(O, D, tr, &t, &u, &v);
+                if (ANY) {
+                    occluded = occluded || (side == 1 && t > tmin && t < tmax);
+                } else {
+                    const uint32_t gid = (uint32_t)__float_as_int(a.w);
+                    if (side != 0 && t > tmin && t < tmax && fx_hit_better(t, gid, best_t, best_gid)) {
+                        best_t = t; best_gid = gid; best_k = first + i; best_u = u; best_v = v;
+                    }
+                }
             }
-            if (sp == 0) break;
-            cur = stack[--sp];
+        }
+        if (ANY && occluded) { best_gid = 0; cur = kDone; return; }
+        pop(stack);
+    }
+
+    // scalar driver (query kernels): one ray per thread, no warp cooperation
+    __device__ __forceinline__ void run(const DeviceBvh& bvh, int2* stack)
+    {
+        while (!done()) {
+            if (at_node()) node_step(bvh, stack);
+            else leaf_step(bvh, stack, leaf_count(cur));
         }
     }
-done:
-    if (best_gid == 0xffffffffu) return false;
-    out.t = best_t; out.u = best_u; out.v = best_v; out.k = best_k; out.gid = best_gid;
+};
+
+__device__ __forceinline__ bool trace_closest(const DeviceBvh& bvh, float3 o, float3 d, float tmin, float tmax, HitRec& out)
+{
+    if (bvh.n_tris == 0) return false;
+    Traversal<false> T;
+    int2 stack[kStackSize];
+    T.begin(o, d, tmin, tmax);
+    T.run(bvh, stack);
+    if (!T.found()) return false;
+    out.t = T.best_t; out.u = T.best_u; out.v = T.best_v; out.k = T.best_k; out.gid = T.best_gid;
     return true;
 }
 
-// any-hit with back-face culling: true iff some FRONT-facing triangle intersects (tmin, tmax).
-// (OPTIX_RAY_FLAG_CULL_BACK_FACING_TRIANGLES + payload-setting any-hit, deviceProgram.cu:242,284-300.)
 __device__ __forceinline__ bool trace_any_front(const DeviceBvh& bvh, float3 o, float3 d, float tmin, float tmax)
 {
     if (bvh.n_tris == 0) return false;
-    const float3 idir = make_float3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
-    const float3 ood = make_float3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
-    const fx_vec3 O = {o.x, o.y, o.z}, D = {d.x, d.y, d.z};
-    int stack[kStackSize];
-    int sp = 0;
-    int cur = 0;
-    for (;;) {
-        while (cur >= 0) {
-            const float4* np = bvh.nodes + 4 * (size_t)cur;
-            const float4 n0 = ldg4(np), n1 = ldg4(np + 1), n2 = ldg4(np + 2), n3 = ldg4(np + 3);
-            float tn0, tf0, tn1, tf1;
-            slab2(n0, n1, n2, idir, ood, tmin, tmax, tn0, tf0, tn1, tf1);
-            const bool h0 = tn0 <= tf0, h1 = tn1 <= tf1;
-            const int c0 = __float_as_int(n3.x), c1 = __float_as_int(n3.y);
-            if (h0 && h1) {
-                cur = c0;
-                if (sp < kStackSize) stack[sp++] = c1;
-            } else if (h0) cur = c0;
-            else if (h1) cur = c1;
-            else {
-                if (sp == 0) return false;
-                cur = stack[--sp];
-            }
-        }
-        const uint32_t enc = (uint32_t)~cur;
-        const uint32_t first = enc >> 2, count = (enc & 3u) + 1u;
-        for (uint32_t i = 0; i < count; ++i) {
-            const float4* tp = bvh.tris + 3 * (size_t)(first + i);
-            const float4 a = ldg4(tp), b = ldg4(tp + 1), c = ldg4(tp + 2);
-            fx_tri tr;
-            tr.v0.x = a.x; tr.v0.y = a.y; tr.v0.z = a.z;
-            tr.e1.x = b.x; tr.e1.y = b.y; tr.e1.z = b.z;
-            tr.e2.x = c.x; tr.e2.y = c.y; tr.e2.z = c.z;
-            float t, u, v;
-            if (fx_ray_tri(O, D, tr, &t, &u, &v) != 1) continue;
-            if (t > tmin && t < tmax) return true;
-        }
-        if (sp == 0) return false;
-        cur = stack[--sp];
-    }
+    Traversal<true> T;
+    int2 stack[kStackSize];
+    T.begin(o, d, tmin, tmax);
+    T.run(bvh, stack);
+    return T.found();
 }
 
 }  // namespace fovpt

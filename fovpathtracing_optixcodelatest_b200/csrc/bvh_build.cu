@@ -7,14 +7,20 @@
 //                   k_radix_hist -> k_scan_u32 -> k_radix_scatter (stable, match_any ranking)
 //   k_hierarchy     Karras 2012: one thread per inner node finds its key range and split
 //   k_refit         bottom-up AABBs, second arriver proceeds (atomic counter per node)
-//   k_mark/k_emit   collapse subtrees with <= 4 triangles into leaves, compact the survivors
-//                   (prefix sum) and write the 64-byte child-box nodes + sorted 48-byte triangles
+//   k_collapse4     breadth-first collapse of the binary tree into the 4-wide nodes of bvh.cuh:
+//                   a wide node takes a binary node's two children and twice replaces the child
+//                   of largest surface area by its own two children; subtrees with <= 4 triangles
+//                   become leaves (their triangles are contiguous in Morton order).  One launch
+//                   per level, work queue + node allocation through device counters.
 //
 // Boxes are padded by pad = max|coordinate| / 65536 so that the fma-form slab test of bvh.cuh can
 // never reject a box whose triangle the exact test (fovpt_exact.h) accepts.  Hit results are
 // independent of the tree (tie-break in fx_hit_better), so tree quality is purely a speed matter.
+#include <algorithm>
 #include <cfloat>
 #include <cstdio>
+#include <cstring>
+#include <vector>
 
 #include "bvh.cuh"
 #include "bvh_build.h"
@@ -267,58 +273,104 @@ __global__ void k_refit(int n, const uint32_t* __restrict__ sorted_ids, const fl
     }
 }
 
-// live[j] = 1 for inner nodes that survive the leaf collapse (subtree > leaf_max triangles)
-__global__ void k_mark_live(int n_inner, const int* __restrict__ rng_first, const int* __restrict__ rng_last, int leaf_max,
-                            uint32_t* __restrict__ live)
+// ------------------------------------------------------------------ 4-wide collapse
+struct CollapseItem { int bvh2; int node4; };
+
+__device__ __forceinline__ float box_area(const float4 lo, const float4 hi)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_inner) return;
-    live[i] = (rng_last[i] - rng_first[i] + 1) > leaf_max ? 1u : 0u;
+    const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+    return dx * dy + dy * dz + dz * dx;
 }
 
-__global__ void k_emit_nodes(int n_inner, const uint32_t* __restrict__ live_flag, const uint32_t* __restrict__ new_index,
-                             const int* __restrict__ left, const int* __restrict__ right,
-                             const int* __restrict__ rng_first, const int* __restrict__ rng_last,
-                             const uint32_t* __restrict__ sorted_ids, const float4* __restrict__ box_lo,
-                             const float4* __restrict__ box_hi, const float4* __restrict__ nlo, const float4* __restrict__ nhi,
-                             float pad, float4* __restrict__ nodes)
+__device__ __forceinline__ void write_node4(float4* __restrict__ o, const float4 lo[4], const float4 hi[4], const int enc[4], float pad)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_inner || !live_flag[i]) return;
-    float4 lo[2], hi[2]; int enc[2];
-    const int ch[2] = {left[i], right[i]};
-    for (int s = 0; s < 2; ++s) {
-        if (ch[s] < 0) {
-            const int pos = ~ch[s];
-            const uint32_t id = sorted_ids[pos];
-            lo[s] = box_lo[id]; hi[s] = box_hi[id];
-            enc[s] = ~(int)(((uint32_t)pos << 2) | 0u);
-        } else {
-            lo[s] = nlo[ch[s]]; hi[s] = nhi[ch[s]];
-            if (live_flag[ch[s]]) enc[s] = (int)new_index[ch[s]];
-            else {
-                const int first = rng_first[ch[s]], cnt = rng_last[ch[s]] - first + 1;
-                enc[s] = ~(int)(((uint32_t)first << 2) | (uint32_t)(cnt - 1));
+    o[0] = make_float4(lo[0].x - pad, lo[1].x - pad, lo[2].x - pad, lo[3].x - pad);
+    o[1] = make_float4(hi[0].x + pad, hi[1].x + pad, hi[2].x + pad, hi[3].x + pad);
+    o[2] = make_float4(lo[0].y - pad, lo[1].y - pad, lo[2].y - pad, lo[3].y - pad);
+    o[3] = make_float4(hi[0].y + pad, hi[1].y + pad, hi[2].y + pad, hi[3].y + pad);
+    o[4] = make_float4(lo[0].z - pad, lo[1].z - pad, lo[2].z - pad, lo[3].z - pad);
+    o[5] = make_float4(hi[0].z + pad, hi[1].z + pad, hi[2].z + pad, hi[3].z + pad);
+    o[6] = make_float4(__int_as_float(enc[0]), __int_as_float(enc[1]), __int_as_float(enc[2]), __int_as_float(enc[3]));
+    o[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+// one level: items_in[0 .. counts[level]) -> nodes4 + items_out[0 .. counts[level+1])
+__global__ void k_collapse4(const CollapseItem* __restrict__ items_in, CollapseItem* __restrict__ items_out,
+                            uint32_t* __restrict__ counts, int level, uint32_t* __restrict__ node_counter,
+                            const int* __restrict__ left, const int* __restrict__ right,
+                            const int* __restrict__ rng_first, const int* __restrict__ rng_last,
+                            const uint32_t* __restrict__ sorted_ids, const float4* __restrict__ box_lo,
+                            const float4* __restrict__ box_hi, const float4* __restrict__ nlo, const float4* __restrict__ nhi,
+                            int leaf_max, float pad, float4* __restrict__ nodes4)
+{
+    const uint32_t n = counts[level];
+    for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < n; it += gridDim.x * blockDim.x) {
+        const CollapseItem item = items_in[it];
+        int c[4]; int nc = 2;
+        c[0] = left[item.bvh2]; c[1] = right[item.bvh2]; c[2] = c[3] = 0;
+        for (int rep = 0; rep < 2; ++rep) {
+            int pick = -1; float best = -1.f;
+            for (int j = 0; j < nc; ++j) {
+                if (c[j] < 0) continue;                                            // single triangle
+                if (rng_last[c[j]] - rng_first[c[j]] + 1 <= leaf_max) continue;    // becomes a leaf as a whole
+                const float a = box_area(nlo[c[j]], nhi[c[j]]);
+                if (a > best) { best = a; pick = j; }
+            }
+            if (pick < 0) break;
+            const int x = c[pick];
+            c[pick] = left[x]; c[nc++] = right[x];
+        }
+        int n_inner = 0;
+        bool inner[4];
+        for (int j = 0; j < 4; ++j) {
+            inner[j] = j < nc && c[j] >= 0 && (rng_last[c[j]] - rng_first[c[j]] + 1 > leaf_max);
+            n_inner += inner[j] ? 1 : 0;
+        }
+        uint32_t base = 0, qbase = 0;
+        if (n_inner) { base = atomicAdd(node_counter, (uint32_t)n_inner); qbase = atomicAdd(&counts[level + 1], (uint32_t)n_inner); }
+        float4 lo[4], hi[4]; int enc[4];
+        int k = 0;
+        for (int j = 0; j < 4; ++j) {
+            if (j >= nc) {                                                         // empty slot: inverted box, never hit
+                const float inf = __int_as_float(0x7f800000);
+                lo[j] = make_float4(inf, inf, inf, 0.f); hi[j] = lo[j];
+                enc[j] = 0x7fffffff;
+            } else if (c[j] < 0) {
+                const int pos = ~c[j];
+                const uint32_t id = sorted_ids[pos];
+                lo[j] = box_lo[id]; hi[j] = box_hi[id];
+                enc[j] = ~(int)(((uint32_t)pos << 2) | 0u);
+            } else {
+                lo[j] = nlo[c[j]]; hi[j] = nhi[c[j]];
+                if (inner[j]) {
+                    enc[j] = (int)(base + k);
+                    items_out[qbase + k] = CollapseItem{c[j], (int)(base + k)};
+                    ++k;
+                } else {
+                    const int first = rng_first[c[j]], cnt = rng_last[c[j]] - first + 1;
+                    enc[j] = ~(int)(((uint32_t)first << 2) | (uint32_t)(cnt - 1));
+                }
             }
         }
+        write_node4(nodes4 + 8 * (size_t)item.node4, lo, hi, enc, pad);
     }
-    float4* o = nodes + 4 * (size_t)new_index[i];
-    o[0] = make_float4(lo[0].x - pad, hi[0].x + pad, lo[0].y - pad, hi[0].y + pad);
-    o[1] = make_float4(lo[1].x - pad, hi[1].x + pad, lo[1].y - pad, hi[1].y + pad);
-    o[2] = make_float4(lo[0].z - pad, hi[0].z + pad, lo[1].z - pad, hi[1].z + pad);
-    o[3] = make_float4(__int_as_float(enc[0]), __int_as_float(enc[1]), 0.f, 0.f);
 }
 
-// tiny scenes (<= leaf_max triangles): a root whose child 0 is the only leaf
-__global__ void k_emit_single(int n, float4* __restrict__ nodes)
+// scenes with <= leaf_max triangles: a root whose slot 0 is the only leaf
+__global__ void k_emit_single4(int n, float4* __restrict__ nodes4)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const float big = 3.0e38f;
-    nodes[0] = make_float4(-big, big, -big, big);
-    nodes[1] = make_float4(big, -big, big, -big);       // child 1: inverted box, never hit
-    nodes[2] = make_float4(-big, big, big, -big);
-    const int enc0 = ~(int)((0u << 2) | (uint32_t)(n - 1));
-    nodes[3] = make_float4(__int_as_float(enc0), __int_as_float(enc0), 0.f, 0.f);
+    const float big = 3.0e38f, inf = __int_as_float(0x7f800000);
+    float4 lo[4], hi[4]; int enc[4];
+    for (int j = 0; j < 4; ++j) { lo[j] = make_float4(inf, inf, inf, 0.f); hi[j] = lo[j]; enc[j] = 0x7fffffff; }
+    lo[0] = make_float4(-big, -big, -big, 0.f); hi[0] = make_float4(big, big, big, 0.f);
+    enc[0] = ~(int)((0u << 2) | (uint32_t)(n - 1));
+    write_node4(nodes4, lo, hi, enc, 0.f);
+}
+
+__global__ void k_seed_collapse(CollapseItem* items, uint32_t* counts, uint32_t* node_counter)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) { items[0] = CollapseItem{0, 0}; counts[0] = 1; *node_counter = 1; }
 }
 
 __global__ void k_gather_tris(uint32_t n, const uint32_t* __restrict__ sorted_ids, const float4* __restrict__ tri_rec,
@@ -348,7 +400,7 @@ cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, uint32_t ntri, 
     int* bounds = nullptr;
     uint64_t *keys[2] = {nullptr, nullptr};
     uint32_t *vals[2] = {nullptr, nullptr};
-    uint32_t *hist = nullptr, *visits = nullptr, *live = nullptr, *newidx = nullptr, *scal = nullptr;
+    uint32_t *hist = nullptr, *visits = nullptr, *scal = nullptr;
     int *left = nullptr, *right = nullptr, *par_in = nullptr, *par_leaf = nullptr, *rf = nullptr, *rl = nullptr;
     const uint32_t nblocks = (ntri + RS_TILE - 1) / RS_TILE;
     const uint32_t ninner = ntri > 1 ? ntri - 1 : 1;
@@ -390,36 +442,60 @@ cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, uint32_t ntri, 
     k_gather_tris<<<gb, T, 0, st>>>(ntri, vals[cur], tri_rec, tri_sorted);
     *launches += 1;
 
+    CollapseItem* items[2] = {nullptr, nullptr};
+    uint32_t* lvl_counts = nullptr;
     if ((int)ntri <= leaf_max) {
-        CK(dalloc(&nodes, 4));
-        k_emit_single<<<1, 32, 0, st>>>((int)ntri, nodes);
+        CK(dalloc(&nodes, 8));
+        k_emit_single4<<<1, 32, 0, st>>>((int)ntri, nodes);
         *launches += 1;
         out->n_nodes = 1; out->max_depth = 1;
     } else {
         CK(dalloc(&left, ninner)); CK(dalloc(&right, ninner)); CK(dalloc(&par_in, ninner)); CK(dalloc(&par_leaf, ntri));
         CK(dalloc(&rf, ninner)); CK(dalloc(&rl, ninner)); CK(dalloc(&nlo, ninner)); CK(dalloc(&nhi, ninner));
-        CK(dalloc(&visits, ninner)); CK(dalloc(&live, ninner)); CK(dalloc(&newidx, ninner));
+        CK(dalloc(&visits, ninner));
         CK(cudaMemsetAsync(visits, 0, ninner * sizeof(uint32_t), st));
         const uint32_t gi = (ninner + T - 1) / T;
         k_hierarchy<<<gi, T, 0, st>>>(keys[cur], (int)ntri, left, right, par_in, par_leaf, rf, rl);
         k_refit<<<gb, T, 0, st>>>((int)ntri, vals[cur], box_lo, box_hi, left, right, par_in, par_leaf, nlo, nhi, visits, scal + 1);
-        k_mark_live<<<gi, T, 0, st>>>((int)ninner, rf, rl, leaf_max, live);
-        CK(cudaMemcpyAsync(newidx, live, ninner * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-        k_scan_u32<<<1, 1024, 0, st>>>(newidx, ninner, scal);
-        uint32_t hs[2];
-        CK(cudaMemcpyAsync(hs, scal, sizeof(hs), cudaMemcpyDeviceToHost, st));
+        uint32_t depth2 = 0;
+        CK(cudaMemcpyAsync(&depth2, scal + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        out->n_nodes = hs[0]; out->max_depth = hs[1];
-        CK(dalloc(&nodes, 4 * (size_t)hs[0]));
-        k_emit_nodes<<<gi, T, 0, st>>>((int)ninner, live, newidx, left, right, rf, rl, vals[cur], box_lo, box_hi, nlo, nhi, pad, nodes);
-        *launches += 5;
+        *launches += 2;
+        // 4-wide collapse, one launch per level of the wide tree (at most the binary depth)
+        const uint32_t cap = ninner;                     // a wide node consumes at least one binary node
+        CK(dalloc(&nodes, 8 * (size_t)cap));
+        CK(dalloc(&items[0], cap)); CK(dalloc(&items[1], cap));
+        CK(dalloc(&lvl_counts, (size_t)depth2 + 2));
+        CK(cudaMemsetAsync(lvl_counts, 0, ((size_t)depth2 + 2) * sizeof(uint32_t), st));
+        k_seed_collapse<<<1, 32, 0, st>>>(items[0], lvl_counts, scal + 2);
+        const int cgrid = (int)std::min<uint32_t>((cap + 127) / 128, 148u * 8u);
+        for (uint32_t lvl = 0; lvl < depth2; ++lvl) {
+            k_collapse4<<<cgrid, 128, 0, st>>>(items[lvl & 1], items[(lvl + 1) & 1], lvl_counts, (int)lvl, scal + 2, left, right, rf, rl,
+                                              vals[cur], box_lo, box_hi, nlo, nhi, leaf_max, pad, nodes);
+            *launches += 1;
+        }
+        std::vector<uint32_t> hc((size_t)depth2 + 2);
+        uint32_t n4 = 0;
+        CK(cudaMemcpyAsync(hc.data(), lvl_counts, hc.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(&n4, scal + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        uint32_t depth4 = 0;
+        while (depth4 < hc.size() && hc[depth4] > 0) ++depth4;
+        out->n_nodes = n4; out->max_depth = depth4;
+        if (n4 < cap) {                                  // shrink to fit
+            float4* exact = nullptr;
+            CK(dalloc(&exact, 8 * (size_t)n4));
+            CK(cudaMemcpyAsync(exact, nodes, 8 * (size_t)n4 * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+            CK(cudaStreamSynchronize(st));
+            cudaFree(nodes); nodes = exact;
+        }
     }
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     out->nodes = nodes; out->tris = tri_sorted; out->tri_rec = tri_rec; out->sorted_ids = vals[cur];
     cudaFree(box_lo); cudaFree(box_hi); cudaFree(bounds); cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[1 - cur]);
     cudaFree(hist); cudaFree(scal); cudaFree(left); cudaFree(right); cudaFree(par_in); cudaFree(par_leaf);
-    cudaFree(rf); cudaFree(rl); cudaFree(nlo); cudaFree(nhi); cudaFree(visits); cudaFree(live); cudaFree(newidx);
+    cudaFree(rf); cudaFree(rl); cudaFree(nlo); cudaFree(nhi); cudaFree(visits); cudaFree(items[0]); cudaFree(items[1]); cudaFree(lvl_counts);
     return cudaSuccess;
 }
 

@@ -139,42 +139,92 @@ __global__ void k_raygen(FrameDev F, int pass, unsigned row0, unsigned row1, uns
     if ((threadIdx.x & 31) == 0 && started) atomicAdd(&stats->samples, started);
 }
 
-// ------------------------------------------------------------------ k_extend  (closest hit)
-__global__ void __launch_bounds__(128) k_extend(SceneDev S, PathState ps, Queues q, float tmin, float tmax, DevStats* __restrict__ stats)
+// the tail of SampleLights / SampleShadow once the occlusion bit is known (deviceProgram.cu:323-341, :367-384)
+__device__ __forceinline__ void shadow_resolve(const PathState& ps, uint32_t pid, bool occluded)
 {
-    const uint32_t n = q.counts[0];
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats->radiance_rays, (unsigned long long)n);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t pid = q.cur[i];
-        const float4 o = ps.ray_o[pid], d = ps.ray_d[pid];
-        HitRec h;
-        const bool ok = trace_closest(S.bvh, make_float3(o.x, o.y, o.z), make_float3(d.x, d.y, d.z), tmin, tmax, h);
-        ps.hit[pid] = ok ? make_float4(h.t, h.u, h.v, __int_as_float((int)h.k)) : make_float4(0.f, 0.f, 0.f, __int_as_float((int)kNoHit));
+    const float4 pe = ps.pend[pid];
+    const uint32_t mode = (uint32_t)__float_as_int(pe.w);
+    if ((mode & 1u) == 0u) {
+        if (!occluded) {
+            float4* dst = (mode & 2u) ? ps.direct : ps.indirect;
+            float4 a = dst[pid];
+            a.x += pe.x; a.y += pe.y; a.z += pe.z;
+            dst[pid] = a;
+        }
+    } else if (occluded) {                                 // shadow catcher
+        float4 a = ps.alpha[pid];
+        a.x += pe.x; a.y += pe.y; a.z += pe.z;
+        ps.alpha[pid] = a;
     }
 }
 
-// ------------------------------------------------------------------ k_shadow  (any hit, back faces culled)
-__global__ void __launch_bounds__(128) k_shadow(SceneDev S, PathState ps, Queues q, float tmin, float tmax, DevStats* __restrict__ stats)
+// ------------------------------------------------------------------ k_trace<ANY>  (optixTrace)
+// Persistent warps with dynamic ray fetch: every warp pulls rays from the stage queue through one
+// warp-aggregated atomicAdd and REPLACES terminated lanes while the others keep their traversal state
+// in registers, so a few long rays do not hold 31 idle lanes hostage (any-hit rays terminate at wildly
+// different times).  ANY=false: closest hit of q.cur (the radiance ray, deviceProgram.cu:196-222);
+// ANY=true: occlusion of q.shadow (:224-248) followed by the NEE accumulate of SampleLights (:323-341).
+constexpr int kFetchMin = 8;          // refill as soon as this many lanes are idle
+
+template <bool ANY>
+__global__ void __launch_bounds__(128) k_trace(SceneDev S, PathState ps, Queues q, float tmin, float tmax, DevStats* __restrict__ stats)
 {
-    const uint32_t n = q.counts[2];
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&stats->shadow_rays, (unsigned long long)n);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t pid = q.shadow[i];
-        const float4 o = ps.ray_o[pid], d = ps.shw_d[pid];
-        const bool occluded = trace_any_front(S.bvh, make_float3(o.x, o.y, o.z), make_float3(d.x, d.y, d.z), tmin, tmax);
-        const float4 pe = ps.pend[pid];
-        const uint32_t mode = (uint32_t)__float_as_int(pe.w);
-        if ((mode & 1u) == 0u) {
-            if (!occluded) {                                   // SampleLights, :323-341
-                float4* dst = (mode & 2u) ? ps.direct : ps.indirect;
-                float4 a = dst[pid];
-                a.x += pe.x; a.y += pe.y; a.z += pe.z;
-                dst[pid] = a;
+    constexpr unsigned FULL = 0xffffffffu;
+    const uint32_t n = ANY ? q.counts[2] : q.counts[0];
+    const uint32_t* __restrict__ queue = ANY ? q.shadow : q.cur;
+    uint32_t* fetch = q.counts + (ANY ? 4 : 3);
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(ANY ? &stats->shadow_rays : &stats->radiance_rays, (unsigned long long)n);
+    if (n == 0 || S.bvh.n_tris == 0) {
+        if (!ANY) for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+            ps.hit[queue[i]] = make_float4(0.f, 0.f, 0.f, __int_as_float((int)kNoHit));
+        else for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+            shadow_resolve(ps, queue[i], false);
+        return;
+    }
+    const unsigned lane = threadIdx.x & 31u;
+    Traversal<ANY> T;
+    int2 stack[kStackSize];
+    uint32_t pid = 0;
+    bool have = false, exhausted = false;
+    T.cur = kDone;
+    for (;;) {
+        const unsigned idle = __ballot_sync(FULL, !have);
+        if (idle == FULL || (!exhausted && __popc(idle) >= kFetchMin)) {
+            if (!exhausted) {
+                const int want = __popc(idle);
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(fetch, (uint32_t)want);
+                base = __shfl_sync(FULL, base, 0);
+                const uint32_t mine = base + __popc(idle & ((1u << lane) - 1u));
+                if (!have && mine < n) {
+                    pid = __ldg(&queue[mine]);
+                    const float4 o = ps.ray_o[pid], d = ANY ? ps.shw_d[pid] : ps.ray_d[pid];
+                    T.begin(make_float3(o.x, o.y, o.z), make_float3(d.x, d.y, d.z), tmin, tmax);
+                    have = true;
+                }
+                if (base + (uint32_t)want >= n) exhausted = true;
             }
-        } else if (occluded) {                                 // SampleShadow on a shadow catcher, :367-384
-            float4 a = ps.alpha[pid];
-            a.x += pe.x; a.y += pe.y; a.z += pe.z;
-            ps.alpha[pid] = a;
+            if (__ballot_sync(FULL, have) == 0u) break;
+        }
+        for (;;) {
+            // each iteration runs the step kind most lanes are waiting for; the others keep their state
+            const bool node = have && T.at_node(), leaf = have && T.at_leaf();
+            const unsigned mn = __ballot_sync(FULL, node), ml = __ballot_sync(FULL, leaf);
+            if (__popc(mn) >= __popc(ml)) {
+                if (node) T.node_step(S.bvh, stack);
+            } else {
+                const uint32_t nmax = __reduce_max_sync(FULL, leaf ? leaf_count(T.cur) : 0u);
+                if (leaf) T.leaf_step(S.bvh, stack, nmax);
+            }
+            if (have && T.done()) {
+                if (!ANY) ps.hit[pid] = T.found() ? make_float4(T.best_t, T.best_u, T.best_v, __int_as_float((int)T.best_k))
+                                                  : make_float4(0.f, 0.f, 0.f, __int_as_float((int)kNoHit));
+                else shadow_resolve(ps, pid, T.found());
+                have = false;
+            }
+            const unsigned act = __ballot_sync(FULL, have);
+            if (act == 0u) break;
+            if (!exhausted && __popc(act) <= 32 - kFetchMin) break;
         }
     }
 }
@@ -375,15 +425,35 @@ __global__ void k_trace_query(SceneDev S, const float* __restrict__ rays, size_t
             const bool ok = trace_closest(S.bvh, o, d, r[3], r[7], h);
             tri[i] = ok ? (int32_t)h.gid : -1;
             tuv[3 * i] = ok ? h.t : 0.f; tuv[3 * i + 1] = ok ? h.u : 0.f; tuv[3 * i + 2] = ok ? h.v : 0.f;
-        } else {
+        } else if (mode == 1) {
             tri[i] = trace_any_front(S.bvh, o, d, r[3], r[7]) ? 1 : 0;
+        } else {                                       // modes 2 / 3: closest / any with visit counters in tuv
+            float nodes = 0.f, leaves = 0.f, tris = 0.f;
+            int2 stack[kStackSize];
+            if (S.bvh.n_tris == 0) { tri[i] = mode == 2 ? -1 : 0; }
+            else if (mode == 2) {
+                Traversal<false> T; T.begin(o, d, r[3], r[7]);
+                while (!T.done()) {
+                    if (T.at_node()) { nodes += 1.f; T.node_step(S.bvh, stack); }
+                    else { leaves += 1.f; tris += (float)leaf_count(T.cur); T.leaf_step(S.bvh, stack, leaf_count(T.cur)); }
+                }
+                tri[i] = T.found() ? (int32_t)T.best_gid : -1;
+            } else {
+                Traversal<true> T; T.begin(o, d, r[3], r[7]);
+                while (!T.done()) {
+                    if (T.at_node()) { nodes += 1.f; T.node_step(S.bvh, stack); }
+                    else { leaves += 1.f; tris += (float)leaf_count(T.cur); T.leaf_step(S.bvh, stack, leaf_count(T.cur)); }
+                }
+                tri[i] = T.found() ? 1 : 0;
+            }
+            tuv[3 * i] = nodes; tuv[3 * i + 1] = leaves; tuv[3 * i + 2] = tris;
         }
     }
 }
 
 __global__ void k_swap_counts(uint32_t* counts)
 {
-    if (threadIdx.x == 0 && blockIdx.x == 0) { counts[0] = counts[1]; counts[1] = 0; counts[2] = 0; }
+    if (threadIdx.x == 0 && blockIdx.x == 0) { counts[0] = counts[1]; counts[1] = 0; counts[2] = 0; counts[3] = 0; counts[4] = 0; }
 }
 
 // ------------------------------------------------------------------ launch wrappers (host)
@@ -398,11 +468,11 @@ void launch_raygen(const LaunchCfg& L, const FrameDev& F, int pass, unsigned row
 }
 void launch_extend(const LaunchCfg& L, const SceneDev& S, const PathState& ps, const Queues& q, float tmin, float tmax, DevStats* stats)
 {
-    k_extend<<<L.grid_trace, 128, 0, L.stream>>>(S, ps, q, tmin, tmax, stats);
+    k_trace<false><<<L.grid_trace, 128, 0, L.stream>>>(S, ps, q, tmin, tmax, stats);
 }
 void launch_shadow(const LaunchCfg& L, const SceneDev& S, const PathState& ps, const Queues& q, float tmin, float tmax, DevStats* stats)
 {
-    k_shadow<<<L.grid_trace, 128, 0, L.stream>>>(S, ps, q, tmin, tmax, stats);
+    k_trace<true><<<L.grid_trace, 128, 0, L.stream>>>(S, ps, q, tmin, tmax, stats);
 }
 void launch_shade(const LaunchCfg& L, const FrameDev& F, const SceneDev& S, const PathState& ps, const Queues& q, bool fast)
 {
@@ -431,7 +501,10 @@ void launch_trace_query(const LaunchCfg& L, const SceneDev& S, const float* rays
 
 void query_occupancy(int* extend_blocks_per_sm, int* shade_blocks_per_sm)
 {
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(extend_blocks_per_sm, k_extend, 128, 0);
+    int a = 0, b = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_trace<false>, 128, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace<true>, 128, 0);
+    *extend_blocks_per_sm = a < b ? a : b;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(shade_blocks_per_sm, k_shade<false>, 128, 0);
 }
 

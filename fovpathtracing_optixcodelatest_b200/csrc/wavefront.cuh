@@ -81,7 +81,7 @@ struct Queues {
     uint32_t* cur;
     uint32_t* next;
     uint32_t* shadow;
-    uint32_t* counts;   // [0] cur [1] next [2] shadow
+    uint32_t* counts;   // [0] cur [1] next [2] shadow [3] fetch cursor of k_trace<closest> [4] of k_trace<any>  (8 words)
 };
 
 struct DevStats { unsigned long long samples, radiance_rays, shadow_rays; };

@@ -73,7 +73,7 @@ int fovpt_scene_begin(fovpt_ctx*);
 int fovpt_scene_add_texture(fovpt_ctx*, const uint32_t* rgba8, int w, int h);
 int fovpt_scene_add_mesh(fovpt_ctx*, const float* vtx, size_t nvtx, const uint32_t* idx, size_t ntri,
                          const float* texcoord_or_null, const void* material104, int texture_id);
-/* builds the BVH on the device (Morton codes, radix sort, Karras hierarchy, refit, leaf collapse);
+/* builds the BVH on the device (Morton codes, radix sort, Karras hierarchy, refit, 4-wide collapse);
  * *traversable_out is what LaunchParams.traversable (offset 160) must carry. */
 int fovpt_scene_commit(fovpt_ctx*, uint64_t* traversable_out);
 
@@ -104,7 +104,8 @@ int fovpt_download_accum(fovpt_ctx*, float* dst_rgba, size_t npix);
 
 /* -- ray queries (optixTrace equivalents, deviceProgram.cu:196-248), for parity tests and tools.
  *    rays: n x {ox,oy,oz,tmin, dx,dy,dz,tmax} host floats.  mode 0: closest hit -> tri = global
- *    triangle id or -1, tuv = t,u,v.  mode 1: any front-facing hit -> tri = 1/0. */
+ *    triangle id or -1, tuv = t,u,v.  mode 1: any front-facing hit -> tri = 1/0.  modes 2 / 3: as 0 / 1
+ *    but tuv = (inner nodes visited, leaves visited, triangles tested) -- BVH-quality introspection. */
 int fovpt_trace(fovpt_ctx*, const float* rays, size_t n, int mode, int32_t* tri, float* tuv);
 /* sample-0 primary hit of every launch index of one launch (host outputs, lw*lh entries):
  * tri = global triangle id, -1 miss, -2 outside the ring; tuv = t,u,v; dir = camera direction. */
@@ -117,9 +118,10 @@ int fovpt_set_tile_owner(fovpt_ctx*, int tile_size, int tiles_x, int tiles_y, co
 
 int fovpt_get_stats(fovpt_ctx*, fovpt_stats*);
 int fovpt_reset_stats(fovpt_ctx*);
-/* BVH introspection for validity tests: copies nodes (64 B each) / sorted triangle ids to host. */
+/* BVH introspection for validity tests: copies the 4-wide nodes (128 B each, layout in csrc/bvh.cuh) /
+ * sorted triangle ids to host. */
 int fovpt_bvh_info(fovpt_ctx*, uint64_t* n_nodes, uint64_t* n_tris);
-int fovpt_bvh_read(fovpt_ctx*, void* nodes64, uint32_t* sorted_tri_ids);
+int fovpt_bvh_read(fovpt_ctx*, void* nodes128, uint32_t* sorted_tri_ids);
 
 #ifdef __cplusplus
 }

@@ -215,6 +215,27 @@ FX_HD int fx_ray_tri(fx_vec3 o, fx_vec3 d, const fx_tri tr, float* t_out, float*
     return det > 0.0f ? 1 : -1;
 }
 
+/* The same test without early returns, for SIMT code: every operation of fx_ray_tri is executed in
+ * the same order on the same operands, only the rejections are folded into one predicate at the
+ * end, so whenever fx_ray_tri accepts, the outputs are bit-identical; when it rejects, this returns
+ * 0 and the outputs are unspecified.  (det == 0 makes inv infinite and u/v/t infinite or NaN, which
+ * the comparisons reject exactly as the early return does.) */
+FX_HD int fx_ray_tri_nb(fx_vec3 o, fx_vec3 d, const fx_tri tr, float* t_out, float* u_out, float* v_out)
+{
+    fx_vec3 p = fx_cross3(d, tr.e2);
+    float det = fx_dot3_fma(tr.e1, p);
+    float inv = FX_RCP(det);
+    fx_vec3 tv;
+    tv.x = FX_SUB(o.x, tr.v0.x); tv.y = FX_SUB(o.y, tr.v0.y); tv.z = FX_SUB(o.z, tr.v0.z);
+    float u = FX_MUL(fx_dot3_fma(tv, p), inv);
+    fx_vec3 q = fx_cross3(tv, tr.e1);
+    float v = FX_MUL(fx_dot3_fma(d, q), inv);
+    float t = FX_MUL(fx_dot3_fma(tr.e2, q), inv);
+    int ok = (det != 0.0f) & (u >= 0.0f) & (u <= 1.0f) & (v >= 0.0f) & (FX_ADD(u, v) <= 1.0f) & (t == t);
+    *t_out = t; *u_out = u; *v_out = v;
+    return ok ? (det > 0.0f ? 1 : -1) : 0;
+}
+
 /* Closest-hit ordering: smaller t wins; equal t -> smaller global triangle id wins.  This makes
  * the result independent of BVH shape and traversal order. */
 FX_HD int fx_hit_better(float t, uint32_t id, float best_t, uint32_t best_id)

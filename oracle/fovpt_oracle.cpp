@@ -412,6 +412,8 @@ struct orc_ctx {
     HostProbe probe;
     bool has_probe = false;
     std::string err;
+    std::vector<float> prev_accum;          // snapshot of the accumulation buffer at frame start (extension mode)
+    bool prev_accum_active = false;
 };
 
 namespace {
@@ -425,6 +427,12 @@ struct PRD {                                                       // RadiancePR
 
 struct Frame {                                                     // one launch in flight
     orc_ctx* c; const LaunchParams* lp; const orc_opts* o; Probe probe;
+    // extension mode only (every ring accumulates, orc_opts.seed_all_passes_with_subframe): the accumulation
+    // buffer as the PREVIOUS frame left it.  Each pixel is then lerped exactly once per frame, against last
+    // frame's value, by whichever pass writes it last -- a running mean of per-frame estimates.  Reading the
+    // live buffer instead (the literal vmv2 statement, used when this is null) would lerp the thin rings
+    // where two passes overlap twice in one frame.  See DESIGN.md "accumulation".
+    const f4* prev_accum = nullptr;
 };
 
 // SampleLights / SampleShadow, deviceProgram.cu:303-387 (kProbeSamples = kBsdfSamples = 1)
@@ -572,7 +580,7 @@ bool raygen(const Frame& F, unsigned lx, unsigned ly, unsigned lw)
             if (o.accumulate && subframe_index > 0 && !p.frame.redraw) {     // vmv2 :545-553 (commented out in sv5 :565-581)
                 accum_color = mk3(clampf(accum_color.x, 0.f, 10.f), clampf(accum_color.y, 0.f, 10.f), clampf(accum_color.z, 0.f, 10.f));
                 const float a_w = 1.0f / (float)(subframe_index + 1);
-                const f4 prev4 = p.frame.accum_buffer[image_index];
+                const f4 prev4 = F.prev_accum ? F.prev_accum[image_index] : p.frame.accum_buffer[image_index];
                 accum_color = lerp3(mk3(prev4.x, prev4.y, prev4.z), accum_color, a_w);
             }
             p.frame.accum_buffer[image_index] = {accum_color.x, accum_color.y, accum_color.z, 1.0f};
@@ -702,6 +710,7 @@ int orc_launch(orc_ctx* c, void* lp248, unsigned lw, unsigned lh, const orc_opts
     LaunchParams* lp = (LaunchParams*)lp248;
     lp->traversable = 1;
     Frame F{c, lp, o, c->probe.view()};
+    F.prev_accum = c->prev_accum_active ? reinterpret_cast<const f4*>(c->prev_accum.data()) : nullptr;
     lp->probe = F.probe;
     std::atomic<uint64_t> nsamp{0};
     ocommon::parallel_rows(lh, ocommon::resolve_threads(o->threads), [&](unsigned y) {
@@ -719,6 +728,12 @@ int orc_render(orc_ctx* c, void* lp248, const orc_fov_cfg* cfg, const orc_opts* 
     if (lp->frame.size_x == 0) return 0;
     auto passes = ocommon::three_pass_schedule(*cfg, lp->frame.size_x, lp->frame.size_y, lp->frame.c_x, lp->frame.c_y);
     unsigned saved = lp->frame.subframe_index;
+    c->prev_accum_active = false;
+    if (o->seed_all_passes_with_subframe && o->accumulate && saved > 0) {
+        const size_t nfl = (size_t)lp->frame.size_x * lp->frame.size_y * 4;
+        c->prev_accum.assign((const float*)lp->frame.accum_buffer, (const float*)lp->frame.accum_buffer + nfl);
+        c->prev_accum_active = true;
+    }
     orc_opts local = *o;
     local.primary_tri = nullptr; local.primary_tuv = nullptr; local.primary_dir = nullptr;
     for (auto& p : passes) {
@@ -733,6 +748,7 @@ int orc_render(orc_ctx* c, void* lp248, const orc_fov_cfg* cfg, const orc_opts* 
         if (orc_launch(c, lp, p.lw, p.lh, &local)) return -1;
     }
     lp->frame.subframe_index = saved + 1;
+    c->prev_accum_active = false;
     return 0;
 }
 

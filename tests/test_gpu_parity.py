@@ -19,8 +19,16 @@ from fovpathtracing_optixcodelatest_b200.structs import LaunchParams, Material
 
 pytestmark = pytest.mark.gpu
 
-RMSE_TOL = 1e-6        # relative MSE of the float accumulation buffer vs the oracle (north_star bar: 1e-3)
+RMSE_TOL = 1e-6        # relative MSE of the float accumulation buffer vs the oracle at depth 4 (north_star bar: 1e-3)
+RMSE_TOL_DEEP = 2e-4   # depth-8 paths: one last-ulp difference between CUDA's and glibc's sinf/cosf/powf can send a
+                       # bounce to a different triangle, which changes that one sample completely (north_star: 1e-3)
 MEAN_TOL = 1e-5        # relative difference of the frame's mean radiance
+
+
+def close_fraction(a, g, rel=1e-4):
+    """fraction of pixels whose three channels agree to `rel`: shows that residual error is isolated samples"""
+    a = a[..., :3].astype(np.float64); g = g[..., :3].astype(np.float64)
+    return (np.abs(a - g) <= rel * (1.0 + np.abs(a))).all(axis=2).mean()
 
 
 def bits(a):
@@ -151,35 +159,38 @@ def test_degenerate_rays_and_geometry(gpu, port):
 
 
 def test_bvh_is_valid(gpu):
-    """on-device LBVH: every triangle in exactly one leaf, children boxes inside what the parent stores"""
+    """on-device builder (Morton sort -> Karras hierarchy -> refit -> 4-wide collapse, csrc/bvh.cuh layout): every
+    triangle sits in exactly one leaf, every stored child box contains the boxes / triangles below it, every
+    node is reachable exactly once, and the depth respects the traversal-stack bound"""
     sc = scenes.atrium(detail=0.3)
     ctx = gpu.native.Context(0); ctx.upload_scene(sc)
     nodes, ids = ctx.bvh()
     n_tris = sc.n_tris
     assert sorted(ids.tolist()) == list(range(n_tris))
-    nd = nodes.reshape(-1, 16)
-    child = nd[:, 12:14].copy().view(np.int32)
+    nd = nodes.reshape(-1, 32)
+    child = nd[:, 24:28].copy().view(np.int32)
     seen = np.zeros(n_tris, np.int32)
     tri_v = np.concatenate([m.vtx[m.idx.astype(np.int64)] for m in sc.meshes])       # [T,3,3]
     lo_t, hi_t = tri_v.min(1), tri_v.max(1)
 
-    def box(i, c):      # child c of node i -> (lo, hi)
+    def box(i, c):      # slot c of node i -> (lo, hi)
         n = nd[i]
-        if c == 0:
-            return np.array([n[0], n[2], n[8]]), np.array([n[1], n[3], n[9]])
-        return np.array([n[4], n[6], n[10]]), np.array([n[5], n[7], n[11]])
-    stack = [0] if len(nd) else []
-    visited = 0
+        return np.array([n[0 + c], n[8 + c], n[16 + c]]), np.array([n[4 + c], n[12 + c], n[20 + c]])
+    stack = [(0, 1)]
+    visited = 0; max_depth = 0
     while stack:
-        i = stack.pop(); visited += 1
-        for c in (0, 1):
+        i, depth = stack.pop(); visited += 1; max_depth = max(max_depth, depth)
+        for c in range(4):
             lo, hi = box(i, c)
+            if np.isinf(lo).all():
+                continue                                              # unused slot
             ch = int(child[i, c])
             if ch >= 0:
-                for cc in (0, 1):
+                for cc in range(4):
                     l2, h2 = box(ch, cc)
-                    assert (l2 >= lo - 1e-3).all() and (h2 <= hi + 1e-3).all()
-                stack.append(ch)
+                    if not np.isinf(l2).all():
+                        assert (l2 >= lo - 1e-3).all() and (h2 <= hi + 1e-3).all()
+                stack.append((ch, depth + 1))
             else:
                 enc = (~ch) & 0xffffffff
                 first, cnt = enc >> 2, (enc & 3) + 1
@@ -187,6 +198,7 @@ def test_bvh_is_valid(gpu):
                     g = ids[k]; seen[g] += 1
                     assert (lo_t[g] >= lo).all() and (hi_t[g] <= hi).all(), "leaf box does not contain its triangle"
     assert visited == len(nd) and (seen == 1).all()
+    assert 3 * max_depth + 1 <= 96
     ctx.close()
 
 
@@ -232,7 +244,8 @@ def test_frame_accumulation_depth8(gpu, port):
     for _ in range(3):
         o.render(lp, cfg, op); r.render()
     g = r.downloadAccum(); gf = r.downloadPixels()
-    assert rmse(accum, g) < RMSE_TOL
+    assert rmse(accum, g) < RMSE_TOL_DEEP and close_fraction(accum, g) > 0.995
+    assert abs(accum[..., :3].mean() - g[..., :3].mean()) < 1e-4 * accum[..., :3].mean()
     assert (gf == frame).mean() > 0.99
     assert r.launchParams.frame.subframe_index == 3
     r.close(); o.close()
@@ -379,7 +392,9 @@ def test_full_size_c3_properties(gpu, port):
     assert (tri == gtri).all() and (bits(tuv) == bits(gtuv)).all() and (tri >= 0).sum() > 10000
     # frames
     r.render(); a0 = r.downloadAccum().copy(); st = r.stats()
-    assert np.isfinite(a0).all() and (a0[..., 3] == 1.0).all()       # 1080 = 4*270: every pixel is written
+    # 4x4 periphery blocks are ring-tested at their origin only (deviceProgram.cu:433-440), so a few pixels on the
+    # outer ring boundary are written by no pass -- in the reference too; everything else has accum.w == 1
+    assert np.isfinite(a0).all() and np.isin(a0[..., 3], (0.0, 1.0)).all() and (a0[..., 3] == 1.0).mean() > 0.999
     # closed-form sample count (the launch indices that own at least one pixel; every active index does at this gaze)
     y, x = np.mgrid[0:h // 4, 0:w // 4].astype(np.float32)
     nP = (np.sqrt((4 * x - w // 2) ** 2 + (4 * y - h // 2) ** 2) >= ro).sum()

@@ -262,12 +262,15 @@ int run_frame(fovpt_ctx* c, const LaunchParamsBlob& lp, const std::vector<PassHo
             Timed t(c, K_RAYGEN);
             launch_raygen(c->L, F, ch.pass, ch.row0, ch.row1, ch.pid_base, c->needed, c->ps, c->q, c->li_backplate, c->d_stats);
         }
-        for (int it = 0; it < iters; ++it) {
-            { Timed t(c, K_EXTEND); launch_extend(c->L, c->scene, c->ps, c->q, c->cfg.tmin, c->cfg.tmax, c->d_stats); }
-            { Timed t(c, K_SHADE); launch_shade(c->L, F, c->scene, c->ps, c->q, c->cfg.fast_math != 0); }
-            { Timed t(c, K_SHADOW); launch_shadow(c->L, c->scene, c->ps, c->q, c->cfg.tmin, c->cfg.tmax, c->d_stats); }
+        // iteration i: k_trace extends the radiance rays of bounce i and resolves the shadow rays that
+        // k_shade(i-1) emitted (counter slot alternates 2 / 5), k_shade(i) consumes the hits.
+        for (int it = 0; it <= iters; ++it) {
+            const int slot_prev = (it & 1) ? 2 : 5, slot_new = (it & 1) ? 5 : 2;
+            { Timed t(c, K_EXTEND); launch_trace(c->L, c->scene, c->ps, c->q, slot_prev, c->cfg.tmin, c->cfg.tmax, c->d_stats); }
+            if (it == iters) break;                      // the last launch only drains the final shadow rays
+            { Timed t(c, K_SHADE); launch_shade(c->L, F, c->scene, c->ps, c->q, slot_new, c->cfg.fast_math != 0); }
             std::swap(c->q.cur, c->q.next);
-            { Timed t(c, 0); launch_swap(c->L, c->q.counts); }
+            { Timed t(c, 0); launch_swap(c->L, c->q.counts, slot_prev); }
         }
         for (auto& ch : g) {
             Timed t(c, K_RESOLVE);
@@ -686,6 +689,13 @@ int fovpt_get_stats(fovpt_ctx* c, fovpt_stats* s)
     CU(cudaMemcpy(&d, c->d_stats, sizeof(d), cudaMemcpyDeviceToHost));
     memset(s, 0, sizeof(*s));
     s->samples = d.samples; s->radiance_rays = d.radiance_rays; s->shadow_rays = d.shadow_rays;
+#ifdef FOVPT_TRACE_STATS
+    for (int k = 0; k < 2; ++k) {
+        const unsigned long long* q = d.dbg + 8 * k;
+        fprintf(stderr, "[trace stats %s] node_exec %llu lanes/exec %.2f | leaf_exec %llu lanes/exec %.2f tris/lane %.2f nmax %.2f | fetch rounds %llu\n", k ? "any" : "closest",
+                q[0], q[0] ? (double)q[1] / q[0] : 0., q[2], q[2] ? (double)q[3] / q[2] : 0., q[3] ? (double)q[4] / q[3] : 0., q[2] ? (double)q[5] / q[2] : 0., q[6]);
+    }
+#endif
     s->kernel_launches = c->launches; s->frames = c->frames;
     s->bvh_nodes = c->bvh.n_nodes; s->bvh_tris = c->bvh.n_tris; s->bvh_build_ms = c->build_ms;
     s->last_frame_ms = c->last_ms[0]; s->last_raygen_ms = c->last_ms[K_RAYGEN]; s->last_extend_ms = c->last_ms[K_EXTEND];

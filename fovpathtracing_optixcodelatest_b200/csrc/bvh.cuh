@@ -77,20 +77,27 @@ __device__ __forceinline__ void cswap(int& a, int& b) { const int lo = min(a, b)
 //   done()     : finished
 // Kernels run 32 rays per warp, execute per iteration the step kind that the majority of lanes is
 // waiting for, and replace finished rays from the stage queue (wavefront.cu k_trace).
-//   ANY = false : closest hit, min t in (tmin, tmax), ties -> smallest global triangle id
-//                 (fx_hit_better), so the result does not depend on tree shape or visiting order.
-//   ANY = true  : true iff some FRONT-facing triangle intersects (tmin, tmax)
-//                 (OPTIX_RAY_FLAG_CULL_BACK_FACING_TRIANGLES + payload-setting any-hit,
-//                 reference deviceProgram.cu:242,284-300); stops at the first one.
+//   closest : min t in (tmin, tmax), ties -> smallest global triangle id (fx_hit_better), so the
+//             result does not depend on tree shape or visiting order.
+//   any     : true iff some FRONT-facing triangle intersects (tmin, tmax)
+//             (OPTIX_RAY_FLAG_CULL_BACK_FACING_TRIANGLES + payload-setting any-hit, reference
+//             deviceProgram.cu:242,284-300); stops at the first one.
+//   MODE = kClosest / kAny fix the kind at compile time; MODE = kMixed keeps it per ray in `any`, so
+//   radiance rays of bounce k+1 and shadow rays of bounce k share one launch (and one warp).
 // The stack lives in the caller's local array: closest-hit entries are (child, bits(t_near)) so that
 // entries that fell behind the current best hit are dropped when popped, without touching the node.
-template <bool ANY>
+constexpr int kClosest = 0, kAny = 1, kMixed = 2;
+
+template <int MODE>
 struct Traversal {
     float3 o, d, idir, ood;
     float tmin, tmax;
     float best_t, best_u, best_v;
     uint32_t best_gid, best_k;
     int cur, sp;
+    bool any = (MODE == kAny);
+
+    __device__ __forceinline__ bool is_any() const { return MODE == kMixed ? any : MODE == kAny; }
 
     __device__ __forceinline__ void begin(float3 o_, float3 d_, float tmin_, float tmax_)
     {
@@ -107,7 +114,7 @@ struct Traversal {
 
     __device__ __forceinline__ void pop(const int2* stack)
     {
-        if (ANY) { cur = sp > 0 ? stack[--sp].x : kDone; return; }
+        if (MODE == kAny) { cur = sp > 0 ? stack[--sp].x : kDone; return; }
         // drop entries whose near distance is already beyond the best hit (strictly: equal t can still win on id)
         cur = kDone;
         while (sp > 0) {
@@ -121,14 +128,14 @@ struct Traversal {
         const float4* np = bvh.nodes + 8 * (size_t)cur;
         const f8 X = ldg256(np), Y = ldg256(np + 2), Z = ldg256(np + 4);
         const float4 C = ldg4(np + 6);
-        const float tlimit = ANY ? tmax : fminf(tmax, best_t);
+        const float tlimit = is_any() ? tmax : fminf(tmax, best_t);
         float tn0, tn1, tn2, tn3, tf0, tf1, tf2, tf3;
         slab(X.a.x, X.b.x, Y.a.x, Y.b.x, Z.a.x, Z.b.x, idir, ood, tmin, tlimit, tn0, tf0);
         slab(X.a.y, X.b.y, Y.a.y, Y.b.y, Z.a.y, Z.b.y, idir, ood, tmin, tlimit, tn1, tf1);
         slab(X.a.z, X.b.z, Y.a.z, Y.b.z, Z.a.z, Z.b.z, idir, ood, tmin, tlimit, tn2, tf2);
         slab(X.a.w, X.b.w, Y.a.w, Y.b.w, Z.a.w, Z.b.w, idir, ood, tmin, tlimit, tn3, tf3);
         const int c0 = __float_as_int(C.x), c1 = __float_as_int(C.y), c2 = __float_as_int(C.z), c3 = __float_as_int(C.w);
-        if (ANY) {
+        if (MODE == kAny) {
             // order is irrelevant for occlusion: enter the first hit child, push the others
             const bool h0 = tn0 <= tf0, h1 = tn1 <= tf1, h2 = tn2 <= tf2, h3 = tn3 <= tf3;
             int next = kDone;
@@ -175,17 +182,17 @@ struct Traversal {
                 tr.e2.x = c.x; tr.e2.y = c.y; tr.e2.z = c.z;
                 float t, u, v;
                 const int side = fx_ray_tri_nb(O, D, tr, &t, &u, &v);
-                if (ANY) {
-                    occluded = occluded || (side == 1 && t > tmin && t < tmax);
-                } else {
+                const bool in_range = t > tmin && t < tmax;
+                if (MODE != kClosest) occluded = occluded || (side == 1 && in_range);
+                if (MODE != kAny) {
                     const uint32_t gid = (uint32_t)__float_as_int(a.w);
-                    if (side != 0 && t > tmin && t < tmax && fx_hit_better(t, gid, best_t, best_gid)) {
+                    if (!is_any() && side != 0 && in_range && fx_hit_better(t, gid, best_t, best_gid)) {
                         best_t = t; best_gid = gid; best_k = first + i; best_u = u; best_v = v;
                     }
                 }
             }
         }
-        if (ANY && occluded) { best_gid = 0; cur = kDone; return; }
+        if (MODE != kClosest && is_any() && occluded) { best_gid = 0; cur = kDone; return; }
         pop(stack);
     }
 
@@ -202,7 +209,7 @@ struct Traversal {
 __device__ __forceinline__ bool trace_closest(const DeviceBvh& bvh, float3 o, float3 d, float tmin, float tmax, HitRec& out)
 {
     if (bvh.n_tris == 0) return false;
-    Traversal<false> T;
+    Traversal<kClosest> T;
     int2 stack[kStackSize];
     T.begin(o, d, tmin, tmax);
     T.run(bvh, stack);
@@ -214,7 +221,7 @@ __device__ __forceinline__ bool trace_closest(const DeviceBvh& bvh, float3 o, fl
 __device__ __forceinline__ bool trace_any_front(const DeviceBvh& bvh, float3 o, float3 d, float tmin, float tmax)
 {
     if (bvh.n_tris == 0) return false;
-    Traversal<true> T;
+    Traversal<kAny> T;
     int2 stack[kStackSize];
     T.begin(o, d, tmin, tmax);
     T.run(bvh, stack);

@@ -158,35 +158,60 @@ __device__ __forceinline__ void shadow_resolve(const PathState& ps, uint32_t pid
     }
 }
 
-// ------------------------------------------------------------------ k_trace<ANY>  (optixTrace)
-// Persistent warps with dynamic ray fetch: every warp pulls rays from the stage queue through one
+// ------------------------------------------------------------------ k_trace  (optixTrace)
+// Persistent warps with dynamic ray fetch: every warp pulls rays from the stage queues through one
 // warp-aggregated atomicAdd and REPLACES terminated lanes while the others keep their traversal state
-// in registers, so a few long rays do not hold 31 idle lanes hostage (any-hit rays terminate at wildly
-// different times).  ANY=false: closest hit of q.cur (the radiance ray, deviceProgram.cu:196-222);
-// ANY=true: occlusion of q.shadow (:224-248) followed by the NEE accumulate of SampleLights (:323-341).
-constexpr int kFetchMin = 8;          // refill as soon as this many lanes are idle
+// in registers, so a few long rays do not hold 31 idle lanes hostage.  One launch serves BOTH ray
+// kinds of a wavefront iteration: the radiance rays q.cur[0..counts[0]) (closest hit, reference
+// deviceProgram.cu:196-222) followed by the shadow rays q.shadow[0..counts[shadow_slot]) of the previous
+// shading pass (any front-facing hit, :224-248, then the NEE accumulate of SampleLights :323-341) --
+// they are independent, and together they keep the machine filled through the late, thin bounces.
+#ifndef FOVPT_FETCH_MIN
+#define FOVPT_FETCH_MIN 8
+#endif
+#ifndef FOVPT_TRACE_BLOCKS
+#define FOVPT_TRACE_BLOCKS 8
+#endif
+#ifndef FOVPT_LEAF_NUM
+#define FOVPT_LEAF_NUM 1      // run the leaf phase when LEAF_NUM * lanes_at_leaf > LEAF_DEN * lanes_at_node
+#define FOVPT_LEAF_DEN 1
+#endif
+#ifndef FOVPT_ROUNDS
+#define FOVPT_ROUNDS 4        // thin launches use fewer warps so that each still refills about this many times
+#endif
+constexpr int kFetchMin = FOVPT_FETCH_MIN;          // refill as soon as this many lanes are idle
 
-template <bool ANY>
-__global__ void __launch_bounds__(128) k_trace(SceneDev S, PathState ps, Queues q, float tmin, float tmax, DevStats* __restrict__ stats)
+__global__ void __launch_bounds__(128, FOVPT_TRACE_BLOCKS) k_trace(SceneDev S, PathState ps, Queues q, int shadow_slot, float tmin, float tmax,
+                                                                    DevStats* __restrict__ stats)
 {
     constexpr unsigned FULL = 0xffffffffu;
-    const uint32_t n = ANY ? q.counts[2] : q.counts[0];
-    const uint32_t* __restrict__ queue = ANY ? q.shadow : q.cur;
-    uint32_t* fetch = q.counts + (ANY ? 4 : 3);
-    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(ANY ? &stats->shadow_rays : &stats->radiance_rays, (unsigned long long)n);
-    if (n == 0 || S.bvh.n_tris == 0) {
-        if (!ANY) for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-            ps.hit[queue[i]] = make_float4(0.f, 0.f, 0.f, __int_as_float((int)kNoHit));
-        else for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-            shadow_resolve(ps, queue[i], false);
+    constexpr bool ANY = false;  (void)ANY;
+    const uint32_t n_closest = q.counts[0], n_any = q.counts[shadow_slot];
+    const uint32_t n = n_closest + n_any;
+    uint32_t* fetch = q.counts + 3;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        atomicAdd(&stats->radiance_rays, (unsigned long long)n_closest);
+        atomicAdd(&stats->shadow_rays, (unsigned long long)n_any);
+    }
+    if (n == 0) return;
+    if (S.bvh.n_tris == 0) {                                   // empty scene: every ray misses
+        for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+            if (i < n_closest) ps.hit[q.cur[i]] = make_float4(0.f, 0.f, 0.f, __int_as_float((int)kNoHit));
+            else shadow_resolve(ps, q.shadow[i - n_closest], false);
+        }
         return;
     }
+    // thin launch: leave whole blocks idle so that the active warps each see ~FOVPT_ROUNDS refills
+    if ((unsigned long long)blockIdx.x * (128ull * FOVPT_ROUNDS) >= (unsigned long long)n && blockIdx.x >= 148u) return;
     const unsigned lane = threadIdx.x & 31u;
-    Traversal<ANY> T;
+    Traversal<kMixed> T;
     int2 stack[kStackSize];
     uint32_t pid = 0;
     bool have = false, exhausted = false;
     T.cur = kDone;
+#ifdef FOVPT_TRACE_STATS
+    unsigned long long st_node_exec = 0, st_node_lanes = 0, st_leaf_exec = 0, st_leaf_lanes = 0, st_leaf_tris = 0, st_leaf_nmax = 0, st_fetch = 0;
+#endif
     for (;;) {
         const unsigned idle = __ballot_sync(FULL, !have);
         if (idle == FULL || (!exhausted && __popc(idle) >= kFetchMin)) {
@@ -197,9 +222,11 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev S, PathState ps, Queues 
                 base = __shfl_sync(FULL, base, 0);
                 const uint32_t mine = base + __popc(idle & ((1u << lane) - 1u));
                 if (!have && mine < n) {
-                    pid = __ldg(&queue[mine]);
-                    const float4 o = ps.ray_o[pid], d = ANY ? ps.shw_d[pid] : ps.ray_d[pid];
+                    const bool is_any = mine >= n_closest;
+                    pid = is_any ? __ldg(&q.shadow[mine - n_closest]) : __ldg(&q.cur[mine]);
+                    const float4 o = ps.ray_o[pid], d = is_any ? ps.shw_d[pid] : ps.ray_d[pid];
                     T.begin(make_float3(o.x, o.y, o.z), make_float3(d.x, d.y, d.z), tmin, tmax);
+                    T.any = is_any;
                     have = true;
                 }
                 if (base + (uint32_t)want >= n) exhausted = true;
@@ -210,15 +237,21 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev S, PathState ps, Queues 
             // each iteration runs the step kind most lanes are waiting for; the others keep their state
             const bool node = have && T.at_node(), leaf = have && T.at_leaf();
             const unsigned mn = __ballot_sync(FULL, node), ml = __ballot_sync(FULL, leaf);
-            if (__popc(mn) >= __popc(ml)) {
+            if (FOVPT_LEAF_NUM * __popc(ml) <= FOVPT_LEAF_DEN * __popc(mn)) {
+#ifdef FOVPT_TRACE_STATS
+                st_node_exec++; st_node_lanes += __popc(mn);
+#endif
                 if (node) T.node_step(S.bvh, stack);
             } else {
                 const uint32_t nmax = __reduce_max_sync(FULL, leaf ? leaf_count(T.cur) : 0u);
+#ifdef FOVPT_TRACE_STATS
+                st_leaf_exec++; st_leaf_lanes += __popc(ml); st_leaf_nmax += nmax; st_leaf_tris += __reduce_add_sync(FULL, leaf ? leaf_count(T.cur) : 0u);
+#endif
                 if (leaf) T.leaf_step(S.bvh, stack, nmax);
             }
             if (have && T.done()) {
-                if (!ANY) ps.hit[pid] = T.found() ? make_float4(T.best_t, T.best_u, T.best_v, __int_as_float((int)T.best_k))
-                                                  : make_float4(0.f, 0.f, 0.f, __int_as_float((int)kNoHit));
+                if (!T.any) ps.hit[pid] = T.found() ? make_float4(T.best_t, T.best_u, T.best_v, __int_as_float((int)T.best_k))
+                                                   : make_float4(0.f, 0.f, 0.f, __int_as_float((int)kNoHit));
                 else shadow_resolve(ps, pid, T.found());
                 have = false;
             }
@@ -226,12 +259,22 @@ __global__ void __launch_bounds__(128) k_trace(SceneDev S, PathState ps, Queues 
             if (act == 0u) break;
             if (!exhausted && __popc(act) <= 32 - kFetchMin) break;
         }
+#ifdef FOVPT_TRACE_STATS
+        st_fetch++;
+#endif
     }
+#ifdef FOVPT_TRACE_STATS
+    if (lane == 0) {
+        unsigned long long* d = stats->dbg;
+        atomicAdd(d + 0, st_node_exec); atomicAdd(d + 1, st_node_lanes); atomicAdd(d + 2, st_leaf_exec); atomicAdd(d + 3, st_leaf_lanes);
+        atomicAdd(d + 4, st_leaf_tris); atomicAdd(d + 5, st_leaf_nmax); atomicAdd(d + 6, st_fetch); atomicAdd(d + 7, (unsigned long long)(blockIdx.x == 0 && threadIdx.x == 0 ? n : 0));
+    }
+#endif
 }
 
 // ------------------------------------------------------------------ k_shade  (closest-hit / miss program)
 template <bool FAST>
-__global__ void __launch_bounds__(128) k_shade(FrameDev F, SceneDev S, PathState ps, Queues q)
+__global__ void __launch_bounds__(128) k_shade(FrameDev F, SceneDev S, PathState ps, Queues q, int shadow_slot)
 {
     const uint32_t n = q.counts[0];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -325,7 +368,7 @@ __global__ void __launch_bounds__(128) k_shade(FrameDev F, SceneDev S, PathState
             ps.shw_d[pid] = make_float4(wi.x, wi.y, wi.z, 0.f);
             const uint32_t mode = (catcher ? 1u : 0u) | (depth == 0 ? 2u : 0u);
             ps.pend[pid] = make_float4(pending.x, pending.y, pending.z, __int_as_float((int)mode));
-            q.shadow[queue_push(&q.counts[2])] = pid;
+            q.shadow[queue_push(&q.counts[shadow_slot])] = pid;
         }
         bool cont = commit;
         if (commit) {
@@ -432,14 +475,14 @@ __global__ void k_trace_query(SceneDev S, const float* __restrict__ rays, size_t
             int2 stack[kStackSize];
             if (S.bvh.n_tris == 0) { tri[i] = mode == 2 ? -1 : 0; }
             else if (mode == 2) {
-                Traversal<false> T; T.begin(o, d, r[3], r[7]);
+                Traversal<kClosest> T; T.begin(o, d, r[3], r[7]);
                 while (!T.done()) {
                     if (T.at_node()) { nodes += 1.f; T.node_step(S.bvh, stack); }
                     else { leaves += 1.f; tris += (float)leaf_count(T.cur); T.leaf_step(S.bvh, stack, leaf_count(T.cur)); }
                 }
                 tri[i] = T.found() ? (int32_t)T.best_gid : -1;
             } else {
-                Traversal<true> T; T.begin(o, d, r[3], r[7]);
+                Traversal<kAny> T; T.begin(o, d, r[3], r[7]);
                 while (!T.done()) {
                     if (T.at_node()) { nodes += 1.f; T.node_step(S.bvh, stack); }
                     else { leaves += 1.f; tris += (float)leaf_count(T.cur); T.leaf_step(S.bvh, stack, leaf_count(T.cur)); }
@@ -451,9 +494,11 @@ __global__ void k_trace_query(SceneDev S, const float* __restrict__ rays, size_t
     }
 }
 
-__global__ void k_swap_counts(uint32_t* counts)
+// end of a wavefront iteration: next becomes cur, the fetch cursor rewinds, and the shadow counter that the
+// trace launch of this iteration consumed (`consumed_slot`) is cleared for the shading pass after next
+__global__ void k_swap_counts(uint32_t* counts, int consumed_slot)
 {
-    if (threadIdx.x == 0 && blockIdx.x == 0) { counts[0] = counts[1]; counts[1] = 0; counts[2] = 0; counts[3] = 0; counts[4] = 0; }
+    if (threadIdx.x == 0 && blockIdx.x == 0) { counts[0] = counts[1]; counts[1] = 0; counts[3] = 0; counts[consumed_slot] = 0; }
 }
 
 // ------------------------------------------------------------------ launch wrappers (host)
@@ -466,20 +511,16 @@ void launch_raygen(const LaunchCfg& L, const FrameDev& F, int pass, unsigned row
 {
     k_raygen<<<L.grid_light, 256, 0, L.stream>>>(F, pass, row0, row1, pid_base, needed, ps, q, li_backplate, stats);
 }
-void launch_extend(const LaunchCfg& L, const SceneDev& S, const PathState& ps, const Queues& q, float tmin, float tmax, DevStats* stats)
+void launch_trace(const LaunchCfg& L, const SceneDev& S, const PathState& ps, const Queues& q, int shadow_slot, float tmin, float tmax, DevStats* stats)
 {
-    k_trace<false><<<L.grid_trace, 128, 0, L.stream>>>(S, ps, q, tmin, tmax, stats);
+    k_trace<<<L.grid_trace, 128, 0, L.stream>>>(S, ps, q, shadow_slot, tmin, tmax, stats);
 }
-void launch_shadow(const LaunchCfg& L, const SceneDev& S, const PathState& ps, const Queues& q, float tmin, float tmax, DevStats* stats)
+void launch_shade(const LaunchCfg& L, const FrameDev& F, const SceneDev& S, const PathState& ps, const Queues& q, int shadow_slot, bool fast)
 {
-    k_trace<true><<<L.grid_trace, 128, 0, L.stream>>>(S, ps, q, tmin, tmax, stats);
+    if (fast) k_shade<true><<<L.grid_shade, 128, 0, L.stream>>>(F, S, ps, q, shadow_slot);
+    else k_shade<false><<<L.grid_shade, 128, 0, L.stream>>>(F, S, ps, q, shadow_slot);
 }
-void launch_shade(const LaunchCfg& L, const FrameDev& F, const SceneDev& S, const PathState& ps, const Queues& q, bool fast)
-{
-    if (fast) k_shade<true><<<L.grid_shade, 128, 0, L.stream>>>(F, S, ps, q);
-    else k_shade<false><<<L.grid_shade, 128, 0, L.stream>>>(F, S, ps, q);
-}
-void launch_swap(const LaunchCfg& L, uint32_t* counts) { k_swap_counts<<<1, 32, 0, L.stream>>>(counts); }
+void launch_swap(const LaunchCfg& L, uint32_t* counts, int consumed_slot) { k_swap_counts<<<1, 32, 0, L.stream>>>(counts, consumed_slot); }
 void launch_resolve_li(const LaunchCfg& L, const FrameDev& F, int pass, unsigned row0, unsigned row1, unsigned pid_base,
                        const uint8_t* needed, const PathState& ps, const float4* li_backplate, float4* li_color)
 {
@@ -501,10 +542,7 @@ void launch_trace_query(const LaunchCfg& L, const SceneDev& S, const float* rays
 
 void query_occupancy(int* extend_blocks_per_sm, int* shade_blocks_per_sm)
 {
-    int a = 0, b = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_trace<false>, 128, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_trace<true>, 128, 0);
-    *extend_blocks_per_sm = a < b ? a : b;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(extend_blocks_per_sm, k_trace, 128, 0);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(shade_blocks_per_sm, k_shade<false>, 128, 0);
 }
 

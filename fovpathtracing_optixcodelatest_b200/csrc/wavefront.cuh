@@ -3,7 +3,8 @@
 // One camera path ("sample", one iteration of reference deviceProgram.cu:448-539) owns slot `pid`
 // in a set of SoA arrays; queues of pids connect the stages:
 //
-//   k_owner_map -> k_raygen -> [ k_extend -> k_shade -> k_shadow ] x (max_depth+1) -> k_resolve_li -> k_resolve_px
+//   k_owner_map -> k_raygen -> [ k_trace -> k_shade ] x (max_depth+1) -> k_trace -> k_resolve_li -> k_resolve_px
+// (k_trace(i) extends the radiance rays of iteration i and resolves the shadow rays emitted by k_shade(i-1))
 //
 // pid = pass.pid_base + li * pass.spp + k, with li the row-major launch index of the pass
 // (optixGetLaunchIndex) and k the sample number, so the spp samples of one launch index are
@@ -81,9 +82,12 @@ struct Queues {
     uint32_t* cur;
     uint32_t* next;
     uint32_t* shadow;
-    uint32_t* counts;   // [0] cur [1] next [2] shadow [3] fetch cursor of k_trace<closest> [4] of k_trace<any>  (8 words)
+    uint32_t* counts;   // [0] cur [1] next [2],[5] shadow (alternating per iteration) [3] fetch cursor of k_trace  (8 words)
 };
 
-struct DevStats { unsigned long long samples, radiance_rays, shadow_rays; };
+struct DevStats {
+    unsigned long long samples, radiance_rays, shadow_rays;
+    unsigned long long dbg[16];     // -DFOVPT_TRACE_STATS builds only: warp-step counters of k_trace (closest 0..7, any 8..15)
+};
 
 }  // namespace fovpt

@@ -18,10 +18,10 @@ struct LaunchCfg {
 void launch_owner_map(const LaunchCfg&, const FrameDev&, uint32_t* owner_map, uint8_t* needed);
 void launch_raygen(const LaunchCfg&, const FrameDev&, int pass, unsigned row0, unsigned row1, unsigned pid_base,
                    const uint8_t* needed, const PathState&, const Queues&, float4* li_backplate, DevStats*);
-void launch_extend(const LaunchCfg&, const SceneDev&, const PathState&, const Queues&, float tmin, float tmax, DevStats*);
-void launch_shadow(const LaunchCfg&, const SceneDev&, const PathState&, const Queues&, float tmin, float tmax, DevStats*);
-void launch_shade(const LaunchCfg&, const FrameDev&, const SceneDev&, const PathState&, const Queues&, bool fast);
-void launch_swap(const LaunchCfg&, uint32_t* counts);
+// shadow_slot: index into Queues::counts (2 or 5, alternating per iteration) of the shadow-ray counter in use
+void launch_trace(const LaunchCfg&, const SceneDev&, const PathState&, const Queues&, int shadow_slot, float tmin, float tmax, DevStats*);
+void launch_shade(const LaunchCfg&, const FrameDev&, const SceneDev&, const PathState&, const Queues&, int shadow_slot, bool fast);
+void launch_swap(const LaunchCfg&, uint32_t* counts, int consumed_slot);
 void launch_resolve_li(const LaunchCfg&, const FrameDev&, int pass, unsigned row0, unsigned row1, unsigned pid_base,
                        const uint8_t* needed, const PathState&, const float4* li_backplate, float4* li_color);
 void launch_resolve_px(const LaunchCfg&, const FrameDev&, const uint32_t* owner_map, const float4* li_color, bool fast);

@@ -53,10 +53,11 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise RuntimeError(f"{LIB_PATH} is missing: build it with __graft_entry__.build() "
+    path = os.environ.get("FOVPT_LIB", LIB_PATH)        # developer knob: A/B-test another build of the same library
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: build it with __graft_entry__.build() "
                            f"(make -C fovpathtracing_optixcodelatest_b200/csrc); there is no CPU fallback")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     vp, i32, u64p = C.c_void_p, C.c_int, C.POINTER(C.c_uint64)
     L.fovpt_create.argtypes = [C.POINTER(vp), i32, vp]
     L.fovpt_destroy.argtypes = [vp]

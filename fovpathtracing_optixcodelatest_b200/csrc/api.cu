@@ -46,6 +46,7 @@ struct fovpt_ctx {
 
     // probe
     float4* p_data = nullptr; float *p_pdfX = nullptr, *p_cdfX = nullptr, *p_pdfY = nullptr, *p_cdfY = nullptr;
+    uint16_t *p_gy = nullptr, *p_gx = nullptr;       // CDF guide tables (shade.cuh ProbeGuide), valid for p_cdfX / p_cdfY
 
     // frame buffers owned by the library (fovpt_resize)
     int fb_w = 0, fb_h = 0;
@@ -164,11 +165,14 @@ struct PassHost { unsigned lw, lh, factor; int fill; float r_inner, r_outer; uns
 
 void fill_frame(fovpt_ctx* c, const LaunchParamsBlob& lp, const std::vector<PassHost>& passes, FrameDev* F, size_t* total_li)
 {
-    memset(F, 0, sizeof(*F));
+    *F = FrameDev{};
     F->w = lp.frame.size_x; F->h = lp.frame.size_y;
     F->cx = lp.frame.c_x; F->cy = lp.frame.c_y;
     memcpy(F->eye, lp.camera.eye, 12); memcpy(F->U, lp.camera.U, 12); memcpy(F->V, lp.camera.V, 12); memcpy(F->W, lp.camera.W, 12);
     F->probe = lp.probe;
+    if (c->p_gy && lp.probe.cdfValuesX == c->p_cdfX && lp.probe.cdfValuesY == c->p_cdfY && lp.probe.width <= 65535 && lp.probe.height <= 65535) {
+        F->guide.gy = c->p_gy; F->guide.gx = c->p_gx;
+    }
     F->accum = lp.frame.accum_buffer; F->frame = lp.frame.frame_buffer;
     F->npass = (int)passes.size();
     size_t li = 0;
@@ -377,7 +381,7 @@ int fovpt_destroy(fovpt_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_scene(c); free_paths(c);
-    cudaFree(c->p_data); cudaFree(c->p_pdfX); cudaFree(c->p_cdfX); cudaFree(c->p_pdfY); cudaFree(c->p_cdfY);
+    cudaFree(c->p_data); cudaFree(c->p_pdfX); cudaFree(c->p_cdfX); cudaFree(c->p_pdfY); cudaFree(c->p_cdfY); cudaFree(c->p_gy); cudaFree(c->p_gx);
     cudaFree(c->fb_accum); cudaFree(c->fb_frame); cudaFree(c->li_backplate); cudaFree(c->li_color); cudaFree(c->needed);
     cudaFree(c->owner_map); cudaFree(c->q.counts); cudaFree(c->d_stats); cudaFree(c->d_tile_owner);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -508,7 +512,8 @@ int fovpt_probe_upload(fovpt_ctx* c, int w, int h, const float* rgba, const floa
     if (w <= 0 || h <= 0 || !rgba || !pdfX || !cdfX || !pdfY || !cdfY || !probe_out64) return fail(c, "Probe Data is not valid");   // Probe.h:104-105
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    cudaFree(c->p_data); cudaFree(c->p_pdfX); cudaFree(c->p_cdfX); cudaFree(c->p_pdfY); cudaFree(c->p_cdfY);
+    cudaFree(c->p_data); cudaFree(c->p_pdfX); cudaFree(c->p_cdfX); cudaFree(c->p_pdfY); cudaFree(c->p_cdfY); cudaFree(c->p_gy); cudaFree(c->p_gx);
+    c->p_gy = c->p_gx = nullptr;
     const size_t n = (size_t)w * h;
     CU(dmalloc(&c->p_data, n)); CU(dmalloc(&c->p_pdfX, n)); CU(dmalloc(&c->p_cdfX, n)); CU(dmalloc(&c->p_pdfY, (size_t)h)); CU(dmalloc(&c->p_cdfY, (size_t)h));
     CU(cudaMemcpy(c->p_data, rgba, n * 16, cudaMemcpyHostToDevice));
@@ -521,6 +526,13 @@ int fovpt_probe_upload(fovpt_ctx* c, int w, int h, const float* rgba, const floa
     if (offset) memcpy(pb.offset, offset, 12);
     pb.pdfValuesX = c->p_pdfX; pb.cdfValuesX = c->p_cdfX; pb.pdfValuesY = c->p_pdfY; pb.cdfValuesY = c->p_cdfY;
     memcpy(probe_out64, &pb, sizeof(pb));
+    if (w <= 65535 && h <= 65535) {                       // guide tables for the CDF inversion (exactly equivalent search)
+        CU(dmalloc(&c->p_gy, (size_t)kGuide + 1)); CU(dmalloc(&c->p_gx, (size_t)h * (kGuide + 1)));
+        launch_probe_guides(c->L, pb, c->p_gy, c->p_gx);
+        c->launches++;
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaGetLastError());
+    }
     return 0;
 }
 
@@ -690,10 +702,12 @@ int fovpt_get_stats(fovpt_ctx* c, fovpt_stats* s)
     memset(s, 0, sizeof(*s));
     s->samples = d.samples; s->radiance_rays = d.radiance_rays; s->shadow_rays = d.shadow_rays;
 #ifdef FOVPT_TRACE_STATS
-    for (int k = 0; k < 2; ++k) {
-        const unsigned long long* q = d.dbg + 8 * k;
-        fprintf(stderr, "[trace stats %s] node_exec %llu lanes/exec %.2f | leaf_exec %llu lanes/exec %.2f tris/lane %.2f nmax %.2f | fetch rounds %llu\n", k ? "any" : "closest",
-                q[0], q[0] ? (double)q[1] / q[0] : 0., q[2], q[2] ? (double)q[3] / q[2] : 0., q[3] ? (double)q[4] / q[3] : 0., q[2] ? (double)q[5] / q[2] : 0., q[6]);
+    {
+        const unsigned long long* q = d.dbg;
+        fprintf(stderr, "[trace stats] node_exec %llu lanes/exec %.2f (per exec: blocked %.2f, empty while queue open %.2f, empty after queue drained %.2f) | "
+                        "leaf_exec %llu lanes/exec %.2f tris/lane %.2f nmax %.2f | fetch rounds %llu\n",
+                q[0], q[0] ? (double)q[1] / q[0] : 0., q[0] ? (double)q[10] / q[0] : 0., q[0] ? (double)q[8] / q[0] : 0., q[0] ? (double)q[9] / q[0] : 0.,
+                q[2], q[2] ? (double)q[3] / q[2] : 0., q[3] ? (double)q[4] / q[3] : 0., q[2] ? (double)q[5] / q[2] : 0., q[6]);
     }
 #endif
     s->kernel_launches = c->launches; s->frames = c->frames;
@@ -725,7 +739,7 @@ int fovpt_bvh_read(fovpt_ctx* c, void* nodes64, uint32_t* sorted_tri_ids)
 {
     if (!c || !c->committed) return 1;
     cudaSetDevice(c->device);
-    if (nodes64 && c->bvh.n_nodes) CU(cudaMemcpy(nodes64, c->bvh.nodes, (size_t)c->bvh.n_nodes * 128, cudaMemcpyDeviceToHost));
+    if (nodes64 && c->bvh.n_nodes) CU(cudaMemcpy(nodes64, c->bvh.nodes, (size_t)c->bvh.n_nodes * 64, cudaMemcpyDeviceToHost));
     if (sorted_tri_ids && c->bvh.n_tris) CU(cudaMemcpy(sorted_tri_ids, c->bvh.sorted_ids, (size_t)c->bvh.n_tris * 4, cudaMemcpyDeviceToHost));
     return 0;
 }

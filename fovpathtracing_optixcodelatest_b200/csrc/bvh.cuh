@@ -2,13 +2,17 @@
 // (reference call sites: PT_sv5_/deviceProgram.cu:196-222 radiance / :224-248 occlusion).
 //
 // Layout in HBM (all 32-byte aligned, read through the read-only path with 256-bit loads):
-//   nodes : 128 B per 4-wide inner node = 8 x float4, structure-of-arrays over the 4 child slots
-//             q0 = lo.x[0..3]   q1 = hi.x[0..3]   q2 = lo.y[0..3]   q3 = hi.y[0..3]
-//             q4 = lo.z[0..3]   q5 = hi.z[0..3]   q6 = child[0..3] (int bits)   q7 = 0
+//   nodes : 64 B per 4-wide inner node = 4 x uint4; child boxes are quantised to 8 bits per plane on
+//           a per-node grid  plane(q) = p + q * 2^(e-127)  (snapped outward, so always conservative):
+//             n0 = (bits(p.x), bits(p.y), bits(p.z), e.x | e.y << 8 | e.z << 16)
+//             n1 = child[0..3]
+//             n2 = (qlo.x[0..3], qhi.x[0..3], qlo.y[0..3], qhi.y[0..3])      one byte per child slot
+//             n3 = (qlo.z[0..3], qhi.z[0..3], 0, 0)
 //           child >= 0 : index of an inner node;  child < 0 : leaf,
 //           ~child = (first_sorted_tri << 2) | (count - 1), count in 1..4;
-//           an unused slot has lo = hi = +inf on every axis: its slab interval is empty for every ray
-//           with finite tmax, so it can never be entered.
+//           an unused slot has the inverted byte box lo = 255, hi = 0 and can never be entered.
+//           Two sectors per node instead of four: the traversal kernels are bound by L1 sector
+//           throughput (profiles/), so bytes per visited node are what buys speed.
 //   tris  : 48 B per triangle in leaf (Morton) order = 3 x float4
 //             (v0.xyz, bits(global id)), (e1.xyz, 0), (e2.xyz, 0)      [fx_make_tri of fovpt_exact.h]
 // Algorithmic bytes per ray are counted on the oracle's canonical binary tree:
@@ -22,7 +26,7 @@
 namespace fovpt {
 
 struct DeviceBvh {
-    const float4* nodes = nullptr;
+    const uint4*  nodes = nullptr;
     const float4* tris = nullptr;
     uint32_t      n_nodes = 0;
     uint32_t      n_tris = 0;
@@ -35,13 +39,13 @@ struct HitRec { float t, u, v; uint32_t k; uint32_t gid; };   // k = sorted tria
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 
-struct f8 { float4 a, b; };
+struct u8x { uint4 a, b; };
 // one 256-bit read-only load (LDG.E.256.CONSTANT); p must be 32-byte aligned
-__device__ __forceinline__ f8 ldg256(const float4* p)
+__device__ __forceinline__ u8x ldg256(const uint4* p)
 {
-    f8 r;
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
+    u8x r;
+    asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r.a.x), "=r"(r.a.y), "=r"(r.a.z), "=r"(r.a.w), "=r"(r.b.x), "=r"(r.b.y), "=r"(r.b.z), "=r"(r.b.w)
                  : "l"(p));
     return r;
 }
@@ -57,17 +61,18 @@ __device__ __forceinline__ float safe_rcp(float d)
     return 1.0f / ad;
 }
 
-// slab test of one child box (origin folded into ood = o * idir).  Boxes are padded at build time
+// slab test of child slot J of a quantised node: near / far byte planes were already selected by the
+// sign of the ray direction (so an inverted box yields an empty interval), a* = 2^e * idir and
+// b* = (p - o) * idir fold the de-quantisation into one fma per plane.  Boxes are padded at build time
 // (bvh_build.cu), which is what makes the fma form conservative with respect to fx_ray_tri.
-__device__ __forceinline__ void slab(float lox, float hix, float loy, float hiy, float loz, float hiz, const float3 idir, const float3 ood,
-                                     float tmin, float tlimit, float& tn, float& tf)
-{
-    const float ax = fmaf(lox, idir.x, -ood.x), bx = fmaf(hix, idir.x, -ood.x);
-    const float ay = fmaf(loy, idir.y, -ood.y), by = fmaf(hiy, idir.y, -ood.y);
-    const float az = fmaf(loz, idir.z, -ood.z), bz = fmaf(hiz, idir.z, -ood.z);
-    tn = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), tmin));
-    tf = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), tlimit));
-}
+#define FOVPT_BYTE(w, J) ((float)(((w) >> (8 * (J))) & 0xffu))
+#define FOVPT_SLAB(J, tn, tf)                                                                                          \
+    do {                                                                                                               \
+        const float nx_ = fmaf(FOVPT_BYTE(nxw, J), ax, bx), ny_ = fmaf(FOVPT_BYTE(nyw, J), ay, by), nz_ = fmaf(FOVPT_BYTE(nzw, J), az, bz); \
+        const float fx_ = fmaf(FOVPT_BYTE(fxw, J), ax, bx), fy_ = fmaf(FOVPT_BYTE(fyw, J), ay, by), fz_ = fmaf(FOVPT_BYTE(fzw, J), az, bz); \
+        tn = fmaxf(fmaxf(nx_, ny_), fmaxf(nz_, tmin));                                                                 \
+        tf = fminf(fminf(fx_, fy_), fminf(fz_, tlimit));                                                               \
+    } while (0)
 
 __device__ __forceinline__ void cswap(int& a, int& b) { const int lo = min(a, b), hi = max(a, b); a = lo; b = hi; }
 
@@ -77,6 +82,8 @@ __device__ __forceinline__ void cswap(int& a, int& b) { const int lo = min(a, b)
 //   done()     : finished
 // Kernels run 32 rays per warp, execute per iteration the step kind that the majority of lanes is
 // waiting for, and replace finished rays from the stage queue (wavefront.cu k_trace).
+// (Tried and measured slower on C3: parking a reached leaf and descending speculatively until a second
+// leaf blocks the lane -- fuller leaf steps, but 9 % more node visits)
 //   closest : min t in (tmin, tmax), ties -> smallest global triangle id (fx_hit_better), so the
 //             result does not depend on tree shape or visiting order.
 //   any     : true iff some FRONT-facing triangle intersects (tmin, tmax)
@@ -125,16 +132,22 @@ struct Traversal {
 
     __device__ __forceinline__ void node_step(const DeviceBvh& bvh, int2* stack)
     {
-        const float4* np = bvh.nodes + 8 * (size_t)cur;
-        const f8 X = ldg256(np), Y = ldg256(np + 2), Z = ldg256(np + 4);
-        const float4 C = ldg4(np + 6);
+        const uint4* np = bvh.nodes + 4 * (size_t)cur;
+        const u8x A = ldg256(np), B = ldg256(np + 2);           // A = (n0, n1), B = (n2, n3)
         const float tlimit = is_any() ? tmax : fminf(tmax, best_t);
+        const float ax = __uint_as_float((A.a.w & 0xffu) << 23) * idir.x;
+        const float ay = __uint_as_float(((A.a.w >> 8) & 0xffu) << 23) * idir.y;
+        const float az = __uint_as_float(((A.a.w >> 16) & 0xffu) << 23) * idir.z;
+        const float bx = fmaf(__uint_as_float(A.a.x), idir.x, -ood.x);
+        const float by = fmaf(__uint_as_float(A.a.y), idir.y, -ood.y);
+        const float bz = fmaf(__uint_as_float(A.a.z), idir.z, -ood.z);
+        const bool px = idir.x >= 0.f, py = idir.y >= 0.f, pz = idir.z >= 0.f;
+        const uint32_t nxw = px ? B.a.x : B.a.y, fxw = px ? B.a.y : B.a.x;
+        const uint32_t nyw = py ? B.a.z : B.a.w, fyw = py ? B.a.w : B.a.z;
+        const uint32_t nzw = pz ? B.b.x : B.b.y, fzw = pz ? B.b.y : B.b.x;
         float tn0, tn1, tn2, tn3, tf0, tf1, tf2, tf3;
-        slab(X.a.x, X.b.x, Y.a.x, Y.b.x, Z.a.x, Z.b.x, idir, ood, tmin, tlimit, tn0, tf0);
-        slab(X.a.y, X.b.y, Y.a.y, Y.b.y, Z.a.y, Z.b.y, idir, ood, tmin, tlimit, tn1, tf1);
-        slab(X.a.z, X.b.z, Y.a.z, Y.b.z, Z.a.z, Z.b.z, idir, ood, tmin, tlimit, tn2, tf2);
-        slab(X.a.w, X.b.w, Y.a.w, Y.b.w, Z.a.w, Z.b.w, idir, ood, tmin, tlimit, tn3, tf3);
-        const int c0 = __float_as_int(C.x), c1 = __float_as_int(C.y), c2 = __float_as_int(C.z), c3 = __float_as_int(C.w);
+        FOVPT_SLAB(0, tn0, tf0); FOVPT_SLAB(1, tn1, tf1); FOVPT_SLAB(2, tn2, tf2); FOVPT_SLAB(3, tn3, tf3);
+        const int c0 = (int)A.b.x, c1 = (int)A.b.y, c2 = (int)A.b.z, c3 = (int)A.b.w;
         if (MODE == kAny) {
             // order is irrelevant for occlusion: enter the first hit child, push the others
             const bool h0 = tn0 <= tf0, h1 = tn1 <= tf1, h2 = tn2 <= tf2, h3 = tn3 <= tf3;

@@ -7,7 +7,7 @@
 //                   k_radix_hist -> k_scan_u32 -> k_radix_scatter (stable, match_any ranking)
 //   k_hierarchy     Karras 2012: one thread per inner node finds its key range and split
 //   k_refit         bottom-up AABBs, second arriver proceeds (atomic counter per node)
-//   k_collapse4     breadth-first collapse of the binary tree into the 4-wide nodes of bvh.cuh:
+//   k_collapse4     breadth-first collapse of the binary tree into the 4-wide, 8-bit-quantised nodes of bvh.cuh:
 //                   a wide node takes a binary node's two children and twice replaces the child
 //                   of largest surface area by its own two children; subtrees with <= 4 triangles
 //                   become leaves (their triangles are contiguous in Morton order).  One launch
@@ -282,16 +282,47 @@ __device__ __forceinline__ float box_area(const float4 lo, const float4 hi)
     return dx * dy + dy * dz + dz * dx;
 }
 
-__device__ __forceinline__ void write_node4(float4* __restrict__ o, const float4 lo[4], const float4 hi[4], const int enc[4], float pad)
+// Encodes one 4-wide node in the 64-byte quantised layout of bvh.cuh.  Child boxes are first padded
+// by `pad` (absorbs the rounding of the fma slab test, see the header of this file), then snapped
+// OUTWARD onto the node's 8-bit grid  plane(q) = p + q * 2^(e-127),  q in 0..255 : the check against
+// the exact (double) plane position makes the outward rounding unconditional.  Unused slots get the
+// inverted byte box lo = 255, hi = 0, which the sign-selecting slab test can never enter.
+__device__ __forceinline__ void write_node4(uint4* __restrict__ o, const float4 lo[4], const float4 hi[4], const int enc[4], int nc, float pad)
 {
-    o[0] = make_float4(lo[0].x - pad, lo[1].x - pad, lo[2].x - pad, lo[3].x - pad);
-    o[1] = make_float4(hi[0].x + pad, hi[1].x + pad, hi[2].x + pad, hi[3].x + pad);
-    o[2] = make_float4(lo[0].y - pad, lo[1].y - pad, lo[2].y - pad, lo[3].y - pad);
-    o[3] = make_float4(hi[0].y + pad, hi[1].y + pad, hi[2].y + pad, hi[3].y + pad);
-    o[4] = make_float4(lo[0].z - pad, lo[1].z - pad, lo[2].z - pad, lo[3].z - pad);
-    o[5] = make_float4(hi[0].z + pad, hi[1].z + pad, hi[2].z + pad, hi[3].z + pad);
-    o[6] = make_float4(__int_as_float(enc[0]), __int_as_float(enc[1]), __int_as_float(enc[2]), __int_as_float(enc[3]));
-    o[7] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float p[3] = {3.0e38f, 3.0e38f, 3.0e38f}, top[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (int j = 0; j < nc; ++j) {
+        p[0] = fminf(p[0], lo[j].x - pad); p[1] = fminf(p[1], lo[j].y - pad); p[2] = fminf(p[2], lo[j].z - pad);
+        top[0] = fmaxf(top[0], hi[j].x + pad); top[1] = fmaxf(top[1], hi[j].y + pad); top[2] = fmaxf(top[2], hi[j].z + pad);
+    }
+    uint32_t ebits[3]; double scale[3];
+    for (int a = 0; a < 3; ++a) {
+        const double ext = (double)top[a] - (double)p[a];
+        int e = 0;
+        (void)frexp(fmax(ext, 1e-30) / 255.0, &e);             // ext/255 = m * 2^e, m in [0.5,1)  ->  2^e >= ext/255
+        e = max(-120, min(e, 120));
+        ebits[a] = (uint32_t)(e + 127);
+        scale[a] = ldexp(1.0, e);
+    }
+    uint32_t qlo[3] = {0, 0, 0}, qhi[3] = {0, 0, 0};
+    for (int j = 0; j < 4; ++j) {
+        uint32_t l3[3] = {255u, 255u, 255u}, h3[3] = {0u, 0u, 0u};
+        if (j < nc) {
+            const float cl[3] = {lo[j].x - pad, lo[j].y - pad, lo[j].z - pad}, ch[3] = {hi[j].x + pad, hi[j].y + pad, hi[j].z + pad};
+            for (int a = 0; a < 3; ++a) {
+                int ql = (int)floor(((double)cl[a] - (double)p[a]) / scale[a]);
+                int qh = (int)ceil(((double)ch[a] - (double)p[a]) / scale[a]);
+                ql = max(0, min(ql, 255)); qh = max(0, min(qh, 255));
+                while (ql > 0 && (double)p[a] + ql * scale[a] > (double)cl[a]) --ql;
+                while (qh < 255 && (double)p[a] + qh * scale[a] < (double)ch[a]) ++qh;
+                l3[a] = (uint32_t)ql; h3[a] = (uint32_t)qh;
+            }
+        }
+        for (int a = 0; a < 3; ++a) { qlo[a] |= l3[a] << (8 * j); qhi[a] |= h3[a] << (8 * j); }
+    }
+    o[0] = make_uint4(__float_as_uint(p[0]), __float_as_uint(p[1]), __float_as_uint(p[2]), ebits[0] | (ebits[1] << 8) | (ebits[2] << 16));
+    o[1] = make_uint4((uint32_t)enc[0], (uint32_t)enc[1], (uint32_t)enc[2], (uint32_t)enc[3]);
+    o[2] = make_uint4(qlo[0], qhi[0], qlo[1], qhi[1]);
+    o[3] = make_uint4(qlo[2], qhi[2], 0u, 0u);
 }
 
 // one level: items_in[0 .. counts[level]) -> nodes4 + items_out[0 .. counts[level+1])
@@ -301,7 +332,7 @@ __global__ void k_collapse4(const CollapseItem* __restrict__ items_in, CollapseI
                             const int* __restrict__ rng_first, const int* __restrict__ rng_last,
                             const uint32_t* __restrict__ sorted_ids, const float4* __restrict__ box_lo,
                             const float4* __restrict__ box_hi, const float4* __restrict__ nlo, const float4* __restrict__ nhi,
-                            int leaf_max, float pad, float4* __restrict__ nodes4)
+                            int leaf_max, float pad, uint4* __restrict__ nodes4)
 {
     const uint32_t n = counts[level];
     for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < n; it += gridDim.x * blockDim.x) {
@@ -331,9 +362,8 @@ __global__ void k_collapse4(const CollapseItem* __restrict__ items_in, CollapseI
         float4 lo[4], hi[4]; int enc[4];
         int k = 0;
         for (int j = 0; j < 4; ++j) {
-            if (j >= nc) {                                                         // empty slot: inverted box, never hit
-                const float inf = __int_as_float(0x7f800000);
-                lo[j] = make_float4(inf, inf, inf, 0.f); hi[j] = lo[j];
+            if (j >= nc) {                                                         // unused slot (write_node4 gives it an inverted box)
+                lo[j] = make_float4(0.f, 0.f, 0.f, 0.f); hi[j] = lo[j];
                 enc[j] = 0x7fffffff;
             } else if (c[j] < 0) {
                 const int pos = ~c[j];
@@ -352,20 +382,20 @@ __global__ void k_collapse4(const CollapseItem* __restrict__ items_in, CollapseI
                 }
             }
         }
-        write_node4(nodes4 + 8 * (size_t)item.node4, lo, hi, enc, pad);
+        write_node4(nodes4 + 4 * (size_t)item.node4, lo, hi, enc, nc, pad);
     }
 }
 
-// scenes with <= leaf_max triangles: a root whose slot 0 is the only leaf
-__global__ void k_emit_single4(int n, float4* __restrict__ nodes4)
+// scenes with <= leaf_max triangles: a root whose slot 0 is the only leaf, boxed by the scene bounds
+__global__ void k_emit_single4(int n, const int* __restrict__ bounds, float pad, uint4* __restrict__ nodes4)
 {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    const float big = 3.0e38f, inf = __int_as_float(0x7f800000);
     float4 lo[4], hi[4]; int enc[4];
-    for (int j = 0; j < 4; ++j) { lo[j] = make_float4(inf, inf, inf, 0.f); hi[j] = lo[j]; enc[j] = 0x7fffffff; }
-    lo[0] = make_float4(-big, -big, -big, 0.f); hi[0] = make_float4(big, big, big, 0.f);
+    for (int j = 0; j < 4; ++j) { lo[j] = make_float4(0.f, 0.f, 0.f, 0.f); hi[j] = lo[j]; enc[j] = 0x7fffffff; }
+    lo[0] = make_float4(ordered_as_float(bounds[0]), ordered_as_float(bounds[1]), ordered_as_float(bounds[2]), 0.f);
+    hi[0] = make_float4(ordered_as_float(bounds[3]), ordered_as_float(bounds[4]), ordered_as_float(bounds[5]), 0.f);
     enc[0] = ~(int)((0u << 2) | (uint32_t)(n - 1));
-    write_node4(nodes4, lo, hi, enc, 0.f);
+    write_node4(nodes4, lo, hi, enc, 1, pad);
 }
 
 __global__ void k_seed_collapse(CollapseItem* items, uint32_t* counts, uint32_t* node_counter)
@@ -437,7 +467,7 @@ cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, uint32_t ntri, 
     const float pad = S * (1.0f / 65536.0f);
     out->pad = pad;
 
-    float4* tri_sorted = nullptr; float4* nodes = nullptr;
+    float4* tri_sorted = nullptr; uint4* nodes = nullptr;
     CK(dalloc(&tri_sorted, 3 * (size_t)ntri));
     k_gather_tris<<<gb, T, 0, st>>>(ntri, vals[cur], tri_rec, tri_sorted);
     *launches += 1;
@@ -445,8 +475,8 @@ cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, uint32_t ntri, 
     CollapseItem* items[2] = {nullptr, nullptr};
     uint32_t* lvl_counts = nullptr;
     if ((int)ntri <= leaf_max) {
-        CK(dalloc(&nodes, 8));
-        k_emit_single4<<<1, 32, 0, st>>>((int)ntri, nodes);
+        CK(dalloc(&nodes, 4));
+        k_emit_single4<<<1, 32, 0, st>>>((int)ntri, bounds, pad, nodes);
         *launches += 1;
         out->n_nodes = 1; out->max_depth = 1;
     } else {
@@ -463,7 +493,7 @@ cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, uint32_t ntri, 
         *launches += 2;
         // 4-wide collapse, one launch per level of the wide tree (at most the binary depth)
         const uint32_t cap = ninner;                     // a wide node consumes at least one binary node
-        CK(dalloc(&nodes, 8 * (size_t)cap));
+        CK(dalloc(&nodes, 4 * (size_t)cap));
         CK(dalloc(&items[0], cap)); CK(dalloc(&items[1], cap));
         CK(dalloc(&lvl_counts, (size_t)depth2 + 2));
         CK(cudaMemsetAsync(lvl_counts, 0, ((size_t)depth2 + 2) * sizeof(uint32_t), st));
@@ -483,9 +513,9 @@ cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, uint32_t ntri, 
         while (depth4 < hc.size() && hc[depth4] > 0) ++depth4;
         out->n_nodes = n4; out->max_depth = depth4;
         if (n4 < cap) {                                  // shrink to fit
-            float4* exact = nullptr;
-            CK(dalloc(&exact, 8 * (size_t)n4));
-            CK(cudaMemcpyAsync(exact, nodes, 8 * (size_t)n4 * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+            uint4* exact = nullptr;
+            CK(dalloc(&exact, 4 * (size_t)n4));
+            CK(cudaMemcpyAsync(exact, nodes, 4 * (size_t)n4 * sizeof(uint4), cudaMemcpyDeviceToDevice, st));
             CK(cudaStreamSynchronize(st));
             cudaFree(nodes); nodes = exact;
         }

@@ -6,7 +6,7 @@
 namespace fovpt {
 
 struct BuiltBvh {
-    const float4*   nodes = nullptr;       // 4 x float4 per inner node (layout: bvh.cuh)
+    const uint4*    nodes = nullptr;       // 4 x uint4 (64 B) per 4-wide inner node (layout: bvh.cuh)
     const float4*   tris = nullptr;        // 3 x float4 per triangle, leaf order
     const float4*   tri_rec = nullptr;     // 3 x float4 per triangle, global-id order
     const uint32_t* sorted_ids = nullptr;  // leaf slot -> global triangle id

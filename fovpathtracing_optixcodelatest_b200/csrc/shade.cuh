@@ -260,13 +260,31 @@ __device__ __forceinline__ int cdf_lower_bound(const float* __restrict__ a, int 
     return lo;
 }
 
+// Guide tables for the CDF inversion (built once per probe by k_probe_guides): gy[k] / gx[row][k] =
+// lower_bound(cdf, k / kGuide) for k = 0..kGuide.  A sample u with floor(u * kGuide) = k has its lower
+// bound inside [g[k], g[k+1]] (lower_bound is monotone and k / kGuide <= u < (k+1) / kGuide holds exactly,
+// kGuide being a power of two), so searching only that range returns the SAME index as the reference's
+// full-row binary search (Probe.cuh:119-136,147-153) with 1-3 dependent loads instead of 10-11 per axis.
+constexpr int kGuide = 128;
+struct ProbeGuide { const uint16_t* gy = nullptr; const uint16_t* gx = nullptr; };
+
 // one importance sample of the probe: row by cdfY then column by that row's cdfX (Probe.cuh:138-169)
 template <bool FAST>
-__device__ __forceinline__ void probe_sample(const ProbeBlob& p, fx_rng& rng, float3& dir, float3& color, float& pdf)
+__device__ __forceinline__ void probe_sample(const ProbeBlob& p, const ProbeGuide& g, fx_rng& rng, float3& dir, float3& color, float& pdf)
 {
     const float r1 = fx_rng_f(&rng), r2 = fx_rng_f(&rng);
-    const int row = cdf_lower_bound(p.cdfValuesY, 0, p.height, r1);
-    const int col = cdf_lower_bound(p.cdfValuesX, row * p.width, (row + 1) * p.width, r2) - row * p.width;
+    int row, col;
+    if (g.gy) {
+        const int ky = min((int)(r1 * (float)kGuide), kGuide - 1);
+        row = cdf_lower_bound(p.cdfValuesY, (int)__ldg(&g.gy[ky]), (int)__ldg(&g.gy[ky + 1]), r1);
+        const int kx = min((int)(r2 * (float)kGuide), kGuide - 1);
+        const uint16_t* gr = g.gx + (size_t)min(row, p.height - 1) * (kGuide + 1);
+        const int base = row * p.width;
+        col = cdf_lower_bound(p.cdfValuesX, base + (int)__ldg(&gr[kx]), base + (int)__ldg(&gr[kx + 1]), r2) - base;
+    } else {
+        row = cdf_lower_bound(p.cdfValuesY, 0, p.height, r1);
+        col = cdf_lower_bound(p.cdfValuesX, row * p.width, (row + 1) * p.width, r2) - row * p.width;
+    }
     const float4 c = __ldg(&p.data[row * p.width + col]);
     color = f3(c.x, c.y, c.z);
     pdf = __ldg(&p.pdfValuesX[row * p.width + col]) * __ldg(&p.pdfValuesY[row]);

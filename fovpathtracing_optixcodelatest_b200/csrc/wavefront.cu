@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(128, FOVPT_TRACE_BLOCKS) k_trace(SceneDev S, P
     bool have = false, exhausted = false;
     T.cur = kDone;
 #ifdef FOVPT_TRACE_STATS
-    unsigned long long st_node_exec = 0, st_node_lanes = 0, st_leaf_exec = 0, st_leaf_lanes = 0, st_leaf_tris = 0, st_leaf_nmax = 0, st_fetch = 0;
+    unsigned long long st_node_exec = 0, st_node_lanes = 0, st_leaf_exec = 0, st_leaf_lanes = 0, st_leaf_tris = 0, st_leaf_nmax = 0, st_fetch = 0, st_idle = 0, st_idle_exh = 0, st_blocked = 0;
 #endif
     for (;;) {
         const unsigned idle = __ballot_sync(FULL, !have);
@@ -237,9 +237,11 @@ __global__ void __launch_bounds__(128, FOVPT_TRACE_BLOCKS) k_trace(SceneDev S, P
             // each iteration runs the step kind most lanes are waiting for; the others keep their state
             const bool node = have && T.at_node(), leaf = have && T.at_leaf();
             const unsigned mn = __ballot_sync(FULL, node), ml = __ballot_sync(FULL, leaf);
+            const unsigned mb = ml; (void)mb;
             if (FOVPT_LEAF_NUM * __popc(ml) <= FOVPT_LEAF_DEN * __popc(mn)) {
 #ifdef FOVPT_TRACE_STATS
-                st_node_exec++; st_node_lanes += __popc(mn);
+                st_node_exec++; st_node_lanes += __popc(mn); st_blocked += __popc(mb);
+                { const int idl = 32 - __popc(__ballot_sync(FULL, have)); if (exhausted) st_idle_exh += idl; else st_idle += idl; }
 #endif
                 if (node) T.node_step(S.bvh, stack);
             } else {
@@ -267,7 +269,7 @@ __global__ void __launch_bounds__(128, FOVPT_TRACE_BLOCKS) k_trace(SceneDev S, P
     if (lane == 0) {
         unsigned long long* d = stats->dbg;
         atomicAdd(d + 0, st_node_exec); atomicAdd(d + 1, st_node_lanes); atomicAdd(d + 2, st_leaf_exec); atomicAdd(d + 3, st_leaf_lanes);
-        atomicAdd(d + 4, st_leaf_tris); atomicAdd(d + 5, st_leaf_nmax); atomicAdd(d + 6, st_fetch); atomicAdd(d + 7, (unsigned long long)(blockIdx.x == 0 && threadIdx.x == 0 ? n : 0));
+        atomicAdd(d + 4, st_leaf_tris); atomicAdd(d + 5, st_leaf_nmax); atomicAdd(d + 6, st_fetch); atomicAdd(d + 8, st_idle); atomicAdd(d + 9, st_idle_exh); atomicAdd(d + 10, st_blocked); atomicAdd(d + 7, (unsigned long long)(blockIdx.x == 0 && threadIdx.x == 0 ? n : 0));
     }
 #endif
 }
@@ -332,7 +334,7 @@ __global__ void __launch_bounds__(128) k_shade(FrameDev F, SceneDev S, PathState
 
         // next-event estimation: one probe sample, balance heuristic (:303-344 / :347-387)
         float3 wi, sky; float sky_pdf;
-        probe_sample<FAST>(F.probe, rng, wi, sky, sky_pdf);
+        probe_sample<FAST>(F.probe, F.guide, rng, wi, sky, sky_pdf);
         float3 pending = f3(0.f);
         {
             const float pdfb = bsdf_pdf<FAST>(bp, ray_eta, out_eta, N, wo, wi);
@@ -438,6 +440,20 @@ __global__ void k_resolve_px(FrameDev F, const uint32_t* __restrict__ owner_map,
     }
 }
 
+// ------------------------------------------------------------------ k_probe_guides
+// gy[k] = lower_bound(cdfY, k / kGuide); gx[row][k] = lower_bound(cdfX[row], k / kGuide), k = 0..kGuide
+__global__ void k_probe_guides(ProbeBlob p, uint16_t* __restrict__ gy, uint16_t* __restrict__ gx)
+{
+    const int per = kGuide + 1;
+    const size_t total = (size_t)(p.height + 1) * per;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(i / per), k = (int)(i % per);
+        const float v = (float)k / (float)kGuide;
+        if (r == p.height) gy[k] = (uint16_t)cdf_lower_bound(p.cdfValuesY, 0, p.height, v);
+        else gx[(size_t)r * per + k] = (uint16_t)(cdf_lower_bound(p.cdfValuesX, r * p.width, (r + 1) * p.width, v) - r * p.width);
+    }
+}
+
 // ------------------------------------------------------------------ debug / query kernels
 __global__ void k_primary_hits(FrameDev F, SceneDev S, int32_t* __restrict__ tri, float* __restrict__ tuv, float* __restrict__ dir)
 {
@@ -530,6 +546,10 @@ void launch_resolve_px(const LaunchCfg& L, const FrameDev& F, const uint32_t* ow
 {
     if (fast) k_resolve_px<true><<<L.grid_light, 256, 0, L.stream>>>(F, owner_map, li_color);
     else k_resolve_px<false><<<L.grid_light, 256, 0, L.stream>>>(F, owner_map, li_color);
+}
+void launch_probe_guides(const LaunchCfg& L, const ProbeBlob& p, uint16_t* gy, uint16_t* gx)
+{
+    k_probe_guides<<<L.grid_light, 256, 0, L.stream>>>(p, gy, gx);
 }
 void launch_primary_hits(const LaunchCfg& L, const FrameDev& F, const SceneDev& S, int32_t* tri, float* tuv, float* dir)
 {

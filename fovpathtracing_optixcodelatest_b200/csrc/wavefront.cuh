@@ -15,6 +15,7 @@
 
 #include "bvh.cuh"
 #include "fovpt_layout.h"
+#include "shade.cuh"
 
 namespace fovpt {
 
@@ -65,6 +66,7 @@ struct FrameDev {
     unsigned  cx, cy;
     float     eye[3], U[3], V[3], W[3];
     ProbeBlob probe;
+    ProbeGuide guide;           // null unless the probe's CDFs are the ones fovpt_probe_upload built guides for
     float4*   accum;
     uint32_t* frame;
     int       npass;

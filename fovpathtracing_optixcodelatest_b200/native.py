@@ -238,6 +238,6 @@ class Context:
     def bvh(self):
         nn, nt = C.c_uint64(), C.c_uint64()
         self._chk(self.L.fovpt_bvh_info(self.h, C.byref(nn), C.byref(nt)))
-        nodes = np.zeros((nn.value, 32), np.float32); ids = np.zeros(nt.value, np.uint32)
+        nodes = np.zeros((nn.value, 16), np.uint32); ids = np.zeros(nt.value, np.uint32)
         self._chk(self.L.fovpt_bvh_read(self.h, _p(nodes), _p(ids)))
         return nodes, ids

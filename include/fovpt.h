@@ -118,10 +118,10 @@ int fovpt_set_tile_owner(fovpt_ctx*, int tile_size, int tiles_x, int tiles_y, co
 
 int fovpt_get_stats(fovpt_ctx*, fovpt_stats*);
 int fovpt_reset_stats(fovpt_ctx*);
-/* BVH introspection for validity tests: copies the 4-wide nodes (128 B each, layout in csrc/bvh.cuh) /
+/* BVH introspection for validity tests: copies the 4-wide quantised nodes (64 B each, layout in csrc/bvh.cuh) /
  * sorted triangle ids to host. */
 int fovpt_bvh_info(fovpt_ctx*, uint64_t* n_nodes, uint64_t* n_tris);
-int fovpt_bvh_read(fovpt_ctx*, void* nodes128, uint32_t* sorted_tri_ids);
+int fovpt_bvh_read(fovpt_ctx*, void* nodes64, uint32_t* sorted_tri_ids);
 
 #ifdef __cplusplus
 }

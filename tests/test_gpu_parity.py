@@ -167,36 +167,47 @@ def test_bvh_is_valid(gpu):
     nodes, ids = ctx.bvh()
     n_tris = sc.n_tris
     assert sorted(ids.tolist()) == list(range(n_tris))
-    nd = nodes.reshape(-1, 32)
-    child = nd[:, 24:28].copy().view(np.int32)
+    nd = nodes.reshape(-1, 16)                                       # 64-byte nodes as 16 uint32 (csrc/bvh.cuh)
+    child = nd[:, 4:8].copy().view(np.int32)
     seen = np.zeros(n_tris, np.int32)
     tri_v = np.concatenate([m.vtx[m.idx.astype(np.int64)] for m in sc.meshes])       # [T,3,3]
     lo_t, hi_t = tri_v.min(1), tri_v.max(1)
+    p = nd[:, 0:3].copy().view(np.float32).astype(np.float64)
+    e = np.stack([(nd[:, 3] >> (8 * a)) & 255 for a in range(3)], 1).astype(np.int64)
+    scale = np.ldexp(1.0, e - 127)
 
-    def box(i, c):      # slot c of node i -> (lo, hi)
-        n = nd[i]
-        return np.array([n[0 + c], n[8 + c], n[16 + c]]), np.array([n[4 + c], n[12 + c], n[20 + c]])
-    stack = [(0, 1)]
-    visited = 0; max_depth = 0
-    while stack:
-        i, depth = stack.pop(); visited += 1; max_depth = max(max_depth, depth)
+    def unused(i, c):
+        return ((nd[i, 8] >> (8 * c)) & 255) > ((nd[i, 9] >> (8 * c)) & 255)
+
+    def box(i, c):      # slot c of node i -> de-quantised (lo, hi)
+        q = [(nd[i, 8 + k] >> (8 * c)) & 255 for k in range(6)]      # qlo.x qhi.x qlo.y qhi.y qlo.z qhi.z
+        return p[i] + np.array([q[0], q[2], q[4]]) * scale[i], p[i] + np.array([q[1], q[3], q[5]]) * scale[i]
+    visited = [0]; max_depth = [0]
+
+    def bounds_below(i, depth):
+        """exact bounds of all triangles under node i; checks every stored (quantised, padded) child box against them"""
+        visited[0] += 1; max_depth[0] = max(max_depth[0], depth)
+        lo_all, hi_all = np.full(3, np.inf), np.full(3, -np.inf)
         for c in range(4):
+            if unused(i, c):
+                continue
             lo, hi = box(i, c)
-            if np.isinf(lo).all():
-                continue                                              # unused slot
             ch = int(child[i, c])
             if ch >= 0:
-                for cc in range(4):
-                    l2, h2 = box(ch, cc)
-                    if not np.isinf(l2).all():
-                        assert (l2 >= lo - 1e-3).all() and (h2 <= hi + 1e-3).all()
-                stack.append((ch, depth + 1))
+                l2, h2 = bounds_below(ch, depth + 1)
             else:
                 enc = (~ch) & 0xffffffff
                 first, cnt = enc >> 2, (enc & 3) + 1
-                for k in range(first, first + cnt):
-                    g = ids[k]; seen[g] += 1
-                    assert (lo_t[g] >= lo).all() and (hi_t[g] <= hi).all(), "leaf box does not contain its triangle"
+                g = ids[first:first + cnt]; seen[g] += 1
+                l2, h2 = lo_t[g].min(0), hi_t[g].max(0)
+            assert (l2 >= lo).all() and (h2 <= hi).all(), "stored child box does not contain the geometry below it"
+            assert ((lo >= l2 - 2 * scale[i] - 0.1) & (hi <= h2 + 2 * scale[i] + 0.1)).all(), "stored child box is looser than one grid step + pad"
+            lo_all, hi_all = np.minimum(lo_all, l2), np.maximum(hi_all, h2)
+        return lo_all, hi_all
+    import sys
+    sys.setrecursionlimit(10000)
+    bounds_below(0, 1)
+    visited, max_depth = visited[0], max_depth[0]
     assert visited == len(nd) and (seen == 1).all()
     assert 3 * max_depth + 1 <= 96
     ctx.close()

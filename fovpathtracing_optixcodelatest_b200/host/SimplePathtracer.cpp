@@ -1,0 +1,112 @@
+// SimplePathtracer.cpp -- SampleRenderer on top of the libfovpt C ABI (see SimplePathtracer.h).
+#include "SimplePathtracer.h"
+
+#include <cstring>
+#include <iostream>
+#include <stdexcept>
+
+void SampleRenderer::check(int rc)
+{
+    if (rc != 0) throw std::runtime_error(std::string("libfovpt: ") + (ctx ? fovpt_last_error(ctx) : "context creation failed"));
+}
+
+SampleRenderer::SampleRenderer(const Model* model_) : SampleRenderer(model_, 0, nullptr) {}
+
+SampleRenderer::SampleRenderer(const Model* model_, int device, const fovpt_config* cfg) : model(model_)
+{
+    std::memset(&launchParams, 0, sizeof(launchParams));          // the reference leaves it uninitialised
+    launchParams.white = 1.0f;
+    const int rc = fovpt_create(&ctx, device, nullptr);
+    if (rc != 0) throw std::runtime_error("#osc: no CUDA capable devices found!");            // SimplePathtracer.cpp:320-321
+    stream = (cudaStream_t)fovpt_stream(ctx);
+    if (cfg) config = *cfg; else fovpt_default_config(&config);
+    check(fovpt_set_config(ctx, &config));
+
+    // buildAccel + createTextures + buildSBT (SimplePathtracer.cpp:602-799, 534-599): hand the meshes over,
+    // libfovpt flattens them and builds the BVH on the device.
+    check(fovpt_scene_begin(ctx));
+    for (const Texture* t : model->textures) {
+        if (fovpt_scene_add_texture(ctx, t->pixel, t->resolution.x, t->resolution.y) < 0) check(1);
+    }
+    for (const TriangleMesh* m : model->meshes) {
+        const float* tc = m->texcoord.size() == m->vertex.size() && !m->texcoord.empty() ? &m->texcoord[0].x : nullptr;
+        // a texture id that does not name a loaded texture (e.g. addBox's default 1, Model.h:19) means "no texture"
+        const int tex = (m->diffuseTextureID >= 0 && m->diffuseTextureID < (int)model->textures.size()) ? m->diffuseTextureID : -1;
+        const float* vtx = m->vertex.empty() ? nullptr : &m->vertex[0].x;
+        const uint32_t* idx = m->index.empty() ? nullptr : &m->index[0].x;
+        static const float dummy_v[3] = {0, 0, 0}; static const uint32_t dummy_i[3] = {0, 0, 0};
+        if (fovpt_scene_add_mesh(ctx, vtx ? vtx : dummy_v, m->vertex.size(), idx ? idx : dummy_i, m->index.size(), tc, &m->material, tex) < 0) check(1);
+    }
+    unsigned long long handle = 0;
+    check(fovpt_scene_commit(ctx, (uint64_t*)&handle));
+    launchParams.traversable = handle;
+}
+
+SampleRenderer::~SampleRenderer() { fovpt_destroy(ctx); }
+
+void SampleRenderer::setConfig(const fovpt_config& cfg)
+{
+    config = cfg;
+    check(fovpt_set_config(ctx, &config));
+}
+
+void SampleRenderer::render()
+{
+    if (launchParams.frame.size.x == 0) return;                   // SimplePathtracer.cpp:81-82
+    check(fovpt_render_frame(ctx, &launchParams));                 // all passes in one submission; advances subframe_index (:210)
+    check(fovpt_sync(ctx));                                        // CUDA_SYNC_CHECK (:212)
+}
+
+void SampleRenderer::render(sutil::CUDAOutputBuffer<uint32_t>& renderTarget)
+{
+    launchParams.frame.frame_buffer = (uchar4*)renderTarget.map();  // SimplePathtracer.cpp:218-219
+    render();
+    renderTarget.unmap();
+}
+
+void SampleRenderer::resize(const int2& newSize)
+{
+    if (newSize.x == 0 || newSize.y == 0) return;                  // window minimised (:231)
+    void *accum = nullptr, *frame = nullptr;
+    check(fovpt_resize(ctx, newSize.x, newSize.y, &accum, &frame));
+    launchParams.frame.size = newSize;
+    launchParams.frame.accum_buffer = (float4*)accum;
+    launchParams.frame.frame_buffer = (uchar4*)frame;
+    ownFrameBuffer = (uchar4*)frame;
+    launchParams.frame.color_buffer = launchParams.frame.normal_buffer = launchParams.frame.albedo_buffer = nullptr;   // dead on device
+    launchParams.viewportSize = newSize;
+}
+
+void SampleRenderer::downloadPixels(uint32_t h_pixels[])
+{
+    check(fovpt_download(ctx, h_pixels, (size_t)launchParams.frame.size.x * launchParams.frame.size.y));
+}
+
+void SampleRenderer::downloadAccum(float4 h_accum[])
+{
+    check(fovpt_download_accum(ctx, &h_accum[0].x, (size_t)launchParams.frame.size.x * launchParams.frame.size.y));
+}
+
+void SampleRenderer::setCamera(const sutil::Camera& camera)
+{
+    if (launchParams.frame.size.y == 0) throw std::runtime_error("setCamera before resize: frame.size is 0");
+    lastSetCamera = camera;
+    lastSetCamera.setAspectRatio(launchParams.frame.size.x / float(launchParams.frame.size.y));        // :286
+    lastSetCamera.UVWFrame(launchParams.camera.U, launchParams.camera.V, launchParams.camera.W);
+    launchParams.camera.eye = lastSetCamera.eye();
+}
+
+void SampleRenderer::setProbe(const ProbeData& probe)
+{
+    if (!probe.valid) throw std::runtime_error("Probe Data is not valid");                             // Probe.h:104-105
+    const float off[3] = {probe.offset.x, probe.offset.y, probe.offset.z};
+    check(fovpt_probe_upload(ctx, probe.width, probe.height, &probe.data[0].x, probe.pdfValuesX, probe.cdfValuesX,
+                             probe.pdfValuesY, probe.cdfValuesY, off, &launchParams.probe));
+}
+
+fovpt_stats SampleRenderer::stats()
+{
+    fovpt_stats s;
+    check(fovpt_get_stats(ctx, &s));
+    return s;
+}

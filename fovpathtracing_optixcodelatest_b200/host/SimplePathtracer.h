@@ -1,0 +1,64 @@
+// SimplePathtracer.h -- class SampleRenderer, the drop-in boundary of the foveated path tracer.
+// Same public surface as the reference's class (PT_sv5_/SimplePathtracer.h:45-189): constructor from
+// a Model, render(), render(CUDAOutputBuffer&), resize, downloadPixels, setCamera, setProbe, and the
+// PUBLIC members the reference's main.cpp pokes directly -- launchParams (gaze frame.c, subframe_index,
+// frame.size; main.cpp:323,366-367,404,435,479) and stream (main.cpp:338).
+//
+// Everything the reference did through OptiX (context, module, program groups, pipeline, SBT, accel
+// build, the three optixLaunch calls) happens behind the C ABI of libfovpt (include/fovpt.h); this
+// class holds no GPU code.  Errors surface as std::runtime_error, the reference's convention
+// (sutil::Exception derives from it, sutil/Exception.h:93-194).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/fovpt.h"
+#include "CUDAOutputBuffer.h"
+#include "Camera.h"
+#include "LaunchParams.h"
+#include "Model.h"
+#include "Probe.h"
+
+class SampleRenderer {
+public:
+    /*! performs all setup: context, scene upload, on-device BVH build (reference ctor, SimplePathtracer.cpp:42-75).
+        The model is borrowed for the renderer's lifetime, as in the reference. */
+    SampleRenderer(const Model* model);
+    /*! extension: choose the CUDA device / pass non-default settings (the reference hard-codes both) */
+    SampleRenderer(const Model* model, int device, const fovpt_config* config);
+    ~SampleRenderer();
+    SampleRenderer(const SampleRenderer&) = delete;
+    SampleRenderer& operator=(const SampleRenderer&) = delete;
+
+    /*! render one frame: the three foveation passes (or the single FOV_OFF pass), then a device sync
+        (SimplePathtracer.cpp:77-214).  A no-op until resize() has been called (:81-82). */
+    void render();
+    /*! render into an external display buffer (SimplePathtracer.cpp:216-226) */
+    void render(sutil::CUDAOutputBuffer<uint32_t>& renderTarget);
+    /*! resize the frame buffers; drops the accumulation (SimplePathtracer.cpp:228-274) */
+    void resize(const int2& newSize);
+    /*! blocking download of frame.size.x * frame.size.y RGBA8 pixels (SimplePathtracer.cpp:276-280) */
+    void downloadPixels(uint32_t h_pixels[]);
+    /*! float4 accumulation buffer (extension, for parity tests) */
+    void downloadAccum(float4 h_accum[]);
+    /*! aspect ratio is taken from frame.size, so call after resize (SimplePathtracer.cpp:282-289) */
+    void setCamera(const sutil::Camera& camera);
+    /*! uploads data + CDF tables; throws "Probe Data is not valid" before BuildCDF (Probe.h:102-124) */
+    void setProbe(const ProbeData& probe);
+
+    /*! runtime form of the reference's compile-time switches (FOV_ON/OFF, radii, spp, depth ...) */
+    void setConfig(const fovpt_config& cfg);
+    const fovpt_config& getConfig() const { return config; }
+    fovpt_stats stats();
+
+    // ---- public data, exactly as in the reference (SimplePathtracer.h:116,146)
+    cudaStream_t stream = nullptr;
+    LaunchParams launchParams;
+
+protected:
+    void check(int rc);
+    fovpt_ctx* ctx = nullptr;
+    fovpt_config config;
+    const Model* model = nullptr;
+    sutil::Camera lastSetCamera;
+    uchar4* ownFrameBuffer = nullptr;      // what resize() allocated (render(target) redirects frame_buffer, :219)
+};

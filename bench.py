@@ -14,7 +14,7 @@ value   : Msamples/s with scene, BVH, probe and frame buffers resident in HBM (d
 e2e     : the same frames through the reference-facing API -- SampleRenderer.render() then
           downloadPixels() into host memory: launch parameters cross host->device every frame and
           the RGBA8 frame comes back device->host inside the timed region.
-roofline: traversal kernel k_extend against the HBM roofline, algorithmic bytes per ray from the
+roofline: traversal kernel k_trace against the HBM roofline, algorithmic bytes per ray from the
           CPU oracle's canonical BVH (profiles/algorithmic_bytes.json).
 cpu_baseline / --impl reference: the CPU checker (oracle/) on the same workload on host cores.
 
@@ -302,16 +302,22 @@ def native_arm(args):
         }
         ab = algorithmic_bytes(wl.name)
         if args.kernel_times and ext_ms > 0:
-            line["kernel_ms_per_step"] = {"k_extend": ext_ms / args.steps, "k_shade": shade_ms / args.steps, "k_shadow": shadow_ms / args.steps}
+            # k_trace serves both ray kinds in one launch (stats field last_extend_ms carries its time)
+            line["kernel_ms_per_step"] = {"k_trace": ext_ms / args.steps, "k_shade": shade_ms / args.steps}
             if ab:
-                b_ray = ab["closest"]["bytes_per_ray"]
-                achieved = (rad / world) * b_ray / (ext_ms * 1e-3) / 1e9     # per GPU
-                line["roofline"] = {"bound": "hbm", "kernel": "k_extend", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                b_closest, b_any = ab["closest"]["bytes_per_ray"], ab["any"]["bytes_per_ray"]
+                n_trace_launches = args.steps * (wl.max_depth + 2)
+                alg_bytes = (rad / world) * b_closest + (shw / world) * b_any              # per GPU, whole timed region
+                achieved = alg_bytes / (ext_ms * 1e-3) / 1e9
+                line["roofline"] = {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                                     "frac": achieved / hbm, "traffic": ab.get("measured_dram_bytes_per_launch"),
-                                    "peak_source": peak_src, "bytes_per_ray": b_ray,
-                                    "rays_per_s_in_kernel": (rad / world) / (ext_ms * 1e-3),
-                                    "note": "algorithmic bytes = oracle canonical-BVH node visits*64 + triangle tests*48 + 48 per ray; "
-                                            "the 21 MB BVH is L2-resident so DRAM traffic is far below this by construction"}
+                                    "peak_source": peak_src, "bytes_per_ray": {"closest": b_closest, "any": b_any},
+                                    "launches": n_trace_launches, "algorithmic_bytes_per_launch": alg_bytes / n_trace_launches,
+                                    "avg_launch_ms": ext_ms / n_trace_launches,
+                                    "rays_per_s_in_kernel": ((rad + shw) / world) / (ext_ms * 1e-3),
+                                    "note": "algorithmic bytes = oracle canonical-BVH node visits*64 + triangle tests*48 + 48 per ray "
+                                            "(DESIGN.md section 5); the BVH is L2-resident, so DRAM traffic (`traffic`, ncu) is far below "
+                                            "this by construction and L1 wavefronts / issue slots are what binds the kernel (profiles/)"}
         if world == 1 and not args.no_cpu_baseline:
             dt1, _, _, _ = run_oracle_frames(wl, 1)                       # sizes the sample: about 12 s of host work
             nfr = int(min(16, max(1, round(12.0 / max(dt1, 1e-3)))))

@@ -38,6 +38,7 @@ int main(int argc, char** argv)
         fovpt_config cfg; fovpt_default_config(&cfg);
         cfg.tmin = 1e-4f * extent;                       // the reference's 0.01 is tuned to Sponza's scale
         cfg.accumulate = 1; cfg.seed_all_passes_with_subframe = 1;
+        cfg.exposure = 1.0f;                             // the reference's 2^4 (deviceProgram.cu:586) saturates a 2.5 ambient probe to white
         SampleRenderer sample(model, 0, &cfg);
         sample.resize(make_int2(w, h));
         sample.setCamera(camera);

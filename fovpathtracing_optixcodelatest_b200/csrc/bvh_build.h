@@ -5,12 +5,15 @@
 
 namespace fovpt {
 
+constexpr uint32_t kMaxWideDepth = 31;      // 3 deferred children per level must fit the traversal stack (bvh.cuh kStackSize = 96)
+
 struct BuiltBvh {
     const uint4*    nodes = nullptr;       // 4 x uint4 (64 B) per 4-wide inner node (layout: bvh.cuh)
     const float4*   tris = nullptr;        // 3 x float4 per triangle, leaf order
     const float4*   tri_rec = nullptr;     // 3 x float4 per triangle, global-id order
     const uint32_t* sorted_ids = nullptr;  // leaf slot -> global triangle id
-    uint32_t        n_nodes = 0, n_tris = 0, max_depth = 0;
+    uint32_t        n_nodes = 0, n_tris = 0, max_depth = 0;   // max_depth: levels of the 4-wide tree
+    uint32_t        ploc_rounds = 0;
     float           pad = 0.f;
     float           bounds[6] = {0, 0, 0, 0, 0, 0};
 };

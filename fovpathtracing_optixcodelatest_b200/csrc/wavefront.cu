@@ -275,8 +275,11 @@ __global__ void __launch_bounds__(128, FOVPT_TRACE_BLOCKS) k_trace(SceneDev S, P
 }
 
 // ------------------------------------------------------------------ k_shade  (closest-hit / miss program)
+#ifndef FOVPT_SHADE_BLOCKS
+#define FOVPT_SHADE_BLOCKS 8
+#endif
 template <bool FAST>
-__global__ void __launch_bounds__(128) k_shade(FrameDev F, SceneDev S, PathState ps, Queues q, int shadow_slot)
+__global__ void __launch_bounds__(128, FOVPT_SHADE_BLOCKS) k_shade(FrameDev F, SceneDev S, PathState ps, Queues q, int shadow_slot)
 {
     const uint32_t n = q.counts[0];
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {

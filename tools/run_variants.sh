@@ -6,6 +6,6 @@ for f in variants/lib_*.so; do
 import json, sys
 d=json.load(open("gpurun_out/v.json"))
 k=d["kernel_ms_per_step"]
-print(f"{sys.argv[1]:40s} {d['value']:7.1f} Msamples/s  frame {d['ms_per_step']:.3f} ms  extend {k['k_extend']:.3f} shade {k['k_shade']:.3f} shadow {k['k_shadow']:.3f}")
+print(f"{sys.argv[1]:40s} {d['value']:7.1f} Msamples/s  frame {d['ms_per_step']:.3f} ms  trace {k['k_trace']:.3f} shade {k['k_shade']:.3f}")
 PY
 done

@@ -205,8 +205,8 @@ def native_arm(args):
     r.setProbe(ProbeData(wl.probe()).BuildCDF())
     lp.frame.c_x, lp.frame.c_y = wl.gaze_xy()
     if world > 1:
-        owner, loads = partition.partition(w, h, wl.gaze_xy(), wl.inner_radius, wl.outer_radius, world, 32, wl.spp, bool(wl.foveated), wl.spp_uniform)
-        r.ctx.set_tile_owner(32, owner, rank)
+        owner, loads = partition.partition(w, h, wl.gaze_xy(), wl.inner_radius, wl.outer_radius, world, args.tile, wl.spp, bool(wl.foveated), wl.spp_uniform)
+        r.ctx.set_tile_owner(args.tile, owner, rank)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     host_frame = torch.empty((h, w), dtype=torch.int32).pin_memory()
@@ -222,6 +222,16 @@ def native_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the frame's own sample count (what one GPU traces for the whole frame); ranks re-trace the few splat blocks
+    # that straddle their tile edges, those duplicates must not count as throughput
+    r.ctx.set_tile_owner(args.tile, None, 0) if world > 1 else None
+    r.ctx.reset_stats(); lp.frame.subframe_index = 0
+    if rank == 0 or world == 1:
+        r.ctx.render_frame(lp); torch.cuda.synchronize()
+    frame_samples = float(r.ctx.stats()["samples"])
+    if world > 1:
+        fs = torch.tensor([frame_samples], dtype=torch.float64, device="cuda"); dist.broadcast(fs, src=0); frame_samples = float(fs[0])
+        r.ctx.set_tile_owner(args.tile, owner, rank)
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
@@ -286,6 +296,8 @@ def native_arm(args):
 
     if rank == 0:
         hbm, peak_src = load_peaks()
+        traced_samples = samples                               # sum over ranks, incl. tile-edge duplicates
+        samples = frame_samples * args.steps                   # unique samples of the frames rendered
         per_step_samples = samples / args.steps
         value = samples / (total_ms * 1e-3) / 1e6
         line = {
@@ -293,7 +305,7 @@ def native_arm(args):
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(wl),
-            "samples_per_step": per_step_samples,
+            "samples_per_step": per_step_samples, "traced_samples_per_step": traced_samples / args.steps,
             "rays_per_s": (rad + shw) / (total_ms * 1e-3), "radiance_rays_per_step": rad / args.steps, "shadow_rays_per_step": shw / args.steps,
             "gpu_launches": int(launches),
             "e2e": {"value": samples / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": C.sizeof(LaunchParams),
@@ -338,6 +350,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c5"])
+    ap.add_argument("--tile", type=int, default=32, help="screen tile edge of the multi-GPU partition")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-times", dest="kernel_times", action="store_false")
     args = ap.parse_args()

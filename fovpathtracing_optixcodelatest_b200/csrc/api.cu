@@ -3,6 +3,7 @@
 // fovpt.h, the reference host function it stands in for (PT_sv5_/SimplePathtracer.cpp).
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -487,7 +488,9 @@ int fovpt_scene_commit(fovpt_ctx* c, uint64_t* traversable_out)
 
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, c->stream);
-    cudaError_t be = build_bvh(c->d_vtx, c->d_idx, (uint32_t)nt, 4, c->stream, &c->bvh, &c->launches);
+    int leaf_max = 4;
+    if (const char* e = getenv("FOVPT_LEAF_MAX")) { const int v = atoi(e); if (v >= 1 && v <= 4) leaf_max = v; }   // tuning knob
+    cudaError_t be = build_bvh(c->d_vtx, c->d_idx, (uint32_t)nt, leaf_max, c->stream, &c->bvh, &c->launches);
     cudaEventRecord(e1, c->stream);
     if (be != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return cuda_fail(c, be, "build_bvh"); }
     cudaEventSynchronize(e1);

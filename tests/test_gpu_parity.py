@@ -348,6 +348,33 @@ def test_tile_partition_union_is_the_frame(gpu, port):
         assert ns >= n_samples_full and ns < 1.15 * n_samples_full      # only splat blocks straddling tile edges are duplicated
 
 
+def test_moving_gaze_stereo_pair(gpu, port):
+    """BASELINE configs[3] scaled down: two eye cameras (+-IPD/2 along U), the gaze point moves every frame
+    (PT_sv4_vmv/main.cpp:309-314 updates frame.c from the cursor each frame), no accumulation; one renderer per
+    eye is reused across frames, so the owner map must follow the gaze"""
+    import math
+    w = h = 240
+    for eye_index in (0, 1):
+        wl0 = workloads.c4_eye(eye_index, 0)
+        sc = scenes.atrium(detail=0.3)
+        ri, ro = 16, 54
+        r, o, lp, accum, frame = make_pair(gpu, port, sc, wl0.camera, w, h, scenes.sky_probe(64, 32, 2), ri, ro)
+        for k in range(3):
+            gaze = (int(w / 2 + 0.28 * w * math.cos(1.3 * k)), int(h / 2 + 0.28 * h * math.sin(1.3 * k)))
+            lp.frame.c_x, lp.frame.c_y = gaze
+            r.launchParams.frame.c_x, r.launchParams.frame.c_y = gaze
+            lp.frame.subframe_index = k; r.launchParams.frame.subframe_index = k      # main.cpp:479 advances it every frame
+            accum[:] = 0; frame[:] = 0
+            o.render(lp, port.FovCfg.sv5(inner_radius=ri, outer_radius=ro), port.Opts.sv5(threads=1))
+            r.render()
+            g = r.downloadAccum(); gf = r.downloadPixels()
+            wr = accum[..., 3] == 1.0
+            assert (g[..., 3] == 1.0)[wr].all()
+            assert rmse(accum[wr], g[wr]) < 1e-4 and close_fraction(accum[wr][None], g[wr][None]) > 0.99
+            assert (gf[wr] == frame[wr]).mean() > 0.99
+        r.close(); o.close()
+
+
 # ------------------------------------------------------------------------------------------- API behaviour
 def test_api_contract_and_errors(gpu):
     sc = scenes.cornell_box()

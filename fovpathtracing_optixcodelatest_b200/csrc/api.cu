@@ -490,7 +490,7 @@ int fovpt_scene_commit(fovpt_ctx* c, uint64_t* traversable_out)
     cudaEventRecord(e0, c->stream);
     int leaf_max = 4;
     if (const char* e = getenv("FOVPT_LEAF_MAX")) { const int v = atoi(e); if (v >= 1 && v <= 4) leaf_max = v; }   // tuning knob
-    cudaError_t be = build_bvh(c->d_vtx, c->d_idx, (uint32_t)nt, leaf_max, c->stream, &c->bvh, &c->launches);
+    cudaError_t be = build_bvh(c->d_vtx, c->d_idx, (uint32_t)nt, leaf_max, kBvhWide, c->stream, &c->bvh, &c->launches);
     cudaEventRecord(e1, c->stream);
     if (be != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return cuda_fail(c, be, "build_bvh"); }
     cudaEventSynchronize(e1);
@@ -739,11 +739,19 @@ int fovpt_bvh_info(fovpt_ctx* c, uint64_t* n_nodes, uint64_t* n_tris)
     return 0;
 }
 
+int fovpt_bvh_layout(fovpt_ctx* c, int* wide, int* node_bytes)
+{
+    if (!c) return 1;
+    if (wide) *wide = kBvhWide;
+    if (node_bytes) *node_bytes = kBvhWide == 8 ? 96 : 64;
+    return 0;
+}
+
 int fovpt_bvh_read(fovpt_ctx* c, void* nodes64, uint32_t* sorted_tri_ids)
 {
     if (!c || !c->committed) return 1;
     cudaSetDevice(c->device);
-    if (nodes64 && c->bvh.n_nodes) CU(cudaMemcpy(nodes64, c->bvh.nodes, (size_t)c->bvh.n_nodes * 64, cudaMemcpyDeviceToHost));
+    if (nodes64 && c->bvh.n_nodes) CU(cudaMemcpy(nodes64, c->bvh.nodes, (size_t)c->bvh.n_nodes * (kBvhWide == 8 ? 96 : 64), cudaMemcpyDeviceToHost));
     if (sorted_tri_ids && c->bvh.n_tris) CU(cudaMemcpy(sorted_tri_ids, c->bvh.sorted_ids, (size_t)c->bvh.n_tris * 4, cudaMemcpyDeviceToHost));
     return 0;
 }

@@ -14,13 +14,14 @@ struct BuiltBvh {
     const uint32_t* sorted_ids = nullptr;  // leaf slot -> global triangle id
     uint32_t        n_nodes = 0, n_tris = 0, max_depth = 0;   // max_depth: levels of the 4-wide tree
     uint32_t        ploc_rounds = 0;
+    int             wide = 4;              // 4: 64-byte nodes, 8: 96-byte compressed wide nodes (bvh.cuh)
     float           pad = 0.f;
     float           bounds[6] = {0, 0, 0, 0, 0, 0};
 };
 
 // d_vtx: float3 soup of all meshes; d_idx: uint3 per triangle, already rebased to the soup.
 // Synchronises the stream (the caller is a one-off setup path, like optixAccelBuild + SYNC).
-cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, uint32_t ntri, int leaf_max, cudaStream_t st,
+cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, uint32_t ntri, int leaf_max, int wide, cudaStream_t st,
                       BuiltBvh* out, uint64_t* launches);
 void free_bvh(BuiltBvh* b);
 

@@ -204,11 +204,11 @@ __global__ void __launch_bounds__(128, FOVPT_TRACE_BLOCKS) k_trace(SceneDev S, P
     // thin launch: leave whole blocks idle so that the active warps each see ~FOVPT_ROUNDS refills
     if ((unsigned long long)blockIdx.x * (128ull * FOVPT_ROUNDS) >= (unsigned long long)n && blockIdx.x >= 148u) return;
     const unsigned lane = threadIdx.x & 31u;
-    Traversal<kMixed> T;
+    FOVPT_TRAV(kMixed) T;
     int2 stack[kStackSize];
     uint32_t pid = 0;
     bool have = false, exhausted = false;
-    T.cur = kDone;
+    T.reset();
 #ifdef FOVPT_TRACE_STATS
     unsigned long long st_node_exec = 0, st_node_lanes = 0, st_leaf_exec = 0, st_leaf_lanes = 0, st_leaf_tris = 0, st_leaf_nmax = 0, st_fetch = 0, st_idle = 0, st_idle_exh = 0, st_blocked = 0;
 #endif
@@ -245,9 +245,9 @@ __global__ void __launch_bounds__(128, FOVPT_TRACE_BLOCKS) k_trace(SceneDev S, P
 #endif
                 if (node) T.node_step(S.bvh, stack);
             } else {
-                const uint32_t nmax = __reduce_max_sync(FULL, leaf ? leaf_count(T.cur) : 0u);
+                const uint32_t nmax = __reduce_max_sync(FULL, leaf ? T.leaf_work() : 0u);
 #ifdef FOVPT_TRACE_STATS
-                st_leaf_exec++; st_leaf_lanes += __popc(ml); st_leaf_nmax += nmax; st_leaf_tris += __reduce_add_sync(FULL, leaf ? leaf_count(T.cur) : 0u);
+                st_leaf_exec++; st_leaf_lanes += __popc(ml); st_leaf_nmax += nmax; st_leaf_tris += __reduce_add_sync(FULL, leaf ? T.leaf_work() : 0u);
 #endif
                 if (leaf) T.leaf_step(S.bvh, stack, nmax);
             }
@@ -494,17 +494,17 @@ __global__ void k_trace_query(SceneDev S, const float* __restrict__ rays, size_t
             int2 stack[kStackSize];
             if (S.bvh.n_tris == 0) { tri[i] = mode == 2 ? -1 : 0; }
             else if (mode == 2) {
-                Traversal<kClosest> T; T.begin(o, d, r[3], r[7]);
+                FOVPT_TRAV(kClosest) T; T.begin(o, d, r[3], r[7]);
                 while (!T.done()) {
                     if (T.at_node()) { nodes += 1.f; T.node_step(S.bvh, stack); }
-                    else { leaves += 1.f; tris += (float)leaf_count(T.cur); T.leaf_step(S.bvh, stack, leaf_count(T.cur)); }
+                    else { leaves += 1.f; tris += (float)T.leaf_work(); T.leaf_step(S.bvh, stack, T.leaf_work()); }
                 }
                 tri[i] = T.found() ? (int32_t)T.best_gid : -1;
             } else {
-                Traversal<kAny> T; T.begin(o, d, r[3], r[7]);
+                FOVPT_TRAV(kAny) T; T.begin(o, d, r[3], r[7]);
                 while (!T.done()) {
                     if (T.at_node()) { nodes += 1.f; T.node_step(S.bvh, stack); }
-                    else { leaves += 1.f; tris += (float)leaf_count(T.cur); T.leaf_step(S.bvh, stack, leaf_count(T.cur)); }
+                    else { leaves += 1.f; tris += (float)T.leaf_work(); T.leaf_step(S.bvh, stack, T.leaf_work()); }
                 }
                 tri[i] = T.found() ? 1 : 0;
             }

@@ -42,7 +42,7 @@ EXPORTS = [
     "fovpt_get_config", "fovpt_scene_begin", "fovpt_scene_add_texture", "fovpt_scene_add_mesh", "fovpt_scene_commit",
     "fovpt_probe_upload", "fovpt_resize", "fovpt_launch", "fovpt_render_frame", "fovpt_sync", "fovpt_download",
     "fovpt_download_accum", "fovpt_trace", "fovpt_primary_hits", "fovpt_set_tile_owner", "fovpt_get_stats",
-    "fovpt_reset_stats", "fovpt_bvh_info", "fovpt_bvh_read",
+    "fovpt_reset_stats", "fovpt_bvh_info", "fovpt_bvh_layout", "fovpt_bvh_read",
 ]
 
 _lib = None
@@ -83,6 +83,7 @@ def load_library():
     L.fovpt_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.fovpt_reset_stats.argtypes = [vp]
     L.fovpt_bvh_info.argtypes = [vp, u64p, u64p]
+    L.fovpt_bvh_layout.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.fovpt_bvh_read.argtypes = [vp, vp, vp]
     for n in EXPORTS:
         if n not in ("fovpt_last_error", "fovpt_stream", "fovpt_default_config"):
@@ -238,6 +239,9 @@ class Context:
     def bvh(self):
         nn, nt = C.c_uint64(), C.c_uint64()
         self._chk(self.L.fovpt_bvh_info(self.h, C.byref(nn), C.byref(nt)))
-        nodes = np.zeros((nn.value, 16), np.uint32); ids = np.zeros(nt.value, np.uint32)
+        wide, nbytes = C.c_int(), C.c_int()
+        self._chk(self.L.fovpt_bvh_layout(self.h, C.byref(wide), C.byref(nbytes)))
+        self.bvh_wide = wide.value
+        nodes = np.zeros((nn.value, nbytes.value // 4), np.uint32); ids = np.zeros(nt.value, np.uint32)
         self._chk(self.L.fovpt_bvh_read(self.h, _p(nodes), _p(ids)))
         return nodes, ids

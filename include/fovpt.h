@@ -73,7 +73,7 @@ int fovpt_scene_begin(fovpt_ctx*);
 int fovpt_scene_add_texture(fovpt_ctx*, const uint32_t* rgba8, int w, int h);
 int fovpt_scene_add_mesh(fovpt_ctx*, const float* vtx, size_t nvtx, const uint32_t* idx, size_t ntri,
                          const float* texcoord_or_null, const void* material104, int texture_id);
-/* builds the BVH on the device (Morton codes, radix sort, Karras hierarchy, refit, 4-wide collapse);
+/* builds the BVH on the device (Morton codes, radix sort, PLOC clustering, collapse into compressed wide nodes);
  * *traversable_out is what LaunchParams.traversable (offset 160) must carry. */
 int fovpt_scene_commit(fovpt_ctx*, uint64_t* traversable_out);
 
@@ -118,10 +118,11 @@ int fovpt_set_tile_owner(fovpt_ctx*, int tile_size, int tiles_x, int tiles_y, co
 
 int fovpt_get_stats(fovpt_ctx*, fovpt_stats*);
 int fovpt_reset_stats(fovpt_ctx*);
-/* BVH introspection for validity tests: copies the 4-wide quantised nodes (64 B each, layout in csrc/bvh.cuh) /
- * sorted triangle ids to host. */
+/* BVH introspection for validity tests: branching factor (8 or 4) and node size in bytes (96 / 64, layout in
+ * csrc/bvh.cuh); copies the quantised nodes / sorted triangle ids to host. */
+int fovpt_bvh_layout(fovpt_ctx*, int* wide, int* node_bytes);
 int fovpt_bvh_info(fovpt_ctx*, uint64_t* n_nodes, uint64_t* n_tris);
-int fovpt_bvh_read(fovpt_ctx*, void* nodes64, uint32_t* sorted_tri_ids);
+int fovpt_bvh_read(fovpt_ctx*, void* nodes, uint32_t* sorted_tri_ids);
 
 #ifdef __cplusplus
 }

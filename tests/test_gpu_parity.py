@@ -159,16 +159,16 @@ def test_degenerate_rays_and_geometry(gpu, port):
 
 
 def test_bvh_is_valid(gpu):
-    """on-device builder (Morton sort -> Karras hierarchy -> refit -> 4-wide collapse, csrc/bvh.cuh layout): every
-    triangle sits in exactly one leaf, every stored child box contains the boxes / triangles below it, every
-    node is reachable exactly once, and the depth respects the traversal-stack bound"""
+    """on-device builder (Morton sort -> PLOC clustering -> collapse into quantised wide nodes, csrc/bvh.cuh layouts):
+    every triangle sits in exactly one leaf, every stored child box contains all geometry below it and is no looser
+    than one grid step + pad, every node is reachable exactly once, depth respects the traversal-stack bound"""
     sc = scenes.atrium(detail=0.3)
     ctx = gpu.native.Context(0); ctx.upload_scene(sc)
     nodes, ids = ctx.bvh()
+    wide = ctx.bvh_wide
     n_tris = sc.n_tris
     assert sorted(ids.tolist()) == list(range(n_tris))
-    nd = nodes.reshape(-1, 16)                                       # 64-byte nodes as 16 uint32 (csrc/bvh.cuh)
-    child = nd[:, 4:8].copy().view(np.int32)
+    nd = nodes
     seen = np.zeros(n_tris, np.int32)
     tri_v = np.concatenate([m.vtx[m.idx.astype(np.int64)] for m in sc.meshes])       # [T,3,3]
     lo_t, hi_t = tri_v.min(1), tri_v.max(1)
@@ -176,28 +176,50 @@ def test_bvh_is_valid(gpu):
     e = np.stack([(nd[:, 3] >> (8 * a)) & 255 for a in range(3)], 1).astype(np.int64)
     scale = np.ldexp(1.0, e - 127)
 
-    def unused(i, c):
-        return ((nd[i, 8] >> (8 * c)) & 255) > ((nd[i, 9] >> (8 * c)) & 255)
+    def byte(word, k):
+        return int((word >> (8 * k)) & 255)
 
-    def box(i, c):      # slot c of node i -> de-quantised (lo, hi)
-        q = [(nd[i, 8 + k] >> (8 * c)) & 255 for k in range(6)]      # qlo.x qhi.x qlo.y qhi.y qlo.z qhi.z
-        return p[i] + np.array([q[0], q[2], q[4]]) * scale[i], p[i] + np.array([q[1], q[3], q[5]]) * scale[i]
+    def slots(i):
+        """-> list of (lo, hi, kind, payload): kind 'inner' payload = node index, kind 'leaf' payload = (first, count)"""
+        n = nd[i]; out = []
+        if wide == 4:       # n1 = child[4]; n2 = (qlo.x, qhi.x, qlo.y, qhi.y); n3 = (qlo.z, qhi.z, 0, 0)
+            for c in range(4):
+                q = [byte(n[8 + k], c) for k in range(6)]
+                if q[0] > q[1]:
+                    continue
+                ch = int(np.int32(n[4 + c]))
+                lo = p[i] + np.array([q[0], q[2], q[4]]) * scale[i]; hi = p[i] + np.array([q[1], q[3], q[5]]) * scale[i]
+                if ch >= 0:
+                    out.append((lo, hi, "inner", ch))
+                else:
+                    enc = (~ch) & 0xffffffff
+                    out.append((lo, hi, "leaf", (enc >> 2, (enc & 3) + 1)))
+        else:               # n1 = (child_base, tri_base, meta0123, meta4567); n2..n4 = (qlo[0..3], qlo[4..7], qhi[0..3], qhi[4..7]) per axis
+            imask = int(n[3] >> 24); child_base, tri_base = int(n[4]), int(n[5])
+            for c in range(8):
+                meta = byte(n[6 + c // 4], c % 4)
+                if meta == 0:
+                    continue
+                q = [byte(n[8 + 4 * a + c // 4], c % 4) for a in range(3)] + [byte(n[8 + 4 * a + 2 + c // 4], c % 4) for a in range(3)]
+                lo = p[i] + np.array(q[0:3]) * scale[i]; hi = p[i] + np.array(q[3:6]) * scale[i]
+                if (meta & 0x18) == 0x18 and (meta >> 5) == 1 and (meta & 31) >= 24:
+                    assert (meta & 31) == 24 + c and (imask >> c) & 1
+                    out.append((lo, hi, "inner", child_base + bin(imask & ((1 << c) - 1)).count("1")))
+                else:
+                    cnt = {1: 1, 3: 2, 7: 3}[meta >> 5]
+                    assert not (imask >> c) & 1 and (meta & 31) + cnt <= 24
+                    out.append((lo, hi, "leaf", (tri_base + (meta & 31), cnt)))
+        return out
     visited = [0]; max_depth = [0]
 
     def bounds_below(i, depth):
-        """exact bounds of all triangles under node i; checks every stored (quantised, padded) child box against them"""
         visited[0] += 1; max_depth[0] = max(max_depth[0], depth)
         lo_all, hi_all = np.full(3, np.inf), np.full(3, -np.inf)
-        for c in range(4):
-            if unused(i, c):
-                continue
-            lo, hi = box(i, c)
-            ch = int(child[i, c])
-            if ch >= 0:
-                l2, h2 = bounds_below(ch, depth + 1)
+        for lo, hi, kind, payload in slots(i):
+            if kind == "inner":
+                l2, h2 = bounds_below(payload, depth + 1)
             else:
-                enc = (~ch) & 0xffffffff
-                first, cnt = enc >> 2, (enc & 3) + 1
+                first, cnt = payload
                 g = ids[first:first + cnt]; seen[g] += 1
                 l2, h2 = lo_t[g].min(0), hi_t[g].max(0)
             assert (l2 >= lo).all() and (h2 <= hi).all(), "stored child box does not contain the geometry below it"
@@ -207,9 +229,8 @@ def test_bvh_is_valid(gpu):
     import sys
     sys.setrecursionlimit(10000)
     bounds_below(0, 1)
-    visited, max_depth = visited[0], max_depth[0]
-    assert visited == len(nd) and (seen == 1).all()
-    assert 3 * max_depth + 1 <= 96
+    assert visited[0] == len(nd) and (seen == 1).all()
+    assert max_depth[0] <= 31
     ctx.close()
 
 

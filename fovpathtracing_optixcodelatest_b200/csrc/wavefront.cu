@@ -205,7 +205,13 @@ __global__ void __launch_bounds__(128, FOVPT_TRACE_BLOCKS) k_trace(SceneDev S, P
     if ((unsigned long long)blockIdx.x * (128ull * FOVPT_ROUNDS) >= (unsigned long long)n && blockIdx.x >= 148u) return;
     const unsigned lane = threadIdx.x & 31u;
     FOVPT_TRAV(kMixed) T;
-    int2 stack[kStackSize];
+    int2 stack_local[kStackSize];
+#if FOVPT_SMEM_STACK > 0
+    __shared__ int2 stack_shared[FOVPT_SMEM_STACK * 128];
+    const RayStack stack{stack_local, stack_shared + threadIdx.x, FOVPT_SMEM_STACK, 128};
+#else
+    const RayStack stack = local_stack(stack_local);
+#endif
     uint32_t pid = 0;
     bool have = false, exhausted = false;
     T.reset();
@@ -237,10 +243,12 @@ __global__ void __launch_bounds__(128, FOVPT_TRACE_BLOCKS) k_trace(SceneDev S, P
             // each iteration runs the step kind most lanes are waiting for; the others keep their state
             const bool node = have && T.at_node(), leaf = have && T.at_leaf();
             const unsigned mn = __ballot_sync(FULL, node), ml = __ballot_sync(FULL, leaf);
-            const unsigned mb = ml; (void)mb;
+            const int n_active = __popc(mn | ml);
+            if (n_active == 0) break;                                    // warp drained
+            if (!exhausted && n_active <= 32 - kFetchMin) break;         // enough idle lanes: refill first
             if (FOVPT_LEAF_NUM * __popc(ml) <= FOVPT_LEAF_DEN * __popc(mn)) {
 #ifdef FOVPT_TRACE_STATS
-                st_node_exec++; st_node_lanes += __popc(mn); st_blocked += __popc(mb);
+                st_node_exec++; st_node_lanes += __popc(mn);
                 { const int idl = 32 - __popc(__ballot_sync(FULL, have)); if (exhausted) st_idle_exh += idl; else st_idle += idl; }
 #endif
                 if (node) T.node_step(S.bvh, stack);
@@ -257,9 +265,6 @@ __global__ void __launch_bounds__(128, FOVPT_TRACE_BLOCKS) k_trace(SceneDev S, P
                 else shadow_resolve(ps, pid, T.found());
                 have = false;
             }
-            const unsigned act = __ballot_sync(FULL, have);
-            if (act == 0u) break;
-            if (!exhausted && __popc(act) <= 32 - kFetchMin) break;
         }
 #ifdef FOVPT_TRACE_STATS
         st_fetch++;
@@ -491,7 +496,8 @@ __global__ void k_trace_query(SceneDev S, const float* __restrict__ rays, size_t
             tri[i] = trace_any_front(S.bvh, o, d, r[3], r[7]) ? 1 : 0;
         } else {                                       // modes 2 / 3: closest / any with visit counters in tuv
             float nodes = 0.f, leaves = 0.f, tris = 0.f;
-            int2 stack[kStackSize];
+            int2 stack_local[kStackSize];
+            const RayStack stack = local_stack(stack_local);
             if (S.bvh.n_tris == 0) { tri[i] = mode == 2 ? -1 : 0; }
             else if (mode == 2) {
                 FOVPT_TRAV(kClosest) T; T.begin(o, d, r[3], r[7]);

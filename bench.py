@@ -207,6 +207,9 @@ def native_arm(args):
     if world > 1:
         owner, loads = partition.partition(w, h, wl.gaze_xy(), wl.inner_radius, wl.outer_radius, world, args.tile, wl.spp, bool(wl.foveated), wl.spp_uniform)
         r.ctx.set_tile_owner(args.tile, owner, rank)
+    elif args.emulate_world > 1:        # profiling aid: one process renders rank 0's share of an N-rank partition
+        owner, loads = partition.partition(w, h, wl.gaze_xy(), wl.inner_radius, wl.outer_radius, args.emulate_world, args.tile, wl.spp, bool(wl.foveated), wl.spp_uniform)
+        r.ctx.set_tile_owner(args.tile, owner, 0)
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     host_frame = torch.empty((h, w), dtype=torch.int32).pin_memory()
@@ -224,7 +227,8 @@ def native_arm(args):
 
     # the frame's own sample count (what one GPU traces for the whole frame); ranks re-trace the few splat blocks
     # that straddle their tile edges, those duplicates must not count as throughput
-    r.ctx.set_tile_owner(args.tile, None, 0) if world > 1 else None
+    if world > 1 or args.emulate_world > 1:
+        r.ctx.set_tile_owner(args.tile, None, 0)
     r.ctx.reset_stats(); lp.frame.subframe_index = 0
     if rank == 0 or world == 1:
         r.ctx.render_frame(lp); torch.cuda.synchronize()
@@ -232,6 +236,8 @@ def native_arm(args):
     if world > 1:
         fs = torch.tensor([frame_samples], dtype=torch.float64, device="cuda"); dist.broadcast(fs, src=0); frame_samples = float(fs[0])
         r.ctx.set_tile_owner(args.tile, owner, rank)
+    elif args.emulate_world > 1:
+        r.ctx.set_tile_owner(args.tile, owner, 0)
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
@@ -266,8 +272,13 @@ def native_arm(args):
         sm = mine.clone(); dist.all_reduce(sm, op=dist.ReduceOp.SUM)
         total_ms = float(mx[0]); samples = float(sm[1]); rad = float(sm[2]); shw = float(sm[3]); launches = float(sm[4])
         ext_ms, shade_ms, shadow_ms = float(mx[5]), float(mx[6]), float(mx[7])
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [{"ms": float(t[0]) / args.steps, "samples": float(t[1]) / args.steps, "rays": float(t[2] + t[3]) / args.steps,
+                     "k_trace_ms": float(t[5]) / args.steps, "k_shade_ms": float(t[6]) / args.steps} for t in allr]
     else:
         samples, rad, shw, launches = float(st["samples"]), float(st["radiance_rays"]), float(st["shadow_rays"]), float(st["kernel_launches"])
+        per_rank = None
     clk = clocks.stop() if clocks else None
 
     # ---- end-to-end region: public API with host buffers (params in, pixels out) every step
@@ -310,7 +321,7 @@ def native_arm(args):
             "gpu_launches": int(launches),
             "e2e": {"value": samples / (e2e_ms * 1e-3) / 1e6, "unit": "Msamples/s", "h2d_bytes_per_step": C.sizeof(LaunchParams),
                     "d2h_bytes_per_step": w * h * 4, "ms_per_step": e2e_ms / args.steps, "frame_checksum": checksum},
-            "clocks": clk, "wall_s_timed_region": t_wall, "step_ms": step_ms,
+            "clocks": clk, "wall_s_timed_region": t_wall, "step_ms": step_ms, "per_rank": per_rank,
         }
         ab = algorithmic_bytes(wl.name)
         if args.kernel_times and ext_ms > 0:
@@ -351,6 +362,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c5"])
     ap.add_argument("--tile", type=int, default=32, help="screen tile edge of the multi-GPU partition")
+    ap.add_argument("--emulate-world", type=int, default=1, help="profiling aid: render only rank 0's tiles of an N-rank partition (single process; value is NOT a benchmark number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-times", dest="kernel_times", action="store_false")
     args = ap.parse_args()

@@ -176,9 +176,6 @@ __device__ __forceinline__ void shadow_resolve(const PathState& ps, uint32_t pid
 #define FOVPT_LEAF_NUM 1      // run the leaf phase when LEAF_NUM * lanes_at_leaf > LEAF_DEN * lanes_at_node
 #define FOVPT_LEAF_DEN 1
 #endif
-#ifndef FOVPT_ROUNDS
-#define FOVPT_ROUNDS 4        // thin launches use fewer warps so that each still refills about this many times
-#endif
 constexpr int kFetchMin = FOVPT_FETCH_MIN;          // refill as soon as this many lanes are idle
 
 __global__ void __launch_bounds__(128, FOVPT_TRACE_BLOCKS) k_trace(SceneDev S, PathState ps, Queues q, int shadow_slot, float tmin, float tmax,
@@ -201,8 +198,13 @@ __global__ void __launch_bounds__(128, FOVPT_TRACE_BLOCKS) k_trace(SceneDev S, P
         }
         return;
     }
-    // thin launch: leave whole blocks idle so that the active warps each see ~FOVPT_ROUNDS refills
-    if ((unsigned long long)blockIdx.x * (128ull * FOVPT_ROUNDS) >= (unsigned long long)n && blockIdx.x >= 148u) return;
+    // thin launch (late bounces, small per-GPU shares): spread the rays over ALL resident warps, `cap` lanes each.
+    // A warp's time is its longest ray plus the serialisation of divergent lanes, so fewer rays per warp finish sooner
+    // when there are SMs to spare (measured: 240 us -> 60 us floor per launch at 1/4 frame per GPU).
+    const uint32_t total_warps = gridDim.x * (blockDim.x >> 5);
+    const uint32_t cap = min(32u, max(1u, (n + total_warps - 1u) / total_warps));
+    const unsigned lanes = cap >= 32u ? FULL : ((1u << cap) - 1u);          // lanes that take rays in this launch
+    const int fetch_min = min(kFetchMin, (int)((cap + 3u) / 4u));
     const unsigned lane = threadIdx.x & 31u;
     FOVPT_TRAV(kMixed) T;
     int2 stack_local[kStackSize];
@@ -219,15 +221,15 @@ __global__ void __launch_bounds__(128, FOVPT_TRACE_BLOCKS) k_trace(SceneDev S, P
     unsigned long long st_node_exec = 0, st_node_lanes = 0, st_leaf_exec = 0, st_leaf_lanes = 0, st_leaf_tris = 0, st_leaf_nmax = 0, st_fetch = 0, st_idle = 0, st_idle_exh = 0, st_blocked = 0;
 #endif
     for (;;) {
-        const unsigned idle = __ballot_sync(FULL, !have);
-        if (idle == FULL || (!exhausted && __popc(idle) >= kFetchMin)) {
+        const unsigned idle = __ballot_sync(FULL, !have) & lanes;
+        if (idle == lanes || (!exhausted && __popc(idle) >= fetch_min)) {
             if (!exhausted) {
                 const int want = __popc(idle);
                 uint32_t base = 0;
                 if (lane == 0) base = atomicAdd(fetch, (uint32_t)want);
                 base = __shfl_sync(FULL, base, 0);
                 const uint32_t mine = base + __popc(idle & ((1u << lane) - 1u));
-                if (!have && mine < n) {
+                if (!have && ((idle >> lane) & 1u) && mine < n) {
                     const bool is_any = mine >= n_closest;
                     pid = is_any ? __ldg(&q.shadow[mine - n_closest]) : __ldg(&q.cur[mine]);
                     const float4 o = ps.ray_o[pid], d = is_any ? ps.shw_d[pid] : ps.ray_d[pid];
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(128, FOVPT_TRACE_BLOCKS) k_trace(SceneDev S, P
             const unsigned mn = __ballot_sync(FULL, node), ml = __ballot_sync(FULL, leaf);
             const int n_active = __popc(mn | ml);
             if (n_active == 0) break;                                    // warp drained
-            if (!exhausted && n_active <= 32 - kFetchMin) break;         // enough idle lanes: refill first
+            if (!exhausted && n_active <= (int)cap - fetch_min) break;   // enough idle lanes: refill first
             if (FOVPT_LEAF_NUM * __popc(ml) <= FOVPT_LEAF_DEN * __popc(mn)) {
 #ifdef FOVPT_TRACE_STATS
                 st_node_exec++; st_node_lanes += __popc(mn);

@@ -149,6 +149,16 @@ CORNELL_CAMERA = CameraSpec(eye=(278.0, 273.0, -800.0), lookat=(278.0, 273.0, 0.
 SPONZA_CAMERA = CameraSpec(eye=(-1293.07, 154.681, 0.0), lookat=(200.0, 0.0, 0.0), fovy=45.0)
 
 
+def cornell_with_shadow_catcher() -> Scene:
+    """Cornell box whose floor is a shadow catcher (reference MATERIAL_FLAG_SHADOW_CATCHER, Material.h:9:
+    deviceProgram.cu:646-651 pass-through for secondary rays, :691-694 + SampleShadow :347-387 alpha accumulation)"""
+    sc = cornell_box()
+    m = sc.meshes[0].material.copy()
+    m.flags = 1
+    sc.meshes[0].material = m
+    return sc
+
+
 def write_obj(scene: Scene, path: str):
     """OBJ + MTL in the form the reference loader handles: one ``o`` group / one ``usemtl`` each,
     Kd -> Material.color, Ke -> Material.emission (Model.cpp:190-191)."""

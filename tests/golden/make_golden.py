@@ -93,8 +93,12 @@ def main():
     R.close(); R = orc.Oracle("reference")
     a2, f2, c2 = small_frame(R, sc, scenes.CORNELL_CAMERA, 160, 90, scenes.constant_probe(16, 8, 2.5), 12, 40, gaze=(20, 70))   # offset wraps (gaze < R)
     R.close()
+    R = orc.Oracle("reference")
+    a3, f3, c3 = small_frame(R, scenes.cornell_with_shadow_catcher(), scenes.CORNELL_CAMERA, 160, 90, scenes.sky_probe(64, 32, seed=4), 12, 40)
+    R.close()
     np.savez_compressed(os.path.join(OUT, "frames.npz"), accum_sky=a1, frame_sky=f1, counts_sky=np.array([c1[k] for k in sorted(c1)], np.uint64),
-                        accum_wrap=a2, frame_wrap=f2, counts_wrap=np.array([c2[k] for k in sorted(c2)], np.uint64))
+                        accum_wrap=a2, frame_wrap=f2, counts_wrap=np.array([c2[k] for k in sorted(c2)], np.uint64),
+                        accum_catcher=a3, frame_catcher=f3, counts_catcher=np.array([c3[k] for k in sorted(c3)], np.uint64))
     # --- loader: the reference's loadOBJ on the committed Cornell OBJ
     obj = os.path.join(ROOT, "assets", "cornell.obj")
     scenes.write_obj(scenes.cornell_box(), obj)

@@ -265,6 +265,21 @@ def test_frame_textured_disney_sky(gpu, port):
     r.close(); o.close()
 
 
+def test_frame_shadow_catcher(gpu, port):
+    """MATERIAL_FLAG_SHADOW_CATCHER floor: secondary rays pass through it (deviceProgram.cu:646-651), primary hits accumulate
+    SampleShadow into alpha and composite the backplate (:691-694, :347-387, :558); extra wavefront iterations cover the pass-throughs"""
+    w, h, ri, ro = 320, 180, 24, 80
+    sc = scenes.cornell_with_shadow_catcher()
+    r, o, lp, accum, frame = make_pair(gpu, port, sc, scenes.CORNELL_CAMERA, w, h, scenes.sky_probe(64, 32, seed=4), ri, ro)
+    o.render(lp, port.FovCfg.sv5(inner_radius=ri, outer_radius=ro), port.Opts.sv5())
+    r.render()
+    g = r.downloadAccum(); gf = r.downloadPixels()
+    assert np.isfinite(g).all()
+    assert rmse(accum, g) < 1e-4 and close_fraction(accum, g) > 0.99
+    assert (gf == frame).mean() > 0.99
+    r.close(); o.close()
+
+
 def test_frame_accumulation_depth8(gpu, port):
     """the C2 configuration scaled down: depth 8, every ring seeded with the running subframe index and
     accumulated with the vmv2 lerp (PT_sv4_vmv2/deviceProgram.cu:545-553) over 3 frames"""

@@ -116,6 +116,20 @@ def test_foveated_frames_golden(port):
     assert (bits(a) == bits(g["accum_wrap"])).all() and (f == g["frame_wrap"]).all() and (c == g["counts_wrap"]).all()
 
 
+def test_shadow_catcher_frame_golden(port):
+    """a frame with a shadow-catcher floor (Material.h:9, deviceProgram.cu:646-651,691-694,347-387) matches the reference build"""
+    g = np.load(os.path.join(GOLDEN, "frames.npz"))
+    o = port.Oracle("port")
+    o.add_scene(scenes.cornell_with_shadow_catcher()); o.commit(); o.set_probe(scenes.sky_probe(64, 32, seed=4))
+    cam = scenes.CORNELL_CAMERA
+    U, V, W = o.camera_uvw(cam.eye, cam.lookat, cam.up, cam.fovy, 160 / 90)
+    lp, accum, frame = o.make_params(160, 90, cam.eye, U, V, W)
+    o.render(lp, port.FovCfg.sv5(inner_radius=12, outer_radius=40), port.Opts.sv5(threads=1, jitter_yx=1))
+    c = o.counters(); o.close()
+    assert (bits(accum) == bits(g["accum_catcher"])).all() and (frame == g["frame_catcher"]).all()
+    assert (np.array([c[k] for k in sorted(c)], np.uint64) == g["counts_catcher"]).all()
+
+
 def test_bvh_never_changes_a_hit(P):
     """closest / any-hit through the canonical BVH == brute force over all triangles"""
     sc = scenes.atrium(detail=0.12)

@@ -72,3 +72,20 @@ def test_primary_hits_bitexact(ref):
     for x, y in zip(got["reference"], got["port"]):
         assert (x.view(np.uint32) == y.view(np.uint32)).all()
     assert (got["port"][0] >= 0).mean() > 0.3
+
+
+def test_shadow_catcher_frame_bitexact(ref):
+    """MATERIAL_FLAG_SHADOW_CATCHER (Material.h:9): secondary rays pass through the catcher (deviceProgram.cu:646-651),
+    primary hits accumulate SampleShadow into alpha (:691-694, :347-387) and composite the backplate (:558)"""
+    sc = scenes.cornell_with_shadow_catcher()
+    out = {}
+    for kind in ("reference", "port"):
+        o = ref.Oracle(kind)
+        o.add_scene(sc); o.commit(); o.set_probe(scenes.sky_probe(64, 32, seed=4))
+        cam = scenes.CORNELL_CAMERA
+        U, V, W = o.camera_uvw(cam.eye, cam.lookat, cam.up, cam.fovy, 160 / 90)
+        lp, accum, frame = o.make_params(160, 90, cam.eye, U, V, W)
+        o.render(lp, ref.FovCfg.sv5(inner_radius=12, outer_radius=40), ref.Opts.sv5(jitter_yx=1))
+        out[kind] = (accum.copy(), frame.copy(), o.counters()); o.close()
+    a, b = out["reference"], out["port"]
+    assert (bits(a[0]) == bits(b[0])).all() and (a[1] == b[1]).all() and a[2] == b[2]

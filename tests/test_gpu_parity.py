@@ -280,6 +280,32 @@ def test_frame_shadow_catcher(gpu, port):
     r.close(); o.close()
 
 
+def test_frame_material_zoo(gpu, port):
+    """every Disney parameter the BSDF reads, randomised per mesh (seeded): metallic, subsurface (hemisphere-sampled branch),
+    specular, roughness, specularTint, clearcoat(+gloss), transmission 0 / 0.4 / 1, eta 0 (index of refraction inferred from
+    specular, Material.h:40-46) and emissive surfaces -- Disney.cuh:152-427 through every sampling branch of SURVEY A.3"""
+    w, h, ri, ro = 320, 180, 24, 80
+    rng = np.random.default_rng(77)
+    sc = scenes.cornell_box()
+    for i, mesh in enumerate(sc.meshes):
+        m = Material.default()
+        m.color.set(rng.random(3)); m.metallic = rng.random(); m.subsurface = rng.random() if i % 2 else 0.0
+        m.specular = rng.random(); m.roughness = 0.05 + 0.95 * rng.random(); m.specularTint = rng.random()
+        m.clearcoat = rng.random(); m.clearcoatGloss = rng.random(); m.transmission = float([0.0, 0.4, 1.0, rng.random()][i % 4])
+        m.eta = 0.0 if i % 3 == 0 else 1.0 + rng.random()
+        m.emission.set((0.0, 0.0, 0.0) if i % 4 else tuple(2.0 * rng.random(3)))
+        mesh.material = m
+    r, o, lp, accum, frame = make_pair(gpu, port, sc, scenes.CORNELL_CAMERA, w, h, scenes.sky_probe(64, 32, seed=4), ri, ro, max_depth=6)
+    o.render(lp, port.FovCfg.sv5(inner_radius=ri, outer_radius=ro), port.Opts.sv5(max_depth=6))
+    r.render()
+    g = r.downloadAccum(); gf = r.downloadPixels()
+    assert np.isfinite(g).all()
+    assert rmse(accum, g) < 1e-3 and close_fraction(accum, g, 1e-3) > 0.98      # glossy + refractive chains amplify last-ulp differences
+    assert abs(accum[..., :3].mean() - g[..., :3].mean()) < 1e-3 * accum[..., :3].mean()
+    assert (gf == frame).mean() > 0.98
+    r.close(); o.close()
+
+
 def test_frame_accumulation_depth8(gpu, port):
     """the C2 configuration scaled down: depth 8, every ring seeded with the running subframe index and
     accumulated with the vmv2 lerp (PT_sv4_vmv2/deviceProgram.cu:545-553) over 3 frames"""

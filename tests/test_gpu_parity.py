@@ -352,6 +352,39 @@ def test_gaze_near_border_wraps_like_the_reference(gpu, port, gaze):
     r.close(); o.close()
 
 
+@pytest.mark.parametrize("seed", list(range(10)))
+def test_random_configurations(gpu, port, seed):
+    """seeded fuzz over the launch-parameter space: odd frame sizes (not multiples of 4), gaze anywhere incl. on the border,
+    radii from degenerate to larger than the frame, ring spp, depth 0..6, foveated / uniform, accumulation on / off, two frames"""
+    rng = np.random.default_rng(1000 + seed)
+    w, h = int(rng.integers(17, 200)), int(rng.integers(17, 120))
+    ri = int(rng.integers(0, 40)); ro = ri + int(rng.integers(0, 80))
+    gaze = (int(rng.integers(0, w)), int(rng.integers(0, h)))
+    spp = (int(rng.integers(1, 5)), int(rng.integers(1, 7)), int(rng.integers(1, 9)))
+    depth = int(rng.integers(0, 7)); fov = int(rng.integers(0, 4) != 0); ext = int(rng.integers(0, 2))
+    sc = [scenes.cornell_box, scenes.cornell_with_shadow_catcher, lambda: scenes.atrium(detail=0.12)][seed % 3]()
+    cam = scenes.SPONZA_CAMERA if seed % 3 == 2 else scenes.CORNELL_CAMERA
+    probe = scenes.sky_probe(32, 16, seed=seed) if seed % 2 else scenes.constant_probe(8, 4, 1.5)
+    kw = dict(max_depth=depth, foveated=fov, spp_periphery=spp[0], spp_mid=spp[1], spp_fovea=spp[2], spp_uniform=spp[0],
+              accumulate=ext, seed_all_passes_with_subframe=ext)
+    r, o, lp, accum, frame = make_pair(gpu, port, sc, cam, w, h, probe, ri, ro, gaze=gaze, **kw)
+    fc = port.FovCfg.sv5(foveated=fov, inner_radius=ri, outer_radius=ro, spp_periphery=spp[0], spp_mid=spp[1], spp_fovea=spp[2], spp_uniform=spp[0])
+    op = port.Opts.sv5(threads=1, max_depth=depth, accumulate=ext, seed_all_passes_with_subframe=ext)
+    for _ in range(2):
+        o.render(lp, fc, op); r.render()
+    g = r.downloadAccum(); gf = r.downloadPixels()
+    cfg = f"{w}x{h} gaze {gaze} radii {ri}/{ro} spp {spp} depth {depth} fov {fov} ext {ext}"
+    assert np.isfinite(g).all(), cfg
+    assert (g[..., 3] == accum[..., 3]).all(), cfg                      # exactly the same pixels written
+    wr = accum[..., 3] == 1.0
+    if wr.any():
+        assert rmse(accum[wr][None], g[wr][None]) < 1e-3, cfg
+        assert close_fraction(accum[wr][None], g[wr][None], 1e-3) > 0.97, cfg
+        assert (gf[wr] == frame[wr]).mean() > 0.97, cfg
+    assert r.launchParams.frame.subframe_index == lp.frame.subframe_index == 2
+    r.close(); o.close()
+
+
 def test_single_launch_matches_oracle_launch(gpu, port):
     """fovpt_launch == one optixLaunch (SimplePathtracer.cpp:148-157): drive the three passes by hand,
     as the reference's render() body does, and compare with the fused fovpt_render_frame"""

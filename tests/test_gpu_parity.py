@@ -64,7 +64,7 @@ def make_pair(gpu, port, scene, cam, w, h, probe_img, ri, ro, gaze=None, **cfgkw
 
 def rmse(a, g):
     a = a[..., :3].astype(np.float64); g = g[..., :3].astype(np.float64)
-    return ((a - g) ** 2).mean() / (a.mean() ** 2 + 1e-30)
+    return ((a - g) ** 2).mean() / (a.mean() ** 2 + 1e-6)      # + 1e-6: black frames (depth 0) differ by fma rounding of ~1e-8 only
 
 
 def pass_params(w, h, gaze, ri, ro):
@@ -352,7 +352,7 @@ def test_gaze_near_border_wraps_like_the_reference(gpu, port, gaze):
     r.close(); o.close()
 
 
-@pytest.mark.parametrize("seed", list(range(10)))
+@pytest.mark.parametrize("seed", list(range(int(__import__("os").environ.get("FOVPT_FUZZ_SEEDS", "10")))))
 def test_random_configurations(gpu, port, seed):
     """seeded fuzz over the launch-parameter space: odd frame sizes (not multiples of 4), gaze anywhere incl. on the border,
     radii from degenerate to larger than the frame, ring spp, depth 0..6, foveated / uniform, accumulation on / off, two frames"""

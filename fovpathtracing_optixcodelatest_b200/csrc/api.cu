@@ -490,7 +490,7 @@ int fovpt_scene_commit(fovpt_ctx* c, uint64_t* traversable_out)
     cudaEventRecord(e0, c->stream);
     int leaf_max = 2;        // measured on C3: 2 -> 4.49 ms, 3 -> 4.52 ms, 4 -> 4.56 ms of k_trace per frame
     if (const char* e = getenv("FOVPT_LEAF_MAX")) { const int v = atoi(e); if (v >= 1 && v <= 4) leaf_max = v; }   // tuning knob
-    cudaError_t be = build_bvh(c->d_vtx, c->d_idx, (uint32_t)nt, leaf_max, kBvhWide, c->stream, &c->bvh, &c->launches);
+    cudaError_t be = build_bvh(c->d_vtx, c->d_idx, c->d_tri_mesh, (uint32_t)nt, leaf_max, kBvhWide, c->stream, &c->bvh, &c->launches);
     cudaEventRecord(e1, c->stream);
     if (be != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return cuda_fail(c, be, "build_bvh"); }
     cudaEventSynchronize(e1);

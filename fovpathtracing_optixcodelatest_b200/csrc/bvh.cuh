@@ -14,7 +14,7 @@
 //           Two sectors per node instead of four: the traversal kernels are bound by L1 sector
 //           throughput (profiles/), so bytes per visited node are what buys speed.
 //   tris  : 48 B per triangle in leaf (Morton) order = 3 x float4
-//             (v0.xyz, bits(global id)), (e1.xyz, 0), (e2.xyz, 0)      [fx_make_tri of fovpt_exact.h]
+//             (v0.xyz, bits(global id)), (e1.xyz, bits(mesh id)), (e2.xyz, 0)      [fx_make_tri of fovpt_exact.h]
 // Algorithmic bytes per ray are counted on the oracle's canonical binary tree:
 // 64 per node visit + 48 per triangle test + 48 (ray in, hit out); see DESIGN.md section 5.
 #pragma once

@@ -51,7 +51,7 @@ __global__ void k_init_bounds(int* b)
 }
 
 // vertices: global float3 soup ; indices: global (already rebased) uint3
-__global__ void k_tri_setup(const float* __restrict__ vtx, const uint32_t* __restrict__ idx, uint32_t ntri,
+__global__ void k_tri_setup(const float* __restrict__ vtx, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ tri_mesh, uint32_t ntri,
                             float4* __restrict__ tri_rec, float4* __restrict__ box_lo, float4* __restrict__ box_hi,
                             int* __restrict__ bounds)
 {
@@ -64,7 +64,7 @@ __global__ void k_tri_setup(const float* __restrict__ vtx, const uint32_t* __res
         fx_vec3 C = {vtx[3 * (size_t)ic], vtx[3 * (size_t)ic + 1], vtx[3 * (size_t)ic + 2]};
         fx_tri t = fx_make_tri(A, B, C);
         tri_rec[3 * (size_t)i + 0] = make_float4(t.v0.x, t.v0.y, t.v0.z, __int_as_float((int)i));
-        tri_rec[3 * (size_t)i + 1] = make_float4(t.e1.x, t.e1.y, t.e1.z, 0.f);
+        tri_rec[3 * (size_t)i + 1] = make_float4(t.e1.x, t.e1.y, t.e1.z, __int_as_float((int)tri_mesh[i]));   // mesh id rides along: saves the shading kernel a dependent load
         tri_rec[3 * (size_t)i + 2] = make_float4(t.e2.x, t.e2.y, t.e2.z, 0.f);
         lo[0] = fminf(A.x, fminf(B.x, C.x)); hi[0] = fmaxf(A.x, fmaxf(B.x, C.x));
         lo[1] = fminf(A.y, fminf(B.y, C.y)); hi[1] = fmaxf(A.y, fmaxf(B.y, C.y));
@@ -588,7 +588,7 @@ __global__ void k_gather_tris(uint32_t n, const uint32_t* __restrict__ sorted_id
 template <typename T>
 static cudaError_t dalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T) + 32); }
 
-cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, uint32_t ntri, int leaf_max, int wide, cudaStream_t st,
+cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, const uint32_t* d_tri_mesh, uint32_t ntri, int leaf_max, int wide, cudaStream_t st,
                       BuiltBvh* out, uint64_t* launches)
 {
     const size_t nstride = wide == 8 ? 6 : 4;          // uint4 per node
@@ -618,7 +618,7 @@ cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, uint32_t ntri, 
     CK(cudaMemsetAsync(scal, 0, 8 * sizeof(uint32_t), st));
 
     k_init_bounds<<<1, 32, 0, st>>>(bounds);
-    k_tri_setup<<<gb, T, 0, st>>>(d_vtx, d_idx, ntri, tri_rec, box_lo, box_hi, bounds);
+    k_tri_setup<<<gb, T, 0, st>>>(d_vtx, d_idx, d_tri_mesh, ntri, tri_rec, box_lo, box_hi, bounds);
     k_morton<<<gb, T, 0, st>>>(box_lo, box_hi, ntri, bounds, keys[0], vals[0]);
     *launches += 3;
     int cur = 0;

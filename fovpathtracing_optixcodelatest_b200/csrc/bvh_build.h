@@ -19,9 +19,9 @@ struct BuiltBvh {
     float           bounds[6] = {0, 0, 0, 0, 0, 0};
 };
 
-// d_vtx: float3 soup of all meshes; d_idx: uint3 per triangle, already rebased to the soup.
+// d_vtx: float3 soup of all meshes; d_idx: uint3 per triangle, already rebased to the soup; d_tri_mesh: mesh id per triangle.
 // Synchronises the stream (the caller is a one-off setup path, like optixAccelBuild + SYNC).
-cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, uint32_t ntri, int leaf_max, int wide, cudaStream_t st,
+cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, const uint32_t* d_tri_mesh, uint32_t ntri, int leaf_max, int wide, cudaStream_t st,
                       BuiltBvh* out, uint64_t* launches);
 void free_bvh(BuiltBvh* b);
 

@@ -265,7 +265,10 @@ __device__ __forceinline__ int cdf_lower_bound(const float* __restrict__ a, int 
 // bound inside [g[k], g[k+1]] (lower_bound is monotone and k / kGuide <= u < (k+1) / kGuide holds exactly,
 // kGuide being a power of two), so searching only that range returns the SAME index as the reference's
 // full-row binary search (Probe.cuh:119-136,147-153) with 1-3 dependent loads instead of 10-11 per axis.
-constexpr int kGuide = 128;
+#ifndef FOVPT_GUIDE
+#define FOVPT_GUIDE 512
+#endif
+constexpr int kGuide = FOVPT_GUIDE;
 struct ProbeGuide { const uint16_t* gy = nullptr; const uint16_t* gx = nullptr; };
 
 // one importance sample of the probe: row by cdfY then column by that row's cdfX (Probe.cuh:138-169)

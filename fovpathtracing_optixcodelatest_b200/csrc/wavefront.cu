@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(128, FOVPT_SHADE_BLOCKS) k_shade(FrameDev F, S
         const float3 wo = -rd;
         const float3 N = n0 * copysignf(1.0f, dot3(wo, n0));
         const float3 P = ro + h4.x * rd;                         // :636-638
-        const uint32_t mesh = __ldg(&S.tri_mesh[gid]);
+        const uint32_t mesh = (uint32_t)__float_as_int(tb.w);      // rides in the triangle record (bvh_build.cu k_tri_setup)
         const MaterialBlob* M = S.materials + mesh;
         const int mflags = __ldg(&M->flags);
         float4 al = ps.alpha[pid];

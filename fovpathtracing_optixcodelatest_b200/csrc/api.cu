@@ -188,7 +188,7 @@ void fill_frame(fovpt_ctx* c, const LaunchParamsBlob& lp, const std::vector<Pass
     }
     *total_li = li;
     F->max_depth = c->cfg.max_depth; F->tmin = c->cfg.tmin; F->tmax = c->cfg.tmax; F->exposure = c->cfg.exposure;
-    F->accumulate = c->cfg.accumulate; F->skip_wasted = c->cfg.skip_wasted_trace;
+    F->accumulate = c->cfg.accumulate; F->skip_wasted = c->cfg.skip_wasted_trace; F->filter = c->cfg.filter;
     F->tile_owner = c->d_tile_owner; F->tile_size = c->tile_size; F->tiles_x = c->tiles_x; F->tiles_y = c->tiles_y; F->rank = c->rank;
 }
 
@@ -282,7 +282,7 @@ int run_frame(fovpt_ctx* c, const LaunchParamsBlob& lp, const std::vector<PassHo
             launch_resolve_li(c->L, F, ch.pass, ch.row0, ch.row1, ch.pid_base, c->needed, c->ps, c->li_backplate, c->li_color);
         }
     }
-    { Timed t(c, K_RESOLVE); launch_resolve_px(c->L, F, c->owner_map, c->li_color, c->cfg.fast_math != 0); }
+    { Timed t(c, K_RESOLVE); launch_resolve_px(c->L, F, c->owner_map, c->li_color, c->needed, c->cfg.fast_math != 0); }
     cudaEventRecord(c->ev_frame1, c->stream);
     c->frame_timed = true;
     c->frames++;
@@ -343,7 +343,7 @@ void fovpt_default_config(fovpt_config* k)
     memset(k, 0, sizeof(*k));
     k->max_depth = 4; k->tmin = 0.01f; k->tmax = 1e16f; k->exposure = 16.0f; k->accumulate = 0; k->foveated = 1;
     k->inner_radius = 74; k->outer_radius = 241; k->spp_periphery = 8; k->spp_mid = 16; k->spp_fovea = 32; k->spp_uniform = 4;
-    k->seed_all_passes_with_subframe = 0; k->skip_wasted_trace = 1; k->fast_math = 0;
+    k->seed_all_passes_with_subframe = 0; k->skip_wasted_trace = 1; k->fast_math = 0; k->filter = 0;
 }
 
 int fovpt_create(fovpt_ctx** out, int device, void* stream)
@@ -402,6 +402,7 @@ int fovpt_set_config(fovpt_ctx* c, const fovpt_config* k)
     if (k->max_depth < 0 || k->max_depth > 200) return fail(c, "max_depth out of range");
     if (k->foveated && (k->inner_radius < 0 || k->outer_radius < k->inner_radius)) return fail(c, "bad radii");
     if (k->spp_periphery <= 0 || k->spp_mid <= 0 || k->spp_fovea <= 0 || k->spp_uniform <= 0) return fail(c, "spp must be positive");
+    if (k->filter < 0 || k->filter > 1) return fail(c, "filter must be 0 (box) or 1 (bilinear)");
     c->cfg = *k;
     return 0;
 }

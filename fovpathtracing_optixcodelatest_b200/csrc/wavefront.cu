@@ -429,16 +429,43 @@ __global__ void k_resolve_li(FrameDev F, int pass, unsigned row0, unsigned row1,
 
 // ------------------------------------------------------------------ k_resolve_px
 // per owned pixel: fetch its owner's colour, optional accumulation lerp, exposure + Reinhard + sRGB8 (:558-600)
+// F.filter == 1: instead of the reference's box splat, a pixel of a sub-sampled ring (fill > 1) blends its own launch
+// index with the three neighbours of the same pass on the side the pixel lies on, weights = distance from the block
+// centre in block units (bilinear reconstruction; the reference's Filter.h is an empty class).  Neighbours that were
+// not rendered (outside the ring / not owned by this rank) fall back to the pixel's own sample.
+__device__ __forceinline__ float3 filtered_color(const FrameDev& F, const PassDev& P, uint32_t li, int X, int Y,
+                                                 const float4* __restrict__ li_color, const uint8_t* __restrict__ needed)
+{
+    const float4 c = li_color[P.li_base + li];
+    const float3 own = f3(c.x, c.y, c.z);
+    if (!F.filter || P.fill <= 1u) return own;
+    const int lx = (int)(li % P.lw), ly = (int)(li / P.lw);
+    const float half = 0.5f * (float)(P.fill - 1u);
+    const float dx = ((float)X - ((float)(lx * (int)P.factor + P.off_x) + half)) / (float)P.factor;
+    const float dy = ((float)Y - ((float)(ly * (int)P.factor + P.off_y) + half)) / (float)P.factor;
+    const int sx = dx < 0.f ? -1 : 1, sy = dy < 0.f ? -1 : 1;
+    const float wx = fminf(fabsf(dx), 1.f), wy = fminf(fabsf(dy), 1.f);
+    auto fetch = [&](int ax, int ay) {
+        if (ax < 0 || ay < 0 || ax >= (int)P.lw || ay >= (int)P.lh) return own;
+        const uint32_t j = (uint32_t)ay * P.lw + (uint32_t)ax;
+        if (!needed[P.li_base + j]) return own;
+        const float4 v = li_color[P.li_base + j];
+        return f3(v.x, v.y, v.z);
+    };
+    const float3 c10 = fetch(lx + sx, ly), c01 = fetch(lx, ly + sy), c11 = fetch(lx + sx, ly + sy);
+    return mix3(mix3(own, c10, wx), mix3(c01, c11, wx), wy);
+}
+
 template <bool FAST>
-__global__ void k_resolve_px(FrameDev F, const uint32_t* __restrict__ owner_map, const float4* __restrict__ li_color)
+__global__ void k_resolve_px(FrameDev F, const uint32_t* __restrict__ owner_map, const float4* __restrict__ li_color,
+                             const uint8_t* __restrict__ needed)
 {
     const size_t npix = (size_t)F.w * F.h;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
         const uint32_t own = owner_map[i];
         if (own == kNoOwner) continue;
         const PassDev& P = F.pass[own >> 28];
-        const float4 c = li_color[P.li_base + (own & 0x0fffffffu)];
-        float3 acc = f3(c.x, c.y, c.z);
+        float3 acc = filtered_color(F, P, own & 0x0fffffffu, (int)(i % F.w), (int)(i / F.w), li_color, needed);
         if (F.accumulate && P.subframe > 0 && !P.redraw) {       // PT_sv4_vmv2/deviceProgram.cu:545-553
             acc = f3(fmaxf(0.f, fminf(acc.x, 10.f)), fmaxf(0.f, fminf(acc.y, 10.f)), fmaxf(0.f, fminf(acc.z, 10.f)));
             const float a = 1.0f / (float)(P.subframe + 1);
@@ -553,10 +580,10 @@ void launch_resolve_li(const LaunchCfg& L, const FrameDev& F, int pass, unsigned
 {
     k_resolve_li<<<L.grid_light, 256, 0, L.stream>>>(F, pass, row0, row1, pid_base, needed, ps, li_backplate, li_color);
 }
-void launch_resolve_px(const LaunchCfg& L, const FrameDev& F, const uint32_t* owner_map, const float4* li_color, bool fast)
+void launch_resolve_px(const LaunchCfg& L, const FrameDev& F, const uint32_t* owner_map, const float4* li_color, const uint8_t* needed, bool fast)
 {
-    if (fast) k_resolve_px<true><<<L.grid_light, 256, 0, L.stream>>>(F, owner_map, li_color);
-    else k_resolve_px<false><<<L.grid_light, 256, 0, L.stream>>>(F, owner_map, li_color);
+    if (fast) k_resolve_px<true><<<L.grid_light, 256, 0, L.stream>>>(F, owner_map, li_color, needed);
+    else k_resolve_px<false><<<L.grid_light, 256, 0, L.stream>>>(F, owner_map, li_color, needed);
 }
 void launch_probe_guides(const LaunchCfg& L, const ProbeBlob& p, uint16_t* gy, uint16_t* gx)
 {

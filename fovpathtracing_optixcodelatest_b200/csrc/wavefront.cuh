@@ -74,7 +74,7 @@ struct FrameDev {
     // config
     int   max_depth;
     float tmin, tmax, exposure;
-    int   accumulate, skip_wasted;
+    int   accumulate, skip_wasted, filter;
     // partition
     const uint8_t* tile_owner;
     int   tile_size, tiles_x, tiles_y, rank;

@@ -24,7 +24,7 @@ void launch_shade(const LaunchCfg&, const FrameDev&, const SceneDev&, const Path
 void launch_swap(const LaunchCfg&, uint32_t* counts, int consumed_slot);
 void launch_resolve_li(const LaunchCfg&, const FrameDev&, int pass, unsigned row0, unsigned row1, unsigned pid_base,
                        const uint8_t* needed, const PathState&, const float4* li_backplate, float4* li_color);
-void launch_resolve_px(const LaunchCfg&, const FrameDev&, const uint32_t* owner_map, const float4* li_color, bool fast);
+void launch_resolve_px(const LaunchCfg&, const FrameDev&, const uint32_t* owner_map, const float4* li_color, const uint8_t* needed, bool fast);
 void launch_probe_guides(const LaunchCfg&, const ProbeBlob&, uint16_t* gy, uint16_t* gx);
 void launch_primary_hits(const LaunchCfg&, const FrameDev&, const SceneDev&, int32_t* tri, float* tuv, float* dir);
 void launch_trace_query(const LaunchCfg&, const SceneDev&, const float* rays, size_t n, int mode, int32_t* tri, float* tuv);

@@ -21,6 +21,7 @@ class Config(C.Structure):
         ("accumulate", C.c_int32), ("foveated", C.c_int32), ("inner_radius", C.c_int32), ("outer_radius", C.c_int32),
         ("spp_periphery", C.c_int32), ("spp_mid", C.c_int32), ("spp_fovea", C.c_int32), ("spp_uniform", C.c_int32),
         ("seed_all_passes_with_subframe", C.c_int32), ("skip_wasted_trace", C.c_int32), ("fast_math", C.c_int32),
+        ("filter", C.c_int32),
     ]
 
 

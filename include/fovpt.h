@@ -42,6 +42,11 @@ typedef struct fovpt_config {
                                * images are identical either way                                         */
     int32_t fast_math;        /* 0 = IEEE sin/cos/pow/log in shading; 1 = SFU approximations, the       *
                                * reference's --use_fast_math build (CMakeLists.txt:181)                  */
+    int32_t filter;           /* reconstruction of the sub-sampled rings.  0 = the reference's box splat  *
+                               * (each launch index fills fillSize^2 pixels, deviceProgram.cu:546-556);   *
+                               * 1 = bilinear interpolation between neighbouring launch indices of the    *
+                               * same ring -- fills the reference's empty Filter.h (Filter.h:3-7); no      *
+                               * reference semantics exist for it (SURVEY 8a R-FILTER, 8f-3)               */
 } fovpt_config;
 
 typedef struct fovpt_stats {

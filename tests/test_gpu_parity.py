@@ -470,6 +470,41 @@ def test_moving_gaze_stereo_pair(gpu, port):
         r.close(); o.close()
 
 
+def test_reconstruction_filter(gpu, port):
+    """config.filter (fills the reference's empty Filter.h; no reference semantics, so properties only): 0 is the box splat
+    = bit-identical to the default; 1 leaves the full-resolution fovea untouched, keeps a constant image constant,
+    preserves the mean radiance and removes most of the block-edge steps of the periphery"""
+    w, h, ri, ro = 384, 216, 24, 80
+    sc, cam, probe = scenes.atrium(detail=0.2), scenes.SPONZA_CAMERA, scenes.sky_probe(64, 32, 2)
+    out = {}
+    for f in (None, 0, 1):
+        r, o, lp, _, _ = make_pair(gpu, port, sc, cam, w, h, probe, ri, ro, **({} if f is None else {"filter": f}))
+        r.render(); out[f] = r.downloadAccum().copy()
+        r.close(); o.close()
+    assert (bits(out[None]) == bits(out[0])).all()
+    box, fil = out[0][..., :3].astype(np.float64), out[1][..., :3].astype(np.float64)
+    y, x = np.mgrid[0:h, 0:w]; rr = np.hypot(x - w // 2, y - h // 2)
+    assert (box[rr < ri - 2] == fil[rr < ri - 2]).all()                       # fovea: fill = 1, nothing to reconstruct
+    per = rr > ro + 8
+    assert (box[per] != fil[per]).any()
+    lum = lambda a: a.sum(axis=2)
+    edge = np.zeros((h, w), bool); edge[:, 3:-1:4] = True                     # between periphery blocks x = 4k+3 | 4k+4
+    m = edge[:, :-1] & per[:, :-1] & per[:, 1:]
+    step_box = np.abs(lum(box)[:, 1:] - lum(box)[:, :-1])[m].mean()
+    step_fil = np.abs(lum(fil)[:, 1:] - lum(fil)[:, :-1])[m].mean()
+    assert step_fil < 0.5 * step_box
+    assert abs(box[per].mean() - fil[per].mean()) < 0.03 * box[per].mean()
+    # constant image stays constant
+    r = gpu.SampleRenderer(scenes.Scene(), 0)
+    r.resize((64, 48)); r.setCamera(scenes.CORNELL_CAMERA); r.setProbe(gpu.ProbeData(scenes.constant_probe(8, 4, 2.5)).BuildCDF())
+    r.launchParams.frame.c_x, r.launchParams.frame.c_y = 32, 24
+    cfg = gpu.native.default_config(); cfg.inner_radius, cfg.outer_radius, cfg.filter = 4, 12, 1; r.setConfig(cfg)
+    r.render()
+    a = r.downloadAccum()
+    assert np.allclose(a[..., :3][a[..., 3] == 1.0], 2.5)
+    r.close()
+
+
 # ------------------------------------------------------------------------------------------- API behaviour
 def test_api_contract_and_errors(gpu):
     sc = scenes.cornell_box()
@@ -490,6 +525,14 @@ def test_api_contract_and_errors(gpu):
     with pytest.raises(RuntimeError):
         ctx.trace(np.zeros((1, 8), np.float32), 0)               # scene not committed
     ctx.close(); r.close()
+
+
+def test_c_program_drives_the_abi(gpu, tmp_path):
+    """tests/c/abi_smoke.c: a C99 program builds a scene and traces rays through include/fovpt.h"""
+    import subprocess
+    from test_host_logic import _build_c_abi_smoke
+    out = subprocess.run([_build_c_abi_smoke(tmp_path)], capture_output=True, text=True)
+    assert out.returncode == 0 and "C ABI ok" in out.stdout, out.stdout + out.stderr
 
 
 def test_empty_scene_shows_backplate(gpu):

@@ -22,6 +22,22 @@ def test_library_exports_every_declared_symbol():
     native.load_library()
 
 
+def _build_c_abi_smoke(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "abi_smoke")
+    pkg = os.path.join(ROOT, "fovpathtracing_optixcodelatest_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "c", "abi_smoke.c"),
+                    "-o", exe, "-L", pkg, "-lfovpt", f"-Wl,-rpath,{pkg}"], check=True)
+    return exe
+
+
+def test_header_is_plain_c_and_library_links_from_c(tmp_path):
+    """include/fovpt.h compiles as pedantic C99 and a C program drives libfovpt.so (here, without a GPU: clean failure)"""
+    import subprocess
+    out = subprocess.run([_build_c_abi_smoke(tmp_path)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+
+
 def test_no_gpu_fails_loudly():
     import torch
     if torch.cuda.is_available():

@@ -170,7 +170,7 @@ __device__ __forceinline__ void shadow_resolve(const PathState& ps, uint32_t pid
 #define FOVPT_FETCH_MIN 8
 #endif
 #ifndef FOVPT_TRACE_BLOCKS
-#define FOVPT_TRACE_BLOCKS 8
+#define FOVPT_TRACE_BLOCKS 9
 #endif
 #ifndef FOVPT_LEAF_NUM
 #define FOVPT_LEAF_NUM 1      // run the leaf phase when LEAF_NUM * lanes_at_leaf > LEAF_DEN * lanes_at_node

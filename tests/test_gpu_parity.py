@@ -324,6 +324,28 @@ def test_frame_accumulation_depth8(gpu, port):
     r.close(); o.close()
 
 
+def test_converged_image_many_subframes(gpu, port):
+    """north_star: converged images agree within a stated relative MSE (< 1e-3) and per-pixel mean radiance.  32 accumulated
+    subframes (every ring accumulates, 1024 foveal spp) of the atrium with the HDR probe, GPU and oracle seeded identically"""
+    w, h, ri, ro = 192, 108, 14, 48
+    sc = scenes.atrium(detail=0.2)
+    r, o, lp, accum, frame = make_pair(gpu, port, sc, scenes.SPONZA_CAMERA, w, h, scenes.sky_probe(64, 32, 2), ri, ro,
+                                       max_depth=8, accumulate=1, seed_all_passes_with_subframe=1)
+    fc = port.FovCfg.sv5(inner_radius=ri, outer_radius=ro); op = port.Opts.sv5(max_depth=8, accumulate=1, seed_all_passes_with_subframe=1)
+    for _ in range(32):
+        o.render(lp, fc, op); r.render()
+    g = r.downloadAccum(); gf = r.downloadPixels()
+    wr = accum[..., 3] == 1.0
+    assert (g[..., 3] == accum[..., 3]).all()
+    a3, g3 = accum[wr][:, :3].astype(np.float64), g[wr][:, :3].astype(np.float64)
+    assert ((a3 - g3) ** 2).mean() / a3.mean() ** 2 < 1e-3                      # the north_star tolerance (measured: ~1e-6)
+    assert ((a3 - g3) ** 2).mean() / a3.mean() ** 2 < 1e-4
+    assert np.abs(a3 - g3).max(axis=1).mean() < 2e-3 * a3.mean()                 # mean per-pixel deviation of the radiance
+    assert (gf[wr] == frame[wr]).mean() > 0.98
+    assert r.launchParams.frame.subframe_index == 32
+    r.close(); o.close()
+
+
 def test_frame_uniform_c1(gpu, port):
     """BASELINE configs[0]: Cornell 512x512, 1 spp, depth 1, FOV_OFF"""
     wl = workloads.c1()

@@ -209,7 +209,10 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint64_t* __
 
 // ------------------------------------------------------------------ PLOC
 // node ids: >= 0 inner binary node, < 0 leaf = ~(global triangle id)
-constexpr int kPlocRadius = 16;
+#ifndef FOVPT_PLOC_RADIUS
+#define FOVPT_PLOC_RADIUS 16
+#endif
+constexpr int kPlocRadius = FOVPT_PLOC_RADIUS;
 constexpr int kPlocThreads = 256;
 
 __device__ __forceinline__ float union_area(const float4 alo, const float4 ahi, const float4 blo, const float4 bhi)

@@ -4,7 +4,8 @@
 //   k_tri_setup     per triangle: fx_make_tri record, AABB, scene bounds (atomic min/max)
 //   k_morton        63-bit Morton code of the AABB centre (21 bits per axis)
 //   radix sort      hand-written LSD sort, 8 x 8-bit passes over (u64 key, u32 triangle id):
-//                   k_radix_hist -> k_scan_u32 -> k_radix_scatter (stable, match_any ranking)
+//                   k_radix_hist -> scan -> k_radix_scatter (stable, match_any ranking); scans of more than
+//                   128 k entries run tiled over the whole GPU (k_scan_tile_sums / k_scan_tiles)
 //   PLOC            parallel locally-ordered clustering (Meister & Bittner 2018) over the Morton-ordered
 //                   triangles: every round each cluster finds, within +-kPlocRadius positions, the
 //                   neighbour whose merged box has the smallest surface area (k_ploc_nearest, boxes
@@ -15,8 +16,8 @@
 //                   and +24 % triangle tests per ray on the atrium).
 //   k_collapse4     breadth-first collapse of the binary tree into the 4-wide, 8-bit-quantised nodes of bvh.cuh:
 //                   a wide node takes a binary node's two children and twice replaces the child
-//                   of largest surface area by its own two children; subtrees with <= 4 triangles
-//                   become leaves and receive consecutive slots of the final triangle order.  One launch
+//                   of largest surface area by its own two children; subtrees with <= leaf_max (default 2, at
+//                   most 4) triangles become leaves and receive consecutive slots of the final triangle order.  One launch
 //                   per level, work queue + node allocation through device counters.
 //   k_gather_tris   48-byte triangle records into leaf order
 //
@@ -169,6 +170,46 @@ __global__ void __launch_bounds__(1024) k_scan_u32(uint32_t* __restrict__ data, 
         __syncthreads();
     }
     if (threadIdx.x == 0 && total_out) *total_out = carry;
+}
+
+// ---- three-step exclusive scan for large arrays: per-tile sums -> single-block scan of the sums -> per-tile scan + offset.
+// (k_scan_u32 alone walks the whole array with one CTA: fine for the 300 k-entry histograms, 10 ms per call at 10 M.)
+constexpr int SC_TILE = 2048;          // entries per CTA (256 threads x 8)
+
+__global__ void __launch_bounds__(256) k_scan_tile_sums(const uint32_t* __restrict__ data, uint32_t n, uint32_t* __restrict__ sums)
+{
+    __shared__ uint32_t ws[8];
+    const uint32_t base = blockIdx.x * SC_TILE;
+    uint32_t v = 0;
+    for (int r = 0; r < 8; ++r) { const uint32_t i = base + r * 256 + threadIdx.x; if (i < n) v += data[i]; }
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t t = 0; for (int w = 0; w < 8; ++w) t += ws[w]; sums[blockIdx.x] = t; }
+}
+
+__global__ void __launch_bounds__(256) k_scan_tiles(uint32_t* __restrict__ data, uint32_t n, const uint32_t* __restrict__ tile_offsets)
+{
+    __shared__ uint32_t ws[8];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = tile_offsets[blockIdx.x];
+    __syncthreads();
+    const uint32_t lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t base = blockIdx.x * SC_TILE;
+    for (int r = 0; r < 8; ++r) {
+        const uint32_t i = base + r * 256 + threadIdx.x;
+        const uint32_t v = i < n ? data[i] : 0u;
+        uint32_t x = v;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= (uint32_t)o) x += y; }
+        if (lane == 31) ws[wid] = x;
+        __syncthreads();
+        uint32_t before = carry;
+        for (uint32_t w = 0; w < wid; ++w) before += ws[w];
+        if (i < n) data[i] = before + x - v;
+        __syncthreads();
+        if (threadIdx.x == 255) carry = before + x;
+        __syncthreads();
+    }
 }
 
 __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in,
@@ -591,6 +632,17 @@ __global__ void k_gather_tris(uint32_t n, const uint32_t* __restrict__ sorted_id
 template <typename T>
 static cudaError_t dalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T) + 32); }
 
+// exclusive scan of data[0..n) in place; *total_out (device, may be null) receives the sum.  tile_sums: scratch of >= n / SC_TILE + 2 words
+static void scan_u32(uint32_t* data, uint32_t n, uint32_t* total_out, uint32_t* tile_sums, cudaStream_t st, uint64_t* launches)
+{
+    if (n <= 64u * SC_TILE) { k_scan_u32<<<1, 1024, 0, st>>>(data, n, total_out); *launches += 1; return; }
+    const uint32_t tiles = (n + SC_TILE - 1) / SC_TILE;
+    k_scan_tile_sums<<<tiles, 256, 0, st>>>(data, n, tile_sums);
+    k_scan_u32<<<1, 1024, 0, st>>>(tile_sums, tiles, total_out);
+    k_scan_tiles<<<tiles, 256, 0, st>>>(data, n, tile_sums);
+    *launches += 3;
+}
+
 cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, const uint32_t* d_tri_mesh, uint32_t ntri, int leaf_max, int wide, cudaStream_t st,
                       BuiltBvh* out, uint64_t* launches)
 {
@@ -618,6 +670,8 @@ cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, const uint32_t*
     CK(dalloc(&bounds, 8)); CK(dalloc(&keys[0], ntri)); CK(dalloc(&keys[1], ntri));
     CK(dalloc(&vals[0], ntri)); CK(dalloc(&vals[1], ntri)); CK(dalloc(&hist, 256 * (size_t)nblocks));
     CK(dalloc(&scal, 8)); CK(dalloc(&sorted, ntri));
+    uint32_t* tile_sums = nullptr;
+    CK(dalloc(&tile_sums, std::max<size_t>(ntri, 256 * (size_t)nblocks) / SC_TILE + 2));
     CK(cudaMemsetAsync(scal, 0, 8 * sizeof(uint32_t), st));
 
     k_init_bounds<<<1, 32, 0, st>>>(bounds);
@@ -628,10 +682,10 @@ cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, const uint32_t*
     for (int pass = 0; pass < 8; ++pass) {
         const int shift = pass * 8;
         k_radix_hist<<<nblocks, RS_THREADS, 0, st>>>(keys[cur], ntri, shift, hist, nblocks);
-        k_scan_u32<<<1, 1024, 0, st>>>(hist, 256 * nblocks, nullptr);
+        scan_u32(hist, 256 * nblocks, nullptr, tile_sums, st, launches);
         k_radix_scatter<<<nblocks, RS_THREADS, 0, st>>>(keys[cur], vals[cur], keys[1 - cur], vals[1 - cur], ntri, shift, hist, nblocks);
         cur = 1 - cur;
-        *launches += 3;
+        *launches += 2;
     }
     // scene pad needs the bounds on the host
     int hb[6];
@@ -669,12 +723,12 @@ cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, const uint32_t*
             k_ploc_nearest<<<g, kPlocThreads, 0, st>>>(n, clo[cb], chi[cb], nn);
             k_ploc_merge<<<g, kPlocThreads, 0, st>>>(n, nn, cid[cb], clo[cb], chi[cb], scal + 3, left, right, nlo, nhi, cnt, alive);
             CK(cudaMemcpyAsync(pos, alive, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-            k_scan_u32<<<1, 1024, 0, st>>>(pos, n, scal + 4);
+            scan_u32(pos, n, scal + 4, tile_sums, st, launches);
             k_ploc_compact<<<g, kPlocThreads, 0, st>>>(n, alive, pos, cid[cb], clo[cb], chi[cb], cid[1 - cb], clo[1 - cb], chi[1 - cb]);
             uint32_t n_next = 0;
             CK(cudaMemcpyAsync(&n_next, scal + 4, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
-            *launches += 4;
+            *launches += 3;
             if (n_next == 0 || n_next >= n) return cudaErrorUnknown;      // every round merges at least the globally closest pair
             n = n_next; cb = 1 - cb; ++rounds;
         }
@@ -719,7 +773,7 @@ cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, const uint32_t*
     CK(cudaGetLastError());
     out->nodes = nodes; out->tris = tri_sorted; out->tri_rec = tri_rec; out->sorted_ids = sorted;
     cudaFree(box_lo); cudaFree(box_hi); cudaFree(bounds); cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]);
-    cudaFree(hist); cudaFree(scal); cudaFree(left); cudaFree(right); cudaFree(nlo); cudaFree(nhi); cudaFree(cnt);
+    cudaFree(hist); cudaFree(scal); cudaFree(tile_sums); cudaFree(left); cudaFree(right); cudaFree(nlo); cudaFree(nhi); cudaFree(cnt);
     cudaFree(nn); cudaFree(alive); cudaFree(pos); cudaFree(items[0]); cudaFree(items[1]); cudaFree(lvl_counts);
     for (int k = 0; k < 2; ++k) { cudaFree(cid[k]); cudaFree(clo[k]); cudaFree(chi[k]); }
     return cudaSuccess;

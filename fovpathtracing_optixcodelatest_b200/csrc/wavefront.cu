@@ -285,117 +285,151 @@ __global__ void __launch_bounds__(128, FOVPT_TRACE_BLOCKS) k_trace(SceneDev S, P
 #ifndef FOVPT_SHADE_BLOCKS
 #define FOVPT_SHADE_BLOCKS 8
 #endif
+// closest-hit program of ONE path (reference __closesthit__radiance, deviceProgram.cu:619-732).  Reports whether the path
+// continues (push_next) and whether it emitted a shadow ray (push_shadow); the caller appends to the queues.
+template <bool FAST>
+__device__ __forceinline__ void shade_path(const FrameDev& F, const SceneDev& S, const PathState& ps, uint32_t pid, bool& push_next, bool& push_shadow)
+{
+    const float4 h4 = ps.hit[pid];
+    const uint32_t slot = (uint32_t)__float_as_int(h4.w);
+    if (slot == kNoHit) return;                               // __miss__radiance: DONE, adds nothing (:253-282)
+    const float4 ro4 = ps.ray_o[pid], rd4 = ps.ray_d[pid];
+    const float3 ro = f3(ro4.x, ro4.y, ro4.z), rd = f3(rd4.x, rd4.y, rd4.z);
+    const float4* tp = S.bvh.tris + 3 * (size_t)slot;
+    const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
+    const uint32_t gid = (uint32_t)__float_as_int(ta.w);
+    // geometric normal, flipped toward the viewer (:632-634); e1,e2 are exactly v1-v0, v2-v0
+    const float3 n0 = unit3<FAST>(cross3(f3(tb.x, tb.y, tb.z), f3(tc.x, tc.y, tc.z)));
+    const float3 wo = -rd;
+    const float3 N = n0 * copysignf(1.0f, dot3(wo, n0));
+    const float3 P = ro + h4.x * rd;                         // :636-638
+    const uint32_t mesh = (uint32_t)__float_as_int(tb.w);      // rides in the triangle record (bvh_build.cu k_tri_setup)
+    const MaterialBlob* M = S.materials + mesh;
+    const int mflags = __ldg(&M->flags);
+    float4 al = ps.alpha[pid];
+    uint32_t st = (uint32_t)__float_as_int(al.w);
+    const uint32_t depth = st & kDepthMask;
+    const bool secondary = (st & kFlagSecondary) != 0;
+    const bool catcher = (mflags & kMaterialShadowCatcher) != 0;
+    if (catcher && secondary) {                              // pass-through, --depth then ++depth (:646-651, :529)
+        ps.ray_o[pid] = make_float4(P.x, P.y, P.z, 0.f);
+        push_next = true;
+        return;
+    }
+    BsdfParams bp;
+    bp.color = f3(__ldg(&M->color[0]), __ldg(&M->color[1]), __ldg(&M->color[2]));
+    bp.metallic = __ldg(&M->metallic); bp.subsurface = __ldg(&M->subsurface); bp.specular = __ldg(&M->specular);
+    bp.roughness = __ldg(&M->roughness); bp.specularTint = __ldg(&M->specularTint); bp.clearcoat = __ldg(&M->clearcoat);
+    bp.clearcoatGloss = __ldg(&M->clearcoatGloss); bp.transmission = __ldg(&M->transmission);
+    float3 albedo = bp.color;
+    const int2 mt = __ldg(&S.mesh_tex[mesh]);
+    if (mt.x >= 0 && mt.y) {                                 // :655-665
+        const uint32_t* vi = S.tri_vidx + 3 * (size_t)gid;
+        const float2 t0 = __ldg(&S.texcoords[vi[0]]), t1 = __ldg(&S.texcoords[vi[1]]), t2 = __ldg(&S.texcoords[vi[2]]);
+        const float u = h4.y, v = h4.z, w0 = 1.f - u - v;
+        const int4 ti = __ldg(&S.tex_info[mt.x]);
+        albedo = texture_bilinear(S.texels + ti.x, ti.y, ti.z, w0 * t0.x + u * t1.x + v * t2.x, w0 * t0.y + u * t1.y + v * t2.y);
+    }
+    const float4 th4 = ps.thr[pid];
+    float3 T = f3(th4.x, th4.y, th4.z);
+    float ray_eta = th4.w;
+    float out_eta = 1.0f;                                    // :673-683
+    if (ray_eta == 1.0f) {
+        const float eta = __ldg(&M->eta);
+        out_eta = eta == 0.f ? 2.f / (1.f - sqrtf(0.08f * bp.specular)) - 1.f : eta;
+    }
+    const uint2 r2 = ps.rng[pid];
+    fx_rng rng; rng.s1 = r2.x; rng.s2 = r2.y;
+
+    // next-event estimation: one probe sample, balance heuristic (:303-344 / :347-387)
+    float3 wi, sky; float sky_pdf;
+    probe_sample<FAST>(F.probe, F.guide, rng, wi, sky, sky_pdf);
+    float3 pending = f3(0.f);
+    {
+        const float pdfb = bsdf_pdf<FAST>(bp, ray_eta, out_eta, N, wo, wi);
+        if (pdfb > 0.f) {
+            const float wgt = 0.5f * sky_pdf / (0.5f * pdfb + 0.5f * sky_pdf);
+            if (wgt > 0.f) {
+                const float3 f = bsdf_eval<FAST>(bp, albedo, ray_eta, out_eta, N, wo, wi);
+                pending = T * ((wgt * sky * f * fabsf(dot3(wi, N))) * Mth<FAST>::rcp(sky_pdf));
+            }
+        }
+    }
+    if (!catcher) { al.x = al.y = al.z = 1.0f; st |= kFlagAlphaOne; }   // :689
+    float3 E = f3(0.f);
+    if (!secondary) E = f3(__ldg(&M->emission[0]), __ldg(&M->emission[1]), __ldg(&M->emission[2]));   // :696-698
+
+    float3 tu, tv, L = f3(0.f);
+    tangent_frame<FAST>(N, tu, tv);
+    const float pdf = bsdf_sample<FAST>(bp, ray_eta, out_eta, tu, tv, N, wo, rng, L);
+    const bool done = !(pdf > 0.f);                          // :708-711
+    const bool commit = !done && (int)depth < F.max_depth;   // radiance of this segment counts (:515-527)
+    if (!done) {
+        const float3 f = bsdf_eval<FAST>(bp, albedo, ray_eta, out_eta, N, wo, L);
+        if (dot3(L, N) <= 0.f) ray_eta = out_eta;            // :717-721
+        T = T * ((f * fabsf(dot3(N, L))) * Mth<FAST>::rcp(pdf));   // :724
+    }
+    const bool has_pending = pending.x != 0.f || pending.y != 0.f || pending.z != 0.f;
+    const bool shadow = catcher ? has_pending : (commit && has_pending);
+    // !secondary implies depth == 0 (depth only advances together with the secondary flag), so the
+    // emission term lands in directLight exactly once; the NEE term is added by k_shadow.
+    if (commit && depth == 0) ps.direct[pid] = make_float4(E.x, E.y, E.z, 0.f);
+    if (shadow || commit) ps.ray_o[pid] = make_float4(P.x, P.y, P.z, 0.f);
+    if (shadow) {
+        ps.shw_d[pid] = make_float4(wi.x, wi.y, wi.z, 0.f);
+        const uint32_t mode = (catcher ? 1u : 0u) | (depth == 0 ? 2u : 0u);
+        ps.pend[pid] = make_float4(pending.x, pending.y, pending.z, __int_as_float((int)mode));
+        push_shadow = true;
+    }
+    bool cont = commit;
+    if (commit) {
+        st = (st & ~kDepthMask) | ((depth + 1) & kDepthMask) | kFlagSecondary;
+        // the (max_depth+1)-th segment only ever sets alpha; skip it when alpha is already 1
+        if (F.skip_wasted && (int)(depth + 1) >= F.max_depth && (st & kFlagAlphaOne) && !S.any_catcher) cont = false;
+    }
+    al.w = __int_as_float((int)st);
+    ps.alpha[pid] = al;
+    if (cont) {
+        ps.ray_d[pid] = make_float4(L.x, L.y, L.z, 0.f);
+        ps.thr[pid] = make_float4(T.x, T.y, T.z, ray_eta);
+        ps.rng[pid] = make_uint2(rng.s1, rng.s2);
+        push_next = true;
+    }
+}
+
+// One thread per queued path.  Queue appends are aggregated per CTA (ballot + shared-memory prefix, ONE atomicAdd per CTA
+// and queue per iteration): with 7 M shaded paths per frame, warp-level aggregation still put ~440 k same-address
+// atomics on the two queue counters, and waiting for them showed up as the top stall of the kernel.
 template <bool FAST>
 __global__ void __launch_bounds__(128, FOVPT_SHADE_BLOCKS) k_shade(FrameDev F, SceneDev S, PathState ps, Queues q, int shadow_slot)
 {
+    constexpr unsigned FULL = 0xffffffffu;
+    __shared__ uint32_t s_cnt[2][4];
+    __shared__ uint32_t s_base[2];
     const uint32_t n = q.counts[0];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t pid = q.cur[i];
-        const float4 h4 = ps.hit[pid];
-        const uint32_t slot = (uint32_t)__float_as_int(h4.w);
-        if (slot == kNoHit) continue;                            // __miss__radiance: DONE, adds nothing (:253-282)
-        const float4 ro4 = ps.ray_o[pid], rd4 = ps.ray_d[pid];
-        const float3 ro = f3(ro4.x, ro4.y, ro4.z), rd = f3(rd4.x, rd4.y, rd4.z);
-        const float4* tp = S.bvh.tris + 3 * (size_t)slot;
-        const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
-        const uint32_t gid = (uint32_t)__float_as_int(ta.w);
-        // geometric normal, flipped toward the viewer (:632-634); e1,e2 are exactly v1-v0, v2-v0
-        const float3 n0 = unit3<FAST>(cross3(f3(tb.x, tb.y, tb.z), f3(tc.x, tc.y, tc.z)));
-        const float3 wo = -rd;
-        const float3 N = n0 * copysignf(1.0f, dot3(wo, n0));
-        const float3 P = ro + h4.x * rd;                         // :636-638
-        const uint32_t mesh = (uint32_t)__float_as_int(tb.w);      // rides in the triangle record (bvh_build.cu k_tri_setup)
-        const MaterialBlob* M = S.materials + mesh;
-        const int mflags = __ldg(&M->flags);
-        float4 al = ps.alpha[pid];
-        uint32_t st = (uint32_t)__float_as_int(al.w);
-        const uint32_t depth = st & kDepthMask;
-        const bool secondary = (st & kFlagSecondary) != 0;
-        const bool catcher = (mflags & kMaterialShadowCatcher) != 0;
-        if (catcher && secondary) {                              // pass-through, --depth then ++depth (:646-651, :529)
-            ps.ray_o[pid] = make_float4(P.x, P.y, P.z, 0.f);
-            q.next[queue_push(&q.counts[1])] = pid;
-            continue;
+    const unsigned lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {      // CTA-uniform trip count
+        const uint32_t i = base + threadIdx.x;
+        bool push_next = false, push_shadow = false;
+        uint32_t pid = 0;
+        if (i < n) {
+            pid = q.cur[i];
+            shade_path<FAST>(F, S, ps, pid, push_next, push_shadow);
         }
-        BsdfParams bp;
-        bp.color = f3(__ldg(&M->color[0]), __ldg(&M->color[1]), __ldg(&M->color[2]));
-        bp.metallic = __ldg(&M->metallic); bp.subsurface = __ldg(&M->subsurface); bp.specular = __ldg(&M->specular);
-        bp.roughness = __ldg(&M->roughness); bp.specularTint = __ldg(&M->specularTint); bp.clearcoat = __ldg(&M->clearcoat);
-        bp.clearcoatGloss = __ldg(&M->clearcoatGloss); bp.transmission = __ldg(&M->transmission);
-        float3 albedo = bp.color;
-        const int2 mt = __ldg(&S.mesh_tex[mesh]);
-        if (mt.x >= 0 && mt.y) {                                 // :655-665
-            const uint32_t* vi = S.tri_vidx + 3 * (size_t)gid;
-            const float2 t0 = __ldg(&S.texcoords[vi[0]]), t1 = __ldg(&S.texcoords[vi[1]]), t2 = __ldg(&S.texcoords[vi[2]]);
-            const float u = h4.y, v = h4.z, w0 = 1.f - u - v;
-            const int4 ti = __ldg(&S.tex_info[mt.x]);
-            albedo = texture_bilinear(S.texels + ti.x, ti.y, ti.z, w0 * t0.x + u * t1.x + v * t2.x, w0 * t0.y + u * t1.y + v * t2.y);
+        const unsigned mn = __ballot_sync(FULL, push_next), ms = __ballot_sync(FULL, push_shadow);
+        if (lane == 0) { s_cnt[0][wib] = __popc(mn); s_cnt[1][wib] = __popc(ms); }
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            const uint32_t tot = s_cnt[threadIdx.x][0] + s_cnt[threadIdx.x][1] + s_cnt[threadIdx.x][2] + s_cnt[threadIdx.x][3];
+            s_base[threadIdx.x] = tot ? atomicAdd(&q.counts[threadIdx.x == 0 ? 1 : shadow_slot], tot) : 0u;
         }
-        const float4 th4 = ps.thr[pid];
-        float3 T = f3(th4.x, th4.y, th4.z);
-        float ray_eta = th4.w;
-        float out_eta = 1.0f;                                    // :673-683
-        if (ray_eta == 1.0f) {
-            const float eta = __ldg(&M->eta);
-            out_eta = eta == 0.f ? 2.f / (1.f - sqrtf(0.08f * bp.specular)) - 1.f : eta;
-        }
-        const uint2 r2 = ps.rng[pid];
-        fx_rng rng; rng.s1 = r2.x; rng.s2 = r2.y;
-
-        // next-event estimation: one probe sample, balance heuristic (:303-344 / :347-387)
-        float3 wi, sky; float sky_pdf;
-        probe_sample<FAST>(F.probe, F.guide, rng, wi, sky, sky_pdf);
-        float3 pending = f3(0.f);
-        {
-            const float pdfb = bsdf_pdf<FAST>(bp, ray_eta, out_eta, N, wo, wi);
-            if (pdfb > 0.f) {
-                const float wgt = 0.5f * sky_pdf / (0.5f * pdfb + 0.5f * sky_pdf);
-                if (wgt > 0.f) {
-                    const float3 f = bsdf_eval<FAST>(bp, albedo, ray_eta, out_eta, N, wo, wi);
-                    pending = T * ((wgt * sky * f * fabsf(dot3(wi, N))) * Mth<FAST>::rcp(sky_pdf));
-                }
-            }
-        }
-        if (!catcher) { al.x = al.y = al.z = 1.0f; st |= kFlagAlphaOne; }   // :689
-        float3 E = f3(0.f);
-        if (!secondary) E = f3(__ldg(&M->emission[0]), __ldg(&M->emission[1]), __ldg(&M->emission[2]));   // :696-698
-
-        float3 tu, tv, L = f3(0.f);
-        tangent_frame<FAST>(N, tu, tv);
-        const float pdf = bsdf_sample<FAST>(bp, ray_eta, out_eta, tu, tv, N, wo, rng, L);
-        const bool done = !(pdf > 0.f);                          // :708-711
-        const bool commit = !done && (int)depth < F.max_depth;   // radiance of this segment counts (:515-527)
-        if (!done) {
-            const float3 f = bsdf_eval<FAST>(bp, albedo, ray_eta, out_eta, N, wo, L);
-            if (dot3(L, N) <= 0.f) ray_eta = out_eta;            // :717-721
-            T = T * ((f * fabsf(dot3(N, L))) * Mth<FAST>::rcp(pdf));   // :724
-        }
-        const bool has_pending = pending.x != 0.f || pending.y != 0.f || pending.z != 0.f;
-        const bool shadow = catcher ? has_pending : (commit && has_pending);
-        // !secondary implies depth == 0 (depth only advances together with the secondary flag), so the
-        // emission term lands in directLight exactly once; the NEE term is added by k_shadow.
-        if (commit && depth == 0) ps.direct[pid] = make_float4(E.x, E.y, E.z, 0.f);
-        if (shadow || commit) ps.ray_o[pid] = make_float4(P.x, P.y, P.z, 0.f);
-        if (shadow) {
-            ps.shw_d[pid] = make_float4(wi.x, wi.y, wi.z, 0.f);
-            const uint32_t mode = (catcher ? 1u : 0u) | (depth == 0 ? 2u : 0u);
-            ps.pend[pid] = make_float4(pending.x, pending.y, pending.z, __int_as_float((int)mode));
-            q.shadow[queue_push(&q.counts[shadow_slot])] = pid;
-        }
-        bool cont = commit;
-        if (commit) {
-            st = (st & ~kDepthMask) | ((depth + 1) & kDepthMask) | kFlagSecondary;
-            // the (max_depth+1)-th segment only ever sets alpha; skip it when alpha is already 1
-            if (F.skip_wasted && (int)(depth + 1) >= F.max_depth && (st & kFlagAlphaOne) && !S.any_catcher) cont = false;
-        }
-        al.w = __int_as_float((int)st);
-        ps.alpha[pid] = al;
-        if (cont) {
-            ps.ray_d[pid] = make_float4(L.x, L.y, L.z, 0.f);
-            ps.thr[pid] = make_float4(T.x, T.y, T.z, ray_eta);
-            ps.rng[pid] = make_uint2(rng.s1, rng.s2);
-            q.next[queue_push(&q.counts[1])] = pid;
-        }
+        __syncthreads();
+        uint32_t on = s_base[0], os = s_base[1];
+        for (unsigned w = 0; w < wib; ++w) { on += s_cnt[0][w]; os += s_cnt[1][w]; }
+        const unsigned lt = (1u << lane) - 1u;
+        if (push_next) q.next[on + __popc(mn & lt)] = pid;
+        if (push_shadow) q.shadow[os + __popc(ms & lt)] = pid;
+        __syncthreads();                                   // s_cnt / s_base are rewritten by the next iteration
     }
 }
 

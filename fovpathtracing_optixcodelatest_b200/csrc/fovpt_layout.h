@@ -17,6 +17,9 @@ struct MaterialBlob {            // 104 B
     int   flags;
 };
 static_assert(sizeof(MaterialBlob) == 104, "Material must stay 104 bytes");
+static_assert(offsetof(MaterialBlob, color) == 12 && offsetof(MaterialBlob, metallic) == 40 && offsetof(MaterialBlob, specular) == 48 &&
+              offsetof(MaterialBlob, roughness) == 52 && offsetof(MaterialBlob, specularTint) == 56 && offsetof(MaterialBlob, clearcoat) == 72 &&
+              offsetof(MaterialBlob, clearcoatGloss) == 76, "k_shade reads the material as float2 words at these offsets");
 static_assert(offsetof(MaterialBlob, eta) == 36 && offsetof(MaterialBlob, transmission) == 80 &&
               offsetof(MaterialBlob, flags) == 100, "Material field offsets");
 constexpr int kMaterialShadowCatcher = 1;     // Material.h:9

@@ -290,10 +290,14 @@ __global__ void __launch_bounds__(128, FOVPT_TRACE_BLOCKS) k_trace(SceneDev S, P
 template <bool FAST>
 __device__ __forceinline__ void shade_path(const FrameDev& F, const SceneDev& S, const PathState& ps, uint32_t pid, bool& push_next, bool& push_shadow)
 {
+    // The kernel is bound by chains of dependent loads, not by arithmetic (removing the BSDF and probe code changes its time by
+    // 10 %): everything indexed by the path id is requested together with the hit record, the material in one batch.
     const float4 h4 = ps.hit[pid];
+    const float4 ro4 = ps.ray_o[pid], rd4 = ps.ray_d[pid], th4 = ps.thr[pid];
+    float4 al = ps.alpha[pid];
+    const uint2 r2 = ps.rng[pid];
     const uint32_t slot = (uint32_t)__float_as_int(h4.w);
     if (slot == kNoHit) return;                               // __miss__radiance: DONE, adds nothing (:253-282)
-    const float4 ro4 = ps.ray_o[pid], rd4 = ps.ray_d[pid];
     const float3 ro = f3(ro4.x, ro4.y, ro4.z), rd = f3(rd4.x, rd4.y, rd4.z);
     const float4* tp = S.bvh.tris + 3 * (size_t)slot;
     const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
@@ -305,8 +309,12 @@ __device__ __forceinline__ void shade_path(const FrameDev& F, const SceneDev& S,
     const float3 P = ro + h4.x * rd;                         // :636-638
     const uint32_t mesh = (uint32_t)__float_as_int(tb.w);      // rides in the triangle record (bvh_build.cu k_tri_setup)
     const MaterialBlob* M = S.materials + mesh;
-    const int mflags = __ldg(&M->flags);
-    float4 al = ps.alpha[pid];
+    // 104-byte Material as ten 8-byte loads issued back to back (the blob is 8-byte aligned, stride 104)
+    const float2* M2 = reinterpret_cast<const float2*>(M);
+    const float2 m0 = __ldg(M2 + 0), m1 = __ldg(M2 + 1), m2 = __ldg(M2 + 2), m4 = __ldg(M2 + 4), m5 = __ldg(M2 + 5), m6 = __ldg(M2 + 6),
+                 m7 = __ldg(M2 + 7), m9 = __ldg(M2 + 9), m10 = __ldg(M2 + 10), m12 = __ldg(M2 + 12);
+    const int2 mt = __ldg(&S.mesh_tex[mesh]);
+    const int mflags = __float_as_int(m12.y);                // flags @100
     uint32_t st = (uint32_t)__float_as_int(al.w);
     const uint32_t depth = st & kDepthMask;
     const bool secondary = (st & kFlagSecondary) != 0;
@@ -317,12 +325,11 @@ __device__ __forceinline__ void shade_path(const FrameDev& F, const SceneDev& S,
         return;
     }
     BsdfParams bp;
-    bp.color = f3(__ldg(&M->color[0]), __ldg(&M->color[1]), __ldg(&M->color[2]));
-    bp.metallic = __ldg(&M->metallic); bp.subsurface = __ldg(&M->subsurface); bp.specular = __ldg(&M->specular);
-    bp.roughness = __ldg(&M->roughness); bp.specularTint = __ldg(&M->specularTint); bp.clearcoat = __ldg(&M->clearcoat);
-    bp.clearcoatGloss = __ldg(&M->clearcoatGloss); bp.transmission = __ldg(&M->transmission);
+    bp.color = f3(m1.y, m2.x, m2.y);                          // color @12,16,20
+    bp.metallic = m5.x; bp.subsurface = m5.y; bp.specular = m6.x;      // @40,44,48
+    bp.roughness = m6.y; bp.specularTint = m7.x; bp.clearcoat = m9.x;  // @52,56,72
+    bp.clearcoatGloss = m9.y; bp.transmission = m10.x;        // @76,80
     float3 albedo = bp.color;
-    const int2 mt = __ldg(&S.mesh_tex[mesh]);
     if (mt.x >= 0 && mt.y) {                                 // :655-665
         const uint32_t* vi = S.tri_vidx + 3 * (size_t)gid;
         const float2 t0 = __ldg(&S.texcoords[vi[0]]), t1 = __ldg(&S.texcoords[vi[1]]), t2 = __ldg(&S.texcoords[vi[2]]);
@@ -330,15 +337,13 @@ __device__ __forceinline__ void shade_path(const FrameDev& F, const SceneDev& S,
         const int4 ti = __ldg(&S.tex_info[mt.x]);
         albedo = texture_bilinear(S.texels + ti.x, ti.y, ti.z, w0 * t0.x + u * t1.x + v * t2.x, w0 * t0.y + u * t1.y + v * t2.y);
     }
-    const float4 th4 = ps.thr[pid];
     float3 T = f3(th4.x, th4.y, th4.z);
     float ray_eta = th4.w;
     float out_eta = 1.0f;                                    // :673-683
     if (ray_eta == 1.0f) {
-        const float eta = __ldg(&M->eta);
+        const float eta = m4.y;                               // eta @36
         out_eta = eta == 0.f ? 2.f / (1.f - sqrtf(0.08f * bp.specular)) - 1.f : eta;
     }
-    const uint2 r2 = ps.rng[pid];
     fx_rng rng; rng.s1 = r2.x; rng.s2 = r2.y;
 
     // next-event estimation: one probe sample, balance heuristic (:303-344 / :347-387)
@@ -357,7 +362,7 @@ __device__ __forceinline__ void shade_path(const FrameDev& F, const SceneDev& S,
     }
     if (!catcher) { al.x = al.y = al.z = 1.0f; st |= kFlagAlphaOne; }   // :689
     float3 E = f3(0.f);
-    if (!secondary) E = f3(__ldg(&M->emission[0]), __ldg(&M->emission[1]), __ldg(&M->emission[2]));   // :696-698
+    if (!secondary) E = f3(m0.x, m0.y, m1.x);                // emission @0,4,8 (:696-698)
 
     float3 tu, tv, L = f3(0.f);
     tangent_frame<FAST>(N, tu, tv);

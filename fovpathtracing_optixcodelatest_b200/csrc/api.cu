@@ -115,20 +115,23 @@ void free_scene(fovpt_ctx* c)
 
 void free_paths(fovpt_ctx* c)
 {
-    cudaFree(c->ps.ray_o); cudaFree(c->ps.ray_d); cudaFree(c->ps.hit); cudaFree(c->ps.thr); cudaFree(c->ps.rng);
-    cudaFree(c->ps.direct); cudaFree(c->ps.indirect); cudaFree(c->ps.alpha); cudaFree(c->ps.shw_d); cudaFree(c->ps.pend);
-    cudaFree(c->q.cur); cudaFree(c->q.next); cudaFree(c->q.shadow);
-    c->ps = PathState{}; c->q.cur = c->q.next = c->q.shadow = nullptr; c->path_cap = 0;
+    cudaFree(c->ps.direct); cudaFree(c->ps.indirect); cudaFree(c->ps.alpha);
+    for (RayBuf* b : {&c->q.cur, &c->q.next}) { cudaFree(b->o); cudaFree(b->d); cudaFree(b->thr); cudaFree(b->rng); cudaFree(b->meta); *b = RayBuf{}; }
+    cudaFree(c->q.shadow.o); cudaFree(c->q.shadow.d); cudaFree(c->q.shadow.pend); cudaFree(c->q.shadow.pid); c->q.shadow = ShadowBuf{};
+    cudaFree(c->q.hit); c->q.hit = nullptr;
+    c->ps = PathState{}; c->path_cap = 0;
 }
 
 int ensure_paths(fovpt_ctx* c, size_t n)
 {
     if (n <= c->path_cap) return 0;
     free_paths(c);
-    CU(dmalloc(&c->ps.ray_o, n)); CU(dmalloc(&c->ps.ray_d, n)); CU(dmalloc(&c->ps.hit, n)); CU(dmalloc(&c->ps.thr, n));
-    CU(dmalloc(&c->ps.rng, n)); CU(dmalloc(&c->ps.direct, n)); CU(dmalloc(&c->ps.indirect, n)); CU(dmalloc(&c->ps.alpha, n));
-    CU(dmalloc(&c->ps.shw_d, n)); CU(dmalloc(&c->ps.pend, n));
-    CU(dmalloc(&c->q.cur, n)); CU(dmalloc(&c->q.next, n)); CU(dmalloc(&c->q.shadow, n));
+    CU(dmalloc(&c->ps.direct, n)); CU(dmalloc(&c->ps.indirect, n)); CU(dmalloc(&c->ps.alpha, n));
+    for (RayBuf* b : {&c->q.cur, &c->q.next}) {
+        CU(dmalloc(&b->o, n)); CU(dmalloc(&b->d, n)); CU(dmalloc(&b->thr, n)); CU(dmalloc(&b->rng, n)); CU(dmalloc(&b->meta, n));
+    }
+    CU(dmalloc(&c->q.shadow.o, n)); CU(dmalloc(&c->q.shadow.d, n)); CU(dmalloc(&c->q.shadow.pend, n)); CU(dmalloc(&c->q.shadow.pid, n));
+    CU(dmalloc(&c->q.hit, n));
     c->path_cap = n;
     return 0;
 }

@@ -120,18 +120,19 @@ __global__ void k_raygen(FrameDev F, int pass, unsigned row0, unsigned row1, uns
         const float jy = fx_rnd(&seed);
         const float3 dir = camera_dir(F, px, py, jx, jy);
         const uint32_t pid = chunk_pid_base + (uint32_t)i;
-        ps.ray_o[pid] = make_float4(F.eye[0], F.eye[1], F.eye[2], 0.f);
-        ps.ray_d[pid] = make_float4(dir.x, dir.y, dir.z, 0.f);
-        ps.thr[pid] = make_float4(1.f, 1.f, 1.f, 1.f);                                   // throughput 1, rayEta 1 (:467-468)
-        ps.rng[pid] = make_uint2(rng.s1, rng.s2);
+        const uint32_t slot = queue_push(&q.counts[0]);
+        q.cur.o[slot] = make_float4(F.eye[0], F.eye[1], F.eye[2], 0.f);
+        q.cur.d[slot] = make_float4(dir.x, dir.y, dir.z, 0.f);
+        q.cur.thr[slot] = make_float4(1.f, 1.f, 1.f, 1.f);                               // throughput 1, rayEta 1 (:467-468)
+        q.cur.rng[slot] = make_uint2(rng.s1, rng.s2);
+        q.cur.meta[slot] = make_uint2(pid, 0u);
         ps.direct[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
         ps.indirect[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
-        ps.alpha[pid] = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
+        ps.alpha[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (k == P.spp - 1) {                                                           // backplate of the LAST sample (:495)
             const float4 bp = probe_eval(F.probe, probe_dir_to_uv(dir));
             li_backplate[P.li_base + li] = bp;
         }
-        q.cur[queue_push(&q.counts[0])] = pid;
         ++started;
     }
     // block-level count of started samples
@@ -140,9 +141,10 @@ __global__ void k_raygen(FrameDev F, int pass, unsigned row0, unsigned row1, uns
 }
 
 // the tail of SampleLights / SampleShadow once the occlusion bit is known (deviceProgram.cu:323-341, :367-384)
-__device__ __forceinline__ void shadow_resolve(const PathState& ps, uint32_t pid, bool occluded)
+__device__ __forceinline__ void shadow_resolve(const PathState& ps, const ShadowBuf& sb, uint32_t k, bool occluded)
 {
-    const float4 pe = ps.pend[pid];
+    const float4 pe = sb.pend[k];
+    const uint32_t pid = sb.pid[k];
     const uint32_t mode = (uint32_t)__float_as_int(pe.w);
     if ((mode & 1u) == 0u) {
         if (!occluded) {
@@ -193,8 +195,8 @@ __global__ void __launch_bounds__(128, FOVPT_TRACE_BLOCKS) k_trace(SceneDev S, P
     if (n == 0) return;
     if (S.bvh.n_tris == 0) {                                   // empty scene: every ray misses
         for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-            if (i < n_closest) ps.hit[q.cur[i]] = make_float4(0.f, 0.f, 0.f, __int_as_float((int)kNoHit));
-            else shadow_resolve(ps, q.shadow[i - n_closest], false);
+            if (i < n_closest) q.hit[i] = make_float4(0.f, 0.f, 0.f, __int_as_float((int)kNoHit));
+            else shadow_resolve(ps, q.shadow, i - n_closest, false);
         }
         return;
     }
@@ -231,8 +233,8 @@ __global__ void __launch_bounds__(128, FOVPT_TRACE_BLOCKS) k_trace(SceneDev S, P
                 const uint32_t mine = base + __popc(idle & ((1u << lane) - 1u));
                 if (!have && ((idle >> lane) & 1u) && mine < n) {
                     const bool is_any = mine >= n_closest;
-                    pid = is_any ? __ldg(&q.shadow[mine - n_closest]) : __ldg(&q.cur[mine]);
-                    const float4 o = ps.ray_o[pid], d = is_any ? ps.shw_d[pid] : ps.ray_d[pid];
+                    pid = is_any ? mine - n_closest : mine;            // slot in the shadow / radiance buffer
+                    const float4 o = is_any ? q.shadow.o[pid] : q.cur.o[pid], d = is_any ? q.shadow.d[pid] : q.cur.d[pid];
                     T.begin(make_float3(o.x, o.y, o.z), make_float3(d.x, d.y, d.z), tmin, tmax);
                     T.any = is_any;
                     have = true;
@@ -262,9 +264,9 @@ __global__ void __launch_bounds__(128, FOVPT_TRACE_BLOCKS) k_trace(SceneDev S, P
                 if (leaf) T.leaf_step(S.bvh, stack, nmax);
             }
             if (have && T.done()) {
-                if (!T.any) ps.hit[pid] = T.found() ? make_float4(T.best_t, T.best_u, T.best_v, __int_as_float((int)T.best_k))
-                                                   : make_float4(0.f, 0.f, 0.f, __int_as_float((int)kNoHit));
-                else shadow_resolve(ps, pid, T.found());
+                if (!T.any) q.hit[pid] = T.found() ? make_float4(T.best_t, T.best_u, T.best_v, __int_as_float((int)T.best_k))
+                                                  : make_float4(0.f, 0.f, 0.f, __int_as_float((int)kNoHit));
+                else shadow_resolve(ps, q.shadow, pid, T.found());
                 have = false;
             }
         }
@@ -283,19 +285,27 @@ __global__ void __launch_bounds__(128, FOVPT_TRACE_BLOCKS) k_trace(SceneDev S, P
 
 // ------------------------------------------------------------------ k_shade  (closest-hit / miss program)
 #ifndef FOVPT_SHADE_BLOCKS
-#define FOVPT_SHADE_BLOCKS 8
+#define FOVPT_SHADE_BLOCKS 7
 #endif
-// closest-hit program of ONE path (reference __closesthit__radiance, deviceProgram.cu:619-732).  Reports whether the path
-// continues (push_next) and whether it emitted a shadow ray (push_shadow); the caller appends to the queues.
+// What one shaded path hands back: the continuation ray (if push_next) and the NEE shadow ray (if push_shadow); the
+// caller appends them to the dense buffers of the next bounce once it knows their slots.
+struct ShadeOut {
+    bool   push_next = false, push_shadow = false;
+    float4 o, d, thr;            // continuation: origin (also the shadow ray's origin), direction, throughput + rayEta
+    uint2  rng, meta;
+    float4 s_d, s_pend;          // shadow ray: direction, pending NEE value + mode bits
+};
+
+// closest-hit program of ONE path (reference __closesthit__radiance, deviceProgram.cu:619-732); `i` = its slot in q.cur
 template <bool FAST>
-__device__ __forceinline__ void shade_path(const FrameDev& F, const SceneDev& S, const PathState& ps, uint32_t pid, bool& push_next, bool& push_shadow)
+__device__ __forceinline__ void shade_path(const FrameDev& F, const SceneDev& S, const PathState& ps, const Queues& q, uint32_t i, ShadeOut& out)
 {
     // The kernel is bound by chains of dependent loads, not by arithmetic (removing the BSDF and probe code changes its time by
     // 10 %): everything indexed by the path id is requested together with the hit record, the material in one batch.
-    const float4 h4 = ps.hit[pid];
-    const float4 ro4 = ps.ray_o[pid], rd4 = ps.ray_d[pid], th4 = ps.thr[pid];
-    float4 al = ps.alpha[pid];
-    const uint2 r2 = ps.rng[pid];
+    const float4 h4 = q.hit[i];
+    const float4 ro4 = q.cur.o[i], rd4 = q.cur.d[i], th4 = q.cur.thr[i];
+    const uint2 r2 = q.cur.rng[i], meta = q.cur.meta[i];
+    const uint32_t pid = meta.x;
     const uint32_t slot = (uint32_t)__float_as_int(h4.w);
     if (slot == kNoHit) return;                               // __miss__radiance: DONE, adds nothing (:253-282)
     const float3 ro = f3(ro4.x, ro4.y, ro4.z), rd = f3(rd4.x, rd4.y, rd4.z);
@@ -315,13 +325,13 @@ __device__ __forceinline__ void shade_path(const FrameDev& F, const SceneDev& S,
                  m7 = __ldg(M2 + 7), m9 = __ldg(M2 + 9), m10 = __ldg(M2 + 10), m12 = __ldg(M2 + 12);
     const int2 mt = __ldg(&S.mesh_tex[mesh]);
     const int mflags = __float_as_int(m12.y);                // flags @100
-    uint32_t st = (uint32_t)__float_as_int(al.w);
+    uint32_t st = meta.y;
     const uint32_t depth = st & kDepthMask;
     const bool secondary = (st & kFlagSecondary) != 0;
     const bool catcher = (mflags & kMaterialShadowCatcher) != 0;
     if (catcher && secondary) {                              // pass-through, --depth then ++depth (:646-651, :529)
-        ps.ray_o[pid] = make_float4(P.x, P.y, P.z, 0.f);
-        push_next = true;
+        out.o = make_float4(P.x, P.y, P.z, 0.f); out.d = rd4; out.thr = th4; out.rng = r2; out.meta = meta;
+        out.push_next = true;
         return;
     }
     BsdfParams bp;
@@ -360,7 +370,7 @@ __device__ __forceinline__ void shade_path(const FrameDev& F, const SceneDev& S,
             }
         }
     }
-    if (!catcher) { al.x = al.y = al.z = 1.0f; st |= kFlagAlphaOne; }   // :689
+    if (!catcher && !(st & kFlagAlphaOne)) { ps.alpha[pid] = make_float4(1.f, 1.f, 1.f, 0.f); st |= kFlagAlphaOne; }   // prd.alpha = 1 (:689), written once per path
     float3 E = f3(0.f);
     if (!secondary) E = f3(m0.x, m0.y, m1.x);                // emission @0,4,8 (:696-698)
 
@@ -379,12 +389,12 @@ __device__ __forceinline__ void shade_path(const FrameDev& F, const SceneDev& S,
     // !secondary implies depth == 0 (depth only advances together with the secondary flag), so the
     // emission term lands in directLight exactly once; the NEE term is added by k_shadow.
     if (commit && depth == 0) ps.direct[pid] = make_float4(E.x, E.y, E.z, 0.f);
-    if (shadow || commit) ps.ray_o[pid] = make_float4(P.x, P.y, P.z, 0.f);
+    out.o = make_float4(P.x, P.y, P.z, 0.f);
     if (shadow) {
-        ps.shw_d[pid] = make_float4(wi.x, wi.y, wi.z, 0.f);
+        out.s_d = make_float4(wi.x, wi.y, wi.z, 0.f);
         const uint32_t mode = (catcher ? 1u : 0u) | (depth == 0 ? 2u : 0u);
-        ps.pend[pid] = make_float4(pending.x, pending.y, pending.z, __int_as_float((int)mode));
-        push_shadow = true;
+        out.s_pend = make_float4(pending.x, pending.y, pending.z, __int_as_float((int)mode));
+        out.push_shadow = true;
     }
     bool cont = commit;
     if (commit) {
@@ -392,13 +402,12 @@ __device__ __forceinline__ void shade_path(const FrameDev& F, const SceneDev& S,
         // the (max_depth+1)-th segment only ever sets alpha; skip it when alpha is already 1
         if (F.skip_wasted && (int)(depth + 1) >= F.max_depth && (st & kFlagAlphaOne) && !S.any_catcher) cont = false;
     }
-    al.w = __int_as_float((int)st);
-    ps.alpha[pid] = al;
+    out.meta = make_uint2(pid, st);                          // the shadow ray needs the pid even when the path ends here
     if (cont) {
-        ps.ray_d[pid] = make_float4(L.x, L.y, L.z, 0.f);
-        ps.thr[pid] = make_float4(T.x, T.y, T.z, ray_eta);
-        ps.rng[pid] = make_uint2(rng.s1, rng.s2);
-        push_next = true;
+        out.d = make_float4(L.x, L.y, L.z, 0.f);
+        out.thr = make_float4(T.x, T.y, T.z, ray_eta);
+        out.rng = make_uint2(rng.s1, rng.s2);
+        out.push_next = true;
     }
 }
 
@@ -415,13 +424,9 @@ __global__ void __launch_bounds__(128, FOVPT_SHADE_BLOCKS) k_shade(FrameDev F, S
     const unsigned lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {      // CTA-uniform trip count
         const uint32_t i = base + threadIdx.x;
-        bool push_next = false, push_shadow = false;
-        uint32_t pid = 0;
-        if (i < n) {
-            pid = q.cur[i];
-            shade_path<FAST>(F, S, ps, pid, push_next, push_shadow);
-        }
-        const unsigned mn = __ballot_sync(FULL, push_next), ms = __ballot_sync(FULL, push_shadow);
+        ShadeOut out;
+        if (i < n) shade_path<FAST>(F, S, ps, q, i, out);
+        const unsigned mn = __ballot_sync(FULL, out.push_next), ms = __ballot_sync(FULL, out.push_shadow);
         if (lane == 0) { s_cnt[0][wib] = __popc(mn); s_cnt[1][wib] = __popc(ms); }
         __syncthreads();
         if (threadIdx.x < 2) {
@@ -432,8 +437,14 @@ __global__ void __launch_bounds__(128, FOVPT_SHADE_BLOCKS) k_shade(FrameDev F, S
         uint32_t on = s_base[0], os = s_base[1];
         for (unsigned w = 0; w < wib; ++w) { on += s_cnt[0][w]; os += s_cnt[1][w]; }
         const unsigned lt = (1u << lane) - 1u;
-        if (push_next) q.next[on + __popc(mn & lt)] = pid;
-        if (push_shadow) q.shadow[os + __popc(ms & lt)] = pid;
+        if (out.push_next) {
+            const uint32_t j = on + __popc(mn & lt);
+            q.next.o[j] = out.o; q.next.d[j] = out.d; q.next.thr[j] = out.thr; q.next.rng[j] = out.rng; q.next.meta[j] = out.meta;
+        }
+        if (out.push_shadow) {
+            const uint32_t k = os + __popc(ms & lt);
+            q.shadow.o[k] = out.o; q.shadow.d[k] = out.s_d; q.shadow.pend[k] = out.s_pend; q.shadow.pid[k] = out.meta.x;
+        }
         __syncthreads();                                   // s_cnt / s_base are rewritten by the next iteration
     }
 }

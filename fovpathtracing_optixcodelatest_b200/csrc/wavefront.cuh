@@ -1,7 +1,7 @@
 // wavefront.cuh -- device-side data model of the wavefront path tracer (kernels: wavefront.cu).
 //
 // One camera path ("sample", one iteration of reference deviceProgram.cu:448-539) owns slot `pid`
-// in a set of SoA arrays; queues of pids connect the stages:
+// of the per-path accumulators; its ray state travels through dense per-bounce buffers that connect the stages:
 //
 //   k_owner_map -> k_raygen -> [ k_trace -> k_shade ] x (max_depth+1) -> k_trace -> k_resolve_li -> k_resolve_px
 // (k_trace(i) extends the radiance rays of iteration i and resolves the shadow rays emitted by k_shade(i-1))
@@ -28,17 +28,27 @@ constexpr uint32_t kFlagSecondary = 1u << 8;   // RAY_STATE_FLAGS_SECONDARY_RAY
 constexpr uint32_t kFlagAlphaOne = 1u << 9;    // prd.alpha was set to 1 by a non-catcher hit
 constexpr uint32_t kDepthMask = 0xffu;
 
-struct PathState {              // SoA, capacity = paths of the largest batch
-    float4* ray_o;              // origin.xyz
-    float4* ray_d;              // direction.xyz
-    float4* hit;                // t, u, v, bits(sorted triangle slot | kNoHit)
-    float4* thr;                // pathThroughput.xyz, rayEta
-    uint2*  rng;                // Random state (maths.h:170-227)
+// Per-path accumulators, indexed by path slot pid (what k_resolve_li sums per launch index).
+struct PathState {
     float4* direct;             // directLight.xyz
     float4* indirect;           // indirectLight.xyz
-    float4* alpha;              // alpha.xyz, bits(depth | flags)
-    float4* shw_d;              // NEE direction.xyz
-    float4* pend;               // throughput * NEE value, bits(mode): bit0 catcher (add to alpha when occluded), bit1 primary
+    float4* alpha;              // alpha.xyz
+};
+
+// The wavefront itself is DENSE: the state of the rays of one bounce lives in queue order, so every kernel reads and
+// writes it fully coalesced and without a pid indirection; k_shade appends the continuing paths to the `next` buffer.
+struct RayBuf {                 // by queue slot
+    float4* o;                  // origin.xyz
+    float4* d;                  // direction.xyz
+    float4* thr;                // pathThroughput.xyz, rayEta
+    uint2*  rng;                // Random state (maths.h:170-227)
+    uint2*  meta;               // (pid, depth | flags)
+};
+struct ShadowBuf {              // by shadow-queue slot: the NEE rays emitted by one shading pass
+    float4*   o;                // origin.xyz
+    float4*   d;                // direction.xyz
+    float4*   pend;             // throughput * NEE value, bits(mode): bit0 catcher (add to alpha when occluded), bit1 primary
+    uint32_t* pid;
 };
 
 struct SceneDev {
@@ -81,9 +91,9 @@ struct FrameDev {
 };
 
 struct Queues {
-    uint32_t* cur;
-    uint32_t* next;
-    uint32_t* shadow;
+    RayBuf    cur, next;
+    ShadowBuf shadow;
+    float4*   hit;              // by slot of `cur`: t, u, v, bits(sorted triangle slot | kNoHit)
     uint32_t* counts;   // [0] cur [1] next [2],[5] shadow (alternating per iteration) [3] fetch cursor of k_trace  (8 words)
 };
 

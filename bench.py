@@ -214,7 +214,14 @@ def native_arm(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     host_frame = torch.empty((h, w), dtype=torch.int32).pin_memory()
 
+    if wl.view_at is not None and world > 1:
+        raise RuntimeError(f"{wl.name} (moving gaze) is measured at --gpus 1 in this round: the tile partition would have to follow the gaze")
+    step_no = [0]
+
     def step():
+        if wl.view_at is not None:                     # stereo / moving gaze: camera and gaze point change every step (host-side only)
+            cam_k, gaze_k = wl.view_at(step_no[0]); step_no[0] += 1
+            r.setCamera(cam_k); lp.frame.c_x, lp.frame.c_y = gaze_k
         r.ctx.render_frame(lp)
         if world > 1:
             dist.reduce(frame_t, dst=0, op=dist.ReduceOp.SUM)
@@ -242,7 +249,7 @@ def native_arm(args):
         step()
     barrier()
     r.ctx.reset_stats()
-    lp.frame.subframe_index = 0
+    lp.frame.subframe_index = 0; step_no[0] = 0
     accum_t.zero_(); frame_t.zero_()
 
     # ---- device-timed region: K steps, each bracketed by its own event pair, L2 flushed in between
@@ -287,7 +294,11 @@ def native_arm(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     host_np = host_frame.numpy().view(np.uint32)
     e0.record()
+    step_no[0] = 0
     for k in range(args.steps):
+        if wl.view_at is not None:
+            cam_k, gaze_k = wl.view_at(step_no[0]); step_no[0] += 1
+            r.setCamera(cam_k); lp.frame.c_x, lp.frame.c_y = gaze_k
         if world == 1:
             r.render()                                 # SampleRenderer::render(): LaunchParams host -> device, 3 passes, sync
         else:
@@ -308,7 +319,8 @@ def native_arm(args):
     if rank == 0:
         hbm, peak_src = load_peaks()
         traced_samples = samples                               # sum over ranks, incl. tile-edge duplicates
-        samples = frame_samples * args.steps                   # unique samples of the frames rendered
+        if wl.view_at is None:
+            samples = frame_samples * args.steps               # unique samples of the frames rendered
         per_step_samples = samples / args.steps
         value = samples / (total_ms * 1e-3) / 1e6
         line = {
@@ -360,7 +372,7 @@ def main():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c5"])
+    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--tile", type=int, default=32, help="screen tile edge of the multi-GPU partition")
     ap.add_argument("--emulate-world", type=int, default=1, help="profiling aid: render only rank 0's tiles of an N-rank partition (single process; value is NOT a benchmark number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

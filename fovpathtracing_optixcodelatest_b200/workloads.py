@@ -32,6 +32,7 @@ class Workload:
     accumulate: int = 0
     seed_all_passes_with_subframe: int = 0
     tmin: float = 0.01
+    view_at: object = None                        # optional: step index -> (camera, gaze) for moving-gaze / stereo workloads
     _scene: object = field(default=None, repr=False)
     _probe: object = field(default=None, repr=False)
 
@@ -102,7 +103,17 @@ def c5(n_tris=10_000_000):
                     frames=32, accumulate=1, seed_all_passes_with_subframe=1)
 
 
-BY_NAME = {"c1": c1, "c2": c2, "c3": c3, "c5": c5}
+def c4():
+    """BASELINE configs[3] as a bench workload: one step = one eye frame of the stereo pair; step k renders eye k % 2
+    of stereo frame k // 2, whose gaze point follows the circular path of c4_eye (per-frame gaze update)."""
+    wl = c4_eye(0, 0)
+    wl.name = "C4"
+    wl.description = "Stereo VR pair 2x2160x2160 foveated, moving gaze (one step = one eye frame, gaze updated every stereo frame)"
+    wl.view_at = lambda k: (c4_eye(k % 2, k // 2).camera, c4_eye(k % 2, k // 2).gaze)
+    return wl
+
+
+BY_NAME = {"c1": c1, "c2": c2, "c3": c3, "c4": c4, "c5": c5}
 
 
 def scaled(wl: Workload, width: int, height: int, radius_scale: float = None):

@@ -134,6 +134,22 @@ def test_random_rays_closest_and_any(gpu, port, scene_name):
     ctx.close(); o.close()
 
 
+def test_large_mesh_random_rays(gpu, port):
+    """the C5 scene class at 1 M triangles (the on-device builder's tiled scans, deep trees, multi-level collapse):
+    closest / any-hit of random rays bit-exact against the oracle's own SAH tree"""
+    sc = scenes.displaced_grid(1_000_000)
+    o = port.Oracle("port"); o.add_scene(sc); o.commit()
+    ctx = gpu.native.Context(0); ctx.upload_scene(sc)
+    assert ctx.stats()["bvh_tris"] == sc.n_tris
+    rays = random_rays(sc, 40000, 9)
+    rays[:, 1] = np.abs(rays[:, 1]) + 50.0; rays[:20000, 5] = -np.abs(rays[:20000, 5])       # start above the terrain, half of them looking down
+    ot, otuv = o.trace(rays, 0); gt, gtuv = ctx.trace(rays, 0)
+    assert (ot == gt).all() and (bits(otuv) == bits(gtuv)).all() and (ot >= 0).mean() > 0.2
+    oa, _ = o.trace(rays, 1); ga, _ = ctx.trace(rays, 1)
+    assert (oa == ga).all()
+    ctx.close(); o.close()
+
+
 def test_degenerate_rays_and_geometry(gpu, port):
     """axis-parallel rays (zero direction components), rays starting on a surface, zero-area and
     duplicated triangles (ties -> lowest global id)"""

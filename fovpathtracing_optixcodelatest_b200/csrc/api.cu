@@ -406,6 +406,7 @@ int fovpt_set_config(fovpt_ctx* c, const fovpt_config* k)
     if (k->foveated && (k->inner_radius < 0 || k->outer_radius < k->inner_radius)) return fail(c, "bad radii");
     if (k->spp_periphery <= 0 || k->spp_mid <= 0 || k->spp_fovea <= 0 || k->spp_uniform <= 0) return fail(c, "spp must be positive");
     if (k->filter < 0 || k->filter > 1) return fail(c, "filter must be 0 (box) or 1 (bilinear)");
+    if (!(k->tmin >= 0.f) || !(k->tmax > k->tmin)) return fail(c, "need 0 <= tmin < tmax");
     c->cfg = *k;
     return 0;
 }

@@ -180,14 +180,94 @@ __device__ __forceinline__ void shadow_resolve(const PathState& ps, const Shadow
 #endif
 constexpr int kFetchMin = FOVPT_FETCH_MIN;          // refill as soon as this many lanes are idle
 
+// The persistent loop of k_trace for one warp.  A lane is idle exactly when its traversal is done(); `keep` is the number
+// of busy lanes at or below which the warp stops stepping and refills first (0 once the queues are drained: then it runs
+// until every lane is done).
+template <bool THIN>
+__device__ __forceinline__ void trace_loop(const SceneDev& S, const PathState& ps, const Queues& q, int shadow_slot, float tmin, float tmax,
+                                           const RayStack& stack, uint32_t n_closest, uint32_t n, uint32_t cap_in, DevStats* stats)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    const uint32_t cap = THIN ? cap_in : 32u;
+    const unsigned lanes = THIN ? ((1u << cap) - 1u) : FULL;               // lanes that take rays in this launch
+    const int fetch_min = THIN ? min(kFetchMin, (int)((cap + 3u) / 4u)) : kFetchMin;
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t* fetch = q.counts + 3;
+    FOVPT_TRAV(kMixed) T;
+    uint32_t pid = 0;
+    int keep = (int)cap - fetch_min;
+    bool exhausted = false;
+    T.reset();
+#ifdef FOVPT_TRACE_STATS
+    unsigned long long st_node_exec = 0, st_node_lanes = 0, st_leaf_exec = 0, st_leaf_lanes = 0, st_leaf_tris = 0, st_leaf_nmax = 0, st_fetch = 0;
+#endif
+    for (;;) {
+        const unsigned idle = __ballot_sync(FULL, T.done()) & lanes;
+        if (idle == lanes || (!exhausted && __popc(idle) >= fetch_min)) {
+            if (!exhausted) {
+                const int want = __popc(idle);
+                uint32_t base = 0;
+                if (lane == 0) base = atomicAdd(fetch, (uint32_t)want);
+                base = __shfl_sync(FULL, base, 0);
+                const uint32_t mine = base + __popc(idle & ((1u << lane) - 1u));
+                if (((idle >> lane) & 1u) && mine < n) {
+                    const bool is_any = mine >= n_closest;
+                    pid = is_any ? mine - n_closest : mine;            // slot in the shadow / radiance buffer
+                    const float4 o = is_any ? q.shadow.o[pid] : q.cur.o[pid], d = is_any ? q.shadow.d[pid] : q.cur.d[pid];
+                    T.begin(make_float3(o.x, o.y, o.z), make_float3(d.x, d.y, d.z), tmin, tmax);
+                    T.any = is_any;
+                }
+                if (base + (uint32_t)want >= n) { exhausted = true; keep = 0; }
+            }
+            if (__ballot_sync(FULL, !T.done()) == 0u) break;
+        }
+        for (;;) {
+            // each iteration runs the step kind most lanes are waiting for; the others keep their state
+            const bool node = T.at_node(), leaf = T.at_leaf();
+            const unsigned mn = __ballot_sync(FULL, node), ml = __ballot_sync(FULL, leaf);
+            if (__popc(mn | ml) <= keep) break;                          // enough idle lanes (refill first), or warp drained
+            bool stepped;
+            if (FOVPT_LEAF_NUM * __popc(ml) <= FOVPT_LEAF_DEN * __popc(mn)) {
+#ifdef FOVPT_TRACE_STATS
+                st_node_exec++; st_node_lanes += __popc(mn);
+#endif
+                if (node) T.node_step(S.bvh, stack);
+                stepped = node;
+            } else {
+                const uint32_t nmax = __reduce_max_sync(FULL, leaf ? T.leaf_work() : 0u);
+#ifdef FOVPT_TRACE_STATS
+                st_leaf_exec++; st_leaf_lanes += __popc(ml); st_leaf_nmax += nmax; st_leaf_tris += __reduce_add_sync(FULL, leaf ? T.leaf_work() : 0u);
+#endif
+                if (leaf) T.leaf_step(S.bvh, stack, nmax);
+                stepped = leaf;
+            }
+            if (stepped && T.done()) {
+                if (!T.any) q.hit[pid] = T.found() ? make_float4(T.best_t, T.best_u, T.best_v, __int_as_float((int)T.best_k))
+                                                  : make_float4(0.f, 0.f, 0.f, __int_as_float((int)kNoHit));
+                else shadow_resolve(ps, q.shadow, pid, T.found());
+            }
+        }
+#ifdef FOVPT_TRACE_STATS
+        st_fetch++;
+#endif
+    }
+#ifdef FOVPT_TRACE_STATS
+    if (lane == 0) {
+        unsigned long long* d = stats->dbg;
+        atomicAdd(d + 0, st_node_exec); atomicAdd(d + 1, st_node_lanes); atomicAdd(d + 2, st_leaf_exec); atomicAdd(d + 3, st_leaf_lanes);
+        atomicAdd(d + 4, st_leaf_tris); atomicAdd(d + 5, st_leaf_nmax); atomicAdd(d + 6, st_fetch);
+        atomicAdd(d + 7, (unsigned long long)(blockIdx.x == 0 && threadIdx.x == 0 ? n : 0));
+    }
+#else
+    (void)stats;
+#endif
+}
+
 __global__ void __launch_bounds__(128, FOVPT_TRACE_BLOCKS) k_trace(SceneDev S, PathState ps, Queues q, int shadow_slot, float tmin, float tmax,
                                                                     DevStats* __restrict__ stats)
 {
-    constexpr unsigned FULL = 0xffffffffu;
-    constexpr bool ANY = false;  (void)ANY;
     const uint32_t n_closest = q.counts[0], n_any = q.counts[shadow_slot];
     const uint32_t n = n_closest + n_any;
-    uint32_t* fetch = q.counts + 3;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         atomicAdd(&stats->radiance_rays, (unsigned long long)n_closest);
         atomicAdd(&stats->shadow_rays, (unsigned long long)n_any);
@@ -205,10 +285,6 @@ __global__ void __launch_bounds__(128, FOVPT_TRACE_BLOCKS) k_trace(SceneDev S, P
     // when there are SMs to spare (measured: 240 us -> 60 us floor per launch at 1/4 frame per GPU).
     const uint32_t total_warps = gridDim.x * (blockDim.x >> 5);
     const uint32_t cap = min(32u, max(1u, (n + total_warps - 1u) / total_warps));
-    const unsigned lanes = cap >= 32u ? FULL : ((1u << cap) - 1u);          // lanes that take rays in this launch
-    const int fetch_min = min(kFetchMin, (int)((cap + 3u) / 4u));
-    const unsigned lane = threadIdx.x & 31u;
-    FOVPT_TRAV(kMixed) T;
     int2 stack_local[kStackSize];
 #if FOVPT_SMEM_STACK > 0
     __shared__ int2 stack_shared[FOVPT_SMEM_STACK * 128];
@@ -216,71 +292,9 @@ __global__ void __launch_bounds__(128, FOVPT_TRACE_BLOCKS) k_trace(SceneDev S, P
 #else
     const RayStack stack = local_stack(stack_local);
 #endif
-    uint32_t pid = 0;
-    bool have = false, exhausted = false;
-    T.reset();
-#ifdef FOVPT_TRACE_STATS
-    unsigned long long st_node_exec = 0, st_node_lanes = 0, st_leaf_exec = 0, st_leaf_lanes = 0, st_leaf_tris = 0, st_leaf_nmax = 0, st_fetch = 0, st_idle = 0, st_idle_exh = 0, st_blocked = 0;
-#endif
-    for (;;) {
-        const unsigned idle = __ballot_sync(FULL, !have) & lanes;
-        if (idle == lanes || (!exhausted && __popc(idle) >= fetch_min)) {
-            if (!exhausted) {
-                const int want = __popc(idle);
-                uint32_t base = 0;
-                if (lane == 0) base = atomicAdd(fetch, (uint32_t)want);
-                base = __shfl_sync(FULL, base, 0);
-                const uint32_t mine = base + __popc(idle & ((1u << lane) - 1u));
-                if (!have && ((idle >> lane) & 1u) && mine < n) {
-                    const bool is_any = mine >= n_closest;
-                    pid = is_any ? mine - n_closest : mine;            // slot in the shadow / radiance buffer
-                    const float4 o = is_any ? q.shadow.o[pid] : q.cur.o[pid], d = is_any ? q.shadow.d[pid] : q.cur.d[pid];
-                    T.begin(make_float3(o.x, o.y, o.z), make_float3(d.x, d.y, d.z), tmin, tmax);
-                    T.any = is_any;
-                    have = true;
-                }
-                if (base + (uint32_t)want >= n) exhausted = true;
-            }
-            if (__ballot_sync(FULL, have) == 0u) break;
-        }
-        for (;;) {
-            // each iteration runs the step kind most lanes are waiting for; the others keep their state
-            const bool node = have && T.at_node(), leaf = have && T.at_leaf();
-            const unsigned mn = __ballot_sync(FULL, node), ml = __ballot_sync(FULL, leaf);
-            const int n_active = __popc(mn | ml);
-            if (n_active == 0) break;                                    // warp drained
-            if (!exhausted && n_active <= (int)cap - fetch_min) break;   // enough idle lanes: refill first
-            if (FOVPT_LEAF_NUM * __popc(ml) <= FOVPT_LEAF_DEN * __popc(mn)) {
-#ifdef FOVPT_TRACE_STATS
-                st_node_exec++; st_node_lanes += __popc(mn);
-                { const int idl = 32 - __popc(__ballot_sync(FULL, have)); if (exhausted) st_idle_exh += idl; else st_idle += idl; }
-#endif
-                if (node) T.node_step(S.bvh, stack);
-            } else {
-                const uint32_t nmax = __reduce_max_sync(FULL, leaf ? T.leaf_work() : 0u);
-#ifdef FOVPT_TRACE_STATS
-                st_leaf_exec++; st_leaf_lanes += __popc(ml); st_leaf_nmax += nmax; st_leaf_tris += __reduce_add_sync(FULL, leaf ? T.leaf_work() : 0u);
-#endif
-                if (leaf) T.leaf_step(S.bvh, stack, nmax);
-            }
-            if (have && T.done()) {
-                if (!T.any) q.hit[pid] = T.found() ? make_float4(T.best_t, T.best_u, T.best_v, __int_as_float((int)T.best_k))
-                                                  : make_float4(0.f, 0.f, 0.f, __int_as_float((int)kNoHit));
-                else shadow_resolve(ps, q.shadow, pid, T.found());
-                have = false;
-            }
-        }
-#ifdef FOVPT_TRACE_STATS
-        st_fetch++;
-#endif
-    }
-#ifdef FOVPT_TRACE_STATS
-    if (lane == 0) {
-        unsigned long long* d = stats->dbg;
-        atomicAdd(d + 0, st_node_exec); atomicAdd(d + 1, st_node_lanes); atomicAdd(d + 2, st_leaf_exec); atomicAdd(d + 3, st_leaf_lanes);
-        atomicAdd(d + 4, st_leaf_tris); atomicAdd(d + 5, st_leaf_nmax); atomicAdd(d + 6, st_fetch); atomicAdd(d + 8, st_idle); atomicAdd(d + 9, st_idle_exh); atomicAdd(d + 10, st_blocked); atomicAdd(d + 7, (unsigned long long)(blockIdx.x == 0 && threadIdx.x == 0 ? n : 0));
-    }
-#endif
+    // the full-width case gets its own copy of the loop with cap / lanes / fetch_min folded into constants
+    if (cap >= 32u) trace_loop<false>(S, ps, q, shadow_slot, tmin, tmax, stack, n_closest, n, 32u, stats);
+    else trace_loop<true>(S, ps, q, shadow_slot, tmin, tmax, stack, n_closest, n, cap, stats);
 }
 
 // ------------------------------------------------------------------ k_shade  (closest-hit / miss program)
@@ -568,25 +582,25 @@ __global__ void k_trace_query(SceneDev S, const float* __restrict__ rays, size_t
         const float3 o = make_float3(r[0], r[1], r[2]), d = make_float3(r[4], r[5], r[6]);
         if (mode == 0) {
             HitRec h;
-            const bool ok = trace_closest(S.bvh, o, d, r[3], r[7], h);
+            const bool ok = trace_closest(S.bvh, o, d, fmaxf(r[3], 0.f), r[7], h);
             tri[i] = ok ? (int32_t)h.gid : -1;
             tuv[3 * i] = ok ? h.t : 0.f; tuv[3 * i + 1] = ok ? h.u : 0.f; tuv[3 * i + 2] = ok ? h.v : 0.f;
         } else if (mode == 1) {
-            tri[i] = trace_any_front(S.bvh, o, d, r[3], r[7]) ? 1 : 0;
+            tri[i] = trace_any_front(S.bvh, o, d, fmaxf(r[3], 0.f), r[7]) ? 1 : 0;
         } else {                                       // modes 2 / 3: closest / any with visit counters in tuv
             float nodes = 0.f, leaves = 0.f, tris = 0.f;
             int2 stack_local[kStackSize];
             const RayStack stack = local_stack(stack_local);
             if (S.bvh.n_tris == 0) { tri[i] = mode == 2 ? -1 : 0; }
             else if (mode == 2) {
-                FOVPT_TRAV(kClosest) T; T.begin(o, d, r[3], r[7]);
+                FOVPT_TRAV(kClosest) T; T.begin(o, d, fmaxf(r[3], 0.f), r[7]);
                 while (!T.done()) {
                     if (T.at_node()) { nodes += 1.f; T.node_step(S.bvh, stack); }
                     else { leaves += 1.f; tris += (float)T.leaf_work(); T.leaf_step(S.bvh, stack, T.leaf_work()); }
                 }
                 tri[i] = T.found() ? (int32_t)T.best_gid : -1;
             } else {
-                FOVPT_TRAV(kAny) T; T.begin(o, d, r[3], r[7]);
+                FOVPT_TRAV(kAny) T; T.begin(o, d, fmaxf(r[3], 0.f), r[7]);
                 while (!T.done()) {
                     if (T.at_node()) { nodes += 1.f; T.node_step(S.bvh, stack); }
                     else { leaves += 1.f; tris += (float)T.leaf_work(); T.leaf_step(S.bvh, stack, T.leaf_work()); }

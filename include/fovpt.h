@@ -26,7 +26,7 @@ typedef struct fovpt_ctx fovpt_ctx;
 /* Runtime form of the reference's compile-time literals; fovpt_default_config() yields sv5's. */
 typedef struct fovpt_config {
     int32_t max_depth;        /* deviceProgram.cu:515 literal 4 (orig: 8, PT_original/deviceProgram.cu:429) */
-    float   tmin, tmax;       /* deviceProgram.cu:41-42 : 0.01f, 1e16f                                 */
+    float   tmin, tmax;       /* deviceProgram.cu:41-42 : 0.01f, 1e16f; need 0 <= tmin < tmax          */
     float   exposure;         /* deviceProgram.cu:586 : 2^4                                            */
     int32_t accumulate;       /* 0 = sv5 (lerp commented out :565-581); 1 = vmv2 lerp                   *
                                * (PT_sv4_vmv2/deviceProgram.cu:545-553)                                 */
@@ -108,7 +108,7 @@ int fovpt_download(fovpt_ctx*, uint32_t* dst, size_t npix);
 int fovpt_download_accum(fovpt_ctx*, float* dst_rgba, size_t npix);
 
 /* -- ray queries (optixTrace equivalents, deviceProgram.cu:196-248), for parity tests and tools.
- *    rays: n x {ox,oy,oz,tmin, dx,dy,dz,tmax} host floats.  mode 0: closest hit -> tri = global
+ *    rays: n x {ox,oy,oz,tmin, dx,dy,dz,tmax} host floats (a negative tmin counts as 0).  mode 0: closest hit -> tri = global
  *    triangle id or -1, tuv = t,u,v.  mode 1: any front-facing hit -> tri = 1/0.  modes 2 / 3: as 0 / 1
  *    but tuv = (inner nodes visited, leaves visited, triangles tested) -- BVH-quality introspection. */
 int fovpt_trace(fovpt_ctx*, const float* rays, size_t n, int mode, int32_t* tri, float* tuv);

@@ -19,10 +19,13 @@ roofline: traversal kernel k_trace against the HBM roofline, algorithmic bytes p
 cpu_baseline / --impl reference: the CPU checker (oracle/) on the same workload on host cores.
 
 Multi-GPU (torchrun, one rank per GPU): tiles weighted by foveal sample density are split across
-ranks (partition.py); each rank traces only its tiles; one NCCL reduce of the RGBA8 frame per step.
+ranks (partition.py); each rank traces only its tiles and stores their pixels straight into rank 0's frame over NVLink peer
+memory (include/fovpt.h fovpt_peer_frame_*; --gather nccl: one NCCL reduce of the RGBA8 frame per step instead).
 """
 import argparse
+import contextlib
 import ctypes as C
+import io
 import json
 import os
 import subprocess
@@ -204,9 +207,27 @@ def native_arm(args):
     r.setCamera(wl.camera)
     r.setProbe(ProbeData(wl.probe()).BuildCDF())
     lp.frame.c_x, lp.frame.c_y = wl.gaze_xy()
+    gather = args.gather if world > 1 else "none"
+    frame_own = None
     if world > 1:
         owner, loads = partition.partition(w, h, wl.gaze_xy(), wl.inner_radius, wl.outer_radius, world, args.tile, wl.spp, bool(wl.foveated), wl.spp_uniform)
         r.ctx.set_tile_owner(args.tile, owner, rank)
+        if gather == "peer":
+            # the frame lives on rank 0; the other ranks map it (CUDA IPC over NVLink) and their resolve kernels store
+            # their tiles straight into it -- include/fovpt.h fovpt_peer_frame_*; no collective call per frame
+            if rank == 0:
+                handle, shared_ptr = r.ctx.peer_frame_create(w * h, world, 0)
+                hb = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")
+            else:
+                hb = torch.empty(128, dtype=torch.uint8, device="cuda")
+            dist.broadcast(hb, src=0)
+            if rank != 0:
+                shared_ptr = r.ctx.peer_frame_open(bytes(hb.cpu().tolist()), rank)
+            lp.frame.frame_buffer = shared_ptr
+        elif rank == 0:
+            # NCCL path: rank 0 renders its tiles into its own buffer; frame_t receives the sum over ranks
+            frame_own = torch.zeros((h, w), dtype=torch.int32, device="cuda")
+            lp.frame.frame_buffer = frame_own.data_ptr()
     elif args.emulate_world > 1:        # profiling aid: one process renders rank 0's share of an N-rank partition
         owner, loads = partition.partition(w, h, wl.gaze_xy(), wl.inner_radius, wl.outer_radius, args.emulate_world, args.tile, wl.spp, bool(wl.foveated), wl.spp_uniform)
         r.ctx.set_tile_owner(args.tile, owner, 0)
@@ -223,8 +244,26 @@ def native_arm(args):
             cam_k, gaze_k = wl.view_at(step_no[0]); step_no[0] += 1
             r.setCamera(cam_k); lp.frame.c_x, lp.frame.c_y = gaze_k
         r.ctx.render_frame(lp)
-        if world > 1:
+        gather_frame()
+
+    def gather_frame(consume=None):
+        """the frame's one exchange step: every rank's tiles end up in rank 0's frame; `consume` reads it on rank 0"""
+        if gather == "peer":
+            if rank == 0:
+                r.ctx.peer_frame_wait()                # this stream waits for every contributor's arrival flag
+                if consume:
+                    consume()
+                r.ctx.peer_frame_release()             # contributors may overwrite the frame from here on
+            else:
+                r.ctx.peer_frame_signal()
+        elif gather == "nccl":
+            if rank == 0:
+                frame_t.copy_(frame_own)
             dist.reduce(frame_t, dst=0, op=dist.ReduceOp.SUM)
+            if rank == 0 and consume:
+                consume()
+        elif consume:
+            consume()
 
     def barrier():
         torch.cuda.synchronize()
@@ -251,6 +290,8 @@ def native_arm(args):
     r.ctx.reset_stats()
     lp.frame.subframe_index = 0; step_no[0] = 0
     accum_t.zero_(); frame_t.zero_()
+    if frame_own is not None:
+        frame_own.zero_()
 
     # ---- device-timed region: K steps, each bracketed by its own event pair, L2 flushed in between
     clocks = ClockSampler(local) if rank == 0 else None
@@ -301,13 +342,15 @@ def native_arm(args):
             r.setCamera(cam_k); lp.frame.c_x, lp.frame.c_y = gaze_k
         if world == 1:
             r.render()                                 # SampleRenderer::render(): LaunchParams host -> device, 3 passes, sync
-        else:
-            r.render_async()
-            dist.reduce(frame_t, dst=0, op=dist.ReduceOp.SUM)
-        if rank == 0:
             r.downloadPixels(host_np)                  # SampleRenderer::downloadPixels(): RGBA8 frame device -> host, blocking
         else:
-            torch.cuda.current_stream().synchronize()
+            r.render_async()
+            if gather == "peer":
+                gather_frame(lambda: r.downloadPixels(host_np))          # blocking D2H of the shared frame on rank 0
+            else:
+                gather_frame(lambda: (host_frame.copy_(frame_t), torch.cuda.current_stream().synchronize()))
+            if rank != 0:
+                torch.cuda.current_stream().synchronize()
     e1.record()
     barrier()
     e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
@@ -335,6 +378,10 @@ def native_arm(args):
                     "d2h_bytes_per_step": w * h * 4, "ms_per_step": e2e_ms / args.steps, "frame_checksum": checksum},
             "clocks": clk, "wall_s_timed_region": t_wall, "step_ms": step_ms, "per_rank": per_rank,
         }
+        if world > 1:
+            line["config"]["parallelism"] = f"{world} ranks, screen tiles of {args.tile} px weighted by foveal sample density"
+            line["config"]["gather"] = ("peer stores into rank 0's frame over NVLink (CUDA IPC), fused into k_resolve_px; device-side arrival/release flags"
+                                        if gather == "peer" else "one NCCL reduce(SUM) of zero-filled RGBA8 frames per step")
         ab = algorithmic_bytes(wl.name)
         if args.kernel_times and ext_ms > 0:
             # k_trace serves both ray kinds in one launch (stats field last_extend_ms carries its time)
@@ -374,14 +421,31 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--tile", type=int, default=32, help="screen tile edge of the multi-GPU partition")
+    ap.add_argument("--gather", choices=("peer", "nccl"), default="peer",
+                    help="N>1: how the ranks' tiles reach rank 0 -- peer: stores into rank 0's frame over NVLink peer memory, fused into "
+                         "the resolve kernel (default); nccl: one dist.reduce(SUM) of zero-filled RGBA8 frames")
     ap.add_argument("--emulate-world", type=int, default=1, help="profiling aid: render only rank 0's tiles of an N-rank partition (single process; value is NOT a benchmark number)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-times", dest="kernel_times", action="store_false")
     args = ap.parse_args()
-    if args.impl == "reference":
-        reference_arm(args)
-    else:
-        native_arm(args)
+    # contract: ONE JSON line on stdout.  Libraries under us may print banners there (NCCL prints its version when the
+    # box exports NCCL_DEBUG), so fd 1 points at stderr while the benchmark runs and is restored for the result line.
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    buf = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(buf):
+            if args.impl == "reference":
+                reference_arm(args)
+            else:
+                native_arm(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    sys.stdout.write(buf.getvalue())
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

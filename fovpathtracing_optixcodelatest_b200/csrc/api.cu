@@ -26,6 +26,9 @@ struct EventPair { cudaEvent_t a, b; int kind; };
 
 }  // namespace
 
+// flag words behind the shared frame of fovpt_peer_frame_*: arrival[0..63] by rank, then release, then the owner's error word
+constexpr int kPeerMaxWorld = 64, kPeerRelease = 64, kPeerError = 65, kPeerFlagWords = 128;
+
 struct fovpt_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -66,6 +69,14 @@ struct fovpt_ctx {
 
     // partition
     uint8_t* d_tile_owner = nullptr; int tile_size = 0, tiles_x = 0, tiles_y = 0, rank = 0;
+
+    // shared frame of a multi-GPU job (fovpt_peer_frame_*): `base` is the owner's allocation (mapped through CUDA IPC on
+    // the contributors) = RGBA8 frame, then kPeerFlagWords u32: arrival[rank] | release | owner-side error
+    struct PeerFrame {
+        unsigned char* base = nullptr; uint32_t* flags = nullptr; uint32_t* d_err = nullptr;
+        bool open = false, owner = false; int world = 0, owner_rank = 0, rank = 0; uint32_t seq = 0; size_t npix = 0;
+        long long timeout_clocks = 0;
+    } peer;
 
     // stats
     uint64_t launches = 0, frames = 0;
@@ -285,6 +296,9 @@ int run_frame(fovpt_ctx* c, const LaunchParamsBlob& lp, const std::vector<PassHo
             launch_resolve_li(c->L, F, ch.pass, ch.row0, ch.row1, ch.pid_base, c->needed, c->ps, c->li_backplate, c->li_color);
         }
     }
+    // a contributor to a shared frame stores its pixels into the owner's memory: not before the owner released the last frame
+    if (c->peer.open && !c->peer.owner)
+        launch_peer_wait(c->L, c->peer.flags + kPeerRelease, 1, -1, c->peer.seq, c->peer.d_err, c->peer.timeout_clocks);
     { Timed t(c, K_RESOLVE); launch_resolve_px(c->L, F, c->owner_map, c->li_color, c->needed, c->cfg.fast_math != 0); }
     cudaEventRecord(c->ev_frame1, c->stream);
     c->frame_timed = true;
@@ -384,6 +398,7 @@ int fovpt_destroy(fovpt_ctx* c)
     if (!c) return 0;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    fovpt_peer_frame_close(c);
     free_scene(c); free_paths(c);
     cudaFree(c->p_data); cudaFree(c->p_pdfX); cudaFree(c->p_cdfX); cudaFree(c->p_pdfY); cudaFree(c->p_cdfY); cudaFree(c->p_gy); cudaFree(c->p_gx);
     cudaFree(c->fb_accum); cudaFree(c->fb_frame); cudaFree(c->li_backplate); cudaFree(c->li_color); cudaFree(c->needed);
@@ -603,6 +618,16 @@ int fovpt_sync(fovpt_ctx* c)
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());
     collect_times(c);
+    if (c->peer.open) {                       // a wait on the shared frame that timed out left the number of the missing rank + 1
+        uint32_t* where = c->peer.owner ? c->peer.flags + kPeerError : c->peer.d_err;
+        uint32_t e = 0;
+        CU(cudaMemcpy(&e, where, 4, cudaMemcpyDeviceToHost));
+        if (e) {
+            CU(cudaMemset(where, 0, 4));
+            return fail(c, c->peer.owner ? "peer frame: rank " + std::to_string(e - 1) + " did not deliver its tiles in time"
+                                         : std::string("peer frame: the owner did not release the previous frame in time"));
+        }
+    }
     return 0;
 }
 
@@ -758,6 +783,117 @@ int fovpt_bvh_read(fovpt_ctx* c, void* nodes64, uint32_t* sorted_tri_ids)
     cudaSetDevice(c->device);
     if (nodes64 && c->bvh.n_nodes) CU(cudaMemcpy(nodes64, c->bvh.nodes, (size_t)c->bvh.n_nodes * (kBvhWide == 8 ? 96 : 64), cudaMemcpyDeviceToHost));
     if (sorted_tri_ids && c->bvh.n_tris) CU(cudaMemcpy(sorted_tri_ids, c->bvh.sorted_ids, (size_t)c->bvh.n_tris * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ---- shared frame over peer memory.  handle = { cudaIpcMemHandle_t (64 B) | npix u64 | world i32 | owner rank i32 | magic u32 }
+namespace {
+struct PeerHandleBlob { cudaIpcMemHandle_t mem; unsigned long long npix; int world, owner_rank; unsigned magic; unsigned pad_[11]; };
+static_assert(sizeof(PeerHandleBlob) == sizeof(fovpt_peer_handle), "fovpt_peer_handle is 128 opaque bytes");
+constexpr unsigned kPeerMagic = 0x46505446u;
+size_t peer_frame_bytes(size_t npix) { return (npix * 4 + 255) & ~(size_t)255; }
+long long peer_timeout_clocks(int device)
+{
+    double ms = 5000.0;
+    if (const char* e = getenv("FOVPT_PEER_TIMEOUT_MS")) ms = atof(e) > 0 ? atof(e) : ms;
+    int khz = 1900000;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device);
+    return (long long)(ms * (double)khz);
+}
+}  // namespace
+
+int fovpt_peer_frame_create(fovpt_ctx* c, size_t npix, int world, int rank, fovpt_peer_handle* handle_out, uint32_t** frame_out)
+{
+    if (!c || !handle_out || !frame_out) return 1;
+    if (c->peer.open) return fail(c, "a peer frame is already open on this context");
+    if (npix == 0 || world < 1 || world > kPeerMaxWorld || rank < 0 || rank >= world) return fail(c, "peer frame: bad size, world or rank");
+    cudaSetDevice(c->device);
+    const size_t fb = peer_frame_bytes(npix);
+    unsigned char* base = nullptr;
+    CU(cudaMalloc((void**)&base, fb + kPeerFlagWords * 4));
+    CU(cudaMemset(base, 0, fb + kPeerFlagWords * 4));
+    PeerHandleBlob h; memset(&h, 0, sizeof(h));
+    cudaError_t e = cudaIpcGetMemHandle(&h.mem, base);
+    if (e != cudaSuccess) { cudaFree(base); return cuda_fail(c, e, "cudaIpcGetMemHandle"); }
+    h.npix = npix; h.world = world; h.owner_rank = rank; h.magic = kPeerMagic;
+    memcpy(handle_out, &h, sizeof(h));
+    c->peer = fovpt_ctx::PeerFrame{};
+    c->peer.base = base; c->peer.flags = (uint32_t*)(base + fb); c->peer.open = true; c->peer.owner = true;
+    c->peer.world = world; c->peer.owner_rank = rank; c->peer.rank = rank; c->peer.npix = npix;
+    c->peer.timeout_clocks = peer_timeout_clocks(c->device);
+    *frame_out = (uint32_t*)base;
+    return 0;
+}
+
+int fovpt_peer_frame_open(fovpt_ctx* c, const fovpt_peer_handle* handle, int rank, uint32_t** frame_out)
+{
+    if (!c || !handle || !frame_out) return 1;
+    if (c->peer.open) return fail(c, "a peer frame is already open on this context");
+    PeerHandleBlob h; memcpy(&h, handle, sizeof(h));
+    if (h.magic != kPeerMagic || h.world < 1 || h.world > kPeerMaxWorld) return fail(c, "peer frame: not a handle from fovpt_peer_frame_create");
+    if (rank < 0 || rank >= h.world || rank == h.owner_rank) return fail(c, "peer frame: rank out of range (or the owner's)");
+    cudaSetDevice(c->device);
+    void* base = nullptr;
+    CU(cudaIpcOpenMemHandle(&base, h.mem, cudaIpcMemLazyEnablePeerAccess));
+    uint32_t* d_err = nullptr;
+    cudaError_t e = dmalloc(&d_err, 1);
+    if (e == cudaSuccess) e = cudaMemset(d_err, 0, 4);
+    if (e != cudaSuccess) { cudaIpcCloseMemHandle(base); return cuda_fail(c, e, "peer frame error word"); }
+    c->peer = fovpt_ctx::PeerFrame{};
+    c->peer.base = (unsigned char*)base; c->peer.flags = (uint32_t*)((unsigned char*)base + peer_frame_bytes(h.npix)); c->peer.d_err = d_err;
+    c->peer.open = true; c->peer.owner = false; c->peer.world = h.world; c->peer.owner_rank = h.owner_rank; c->peer.rank = rank;
+    c->peer.npix = (size_t)h.npix; c->peer.timeout_clocks = peer_timeout_clocks(c->device);
+    *frame_out = (uint32_t*)base;
+    return 0;
+}
+
+int fovpt_peer_frame_signal(fovpt_ctx* c)
+{
+    if (!c) return 1;
+    if (!c->peer.open || c->peer.owner) return fail(c, "peer frame: signal is the contributor's call");
+    cudaSetDevice(c->device);
+    launch_peer_signal(c->L, c->peer.flags + c->peer.rank, ++c->peer.seq);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int fovpt_peer_frame_wait(fovpt_ctx* c)
+{
+    if (!c) return 1;
+    if (!c->peer.open || !c->peer.owner) return fail(c, "peer frame: wait is the owner's call");
+    cudaSetDevice(c->device);
+    ++c->peer.seq;
+    if (c->peer.world > 1) {
+        launch_peer_wait(c->L, c->peer.flags, c->peer.world, c->peer.owner_rank, c->peer.seq, c->peer.flags + kPeerError, c->peer.timeout_clocks);
+        c->launches++;
+    }
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int fovpt_peer_frame_release(fovpt_ctx* c)
+{
+    if (!c) return 1;
+    if (!c->peer.open || !c->peer.owner) return fail(c, "peer frame: release is the owner's call");
+    cudaSetDevice(c->device);
+    launch_peer_signal(c->L, c->peer.flags + kPeerRelease, c->peer.seq);
+    c->launches++;
+    CU(cudaGetLastError());
+    return 0;
+}
+
+int fovpt_peer_frame_close(fovpt_ctx* c)
+{
+    if (!c) return 1;
+    if (!c->peer.open) return 0;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    if (c->last_frame_ptr == (uint32_t*)c->peer.base) { c->last_frame_ptr = nullptr; c->last_npix = 0; }
+    if (c->peer.owner) cudaFree(c->peer.base);
+    else { cudaIpcCloseMemHandle(c->peer.base); cudaFree(c->peer.d_err); }
+    c->peer = fovpt_ctx::PeerFrame{};
+    cudaGetLastError();
     return 0;
 }
 

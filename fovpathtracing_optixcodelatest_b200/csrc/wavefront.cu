@@ -619,6 +619,37 @@ __global__ void k_swap_counts(uint32_t* counts, int consumed_slot)
     if (threadIdx.x == 0 && blockIdx.x == 0) { counts[0] = counts[1]; counts[1] = 0; counts[3] = 0; counts[consumed_slot] = 0; }
 }
 
+// ------------------------------------------------------------------ peer-frame flags (multi-GPU gather over NVLink peer memory)
+// The shared frame lives in the owner's memory; contributors store their tiles into it from k_resolve_px.  Ordering between
+// the processes is carried by 32-bit sequence numbers in the same allocation, written and polled at system scope: a
+// kernel boundary on the writer's stream precedes the signal, so every pixel store of the frame is performed before the
+// flag becomes visible.  Sequence numbers compare modulo 2^32.
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__global__ void k_peer_signal(uint32_t* flag, uint32_t seq)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(seq) : "memory");
+    }
+}
+// thread i waits until flags[i] has reached seq (skip = the index that is not waited for, -1: none); a peer that does not
+// arrive within `timeout` clocks raises *err instead of hanging the stream
+__global__ void k_peer_wait(const uint32_t* flags, int count, int skip, uint32_t seq, uint32_t* err, long long timeout)
+{
+    const int i = (int)threadIdx.x;
+    if (i >= count || i == skip) return;
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys(flags + i) - seq) < 0) {
+        if (clock64() - t0 > timeout) { atomicExch(err, 1u + (uint32_t)i); return; }
+        __nanosleep(256);
+    }
+}
+
 // ------------------------------------------------------------------ launch wrappers (host)
 void launch_owner_map(const LaunchCfg& L, const FrameDev& F, uint32_t* owner_map, uint8_t* needed)
 {
@@ -639,6 +670,11 @@ void launch_shade(const LaunchCfg& L, const FrameDev& F, const SceneDev& S, cons
     else k_shade<false><<<L.grid_shade, 128, 0, L.stream>>>(F, S, ps, q, shadow_slot);
 }
 void launch_swap(const LaunchCfg& L, uint32_t* counts, int consumed_slot) { k_swap_counts<<<1, 32, 0, L.stream>>>(counts, consumed_slot); }
+void launch_peer_signal(const LaunchCfg& L, uint32_t* flag, uint32_t seq) { k_peer_signal<<<1, 32, 0, L.stream>>>(flag, seq); }
+void launch_peer_wait(const LaunchCfg& L, const uint32_t* flags, int count, int skip, uint32_t seq, uint32_t* err, long long timeout_clocks)
+{
+    k_peer_wait<<<1, 64, 0, L.stream>>>(flags, count, skip, seq, err, timeout_clocks);
+}
 void launch_resolve_li(const LaunchCfg& L, const FrameDev& F, int pass, unsigned row0, unsigned row1, unsigned pid_base,
                        const uint8_t* needed, const PathState& ps, const float4* li_backplate, float4* li_color)
 {

@@ -44,6 +44,8 @@ EXPORTS = [
     "fovpt_probe_upload", "fovpt_resize", "fovpt_launch", "fovpt_render_frame", "fovpt_sync", "fovpt_download",
     "fovpt_download_accum", "fovpt_trace", "fovpt_primary_hits", "fovpt_set_tile_owner", "fovpt_get_stats",
     "fovpt_reset_stats", "fovpt_bvh_info", "fovpt_bvh_layout", "fovpt_bvh_read",
+    "fovpt_peer_frame_create", "fovpt_peer_frame_open", "fovpt_peer_frame_signal", "fovpt_peer_frame_wait",
+    "fovpt_peer_frame_release", "fovpt_peer_frame_close",
 ]
 
 _lib = None
@@ -86,6 +88,10 @@ def load_library():
     L.fovpt_bvh_info.argtypes = [vp, u64p, u64p]
     L.fovpt_bvh_layout.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.fovpt_bvh_read.argtypes = [vp, vp, vp]
+    L.fovpt_peer_frame_create.argtypes = [vp, C.c_size_t, i32, i32, vp, C.POINTER(vp)]
+    L.fovpt_peer_frame_open.argtypes = [vp, vp, i32, C.POINTER(vp)]
+    for n in ("signal", "wait", "release", "close"):
+        getattr(L, "fovpt_peer_frame_" + n).argtypes = [vp]
     for n in EXPORTS:
         if n not in ("fovpt_last_error", "fovpt_stream", "fovpt_default_config"):
             getattr(L, n).restype = C.c_int
@@ -228,6 +234,31 @@ class Context:
             return
         o = np.ascontiguousarray(owner, dtype=np.uint8)
         self._chk(self.L.fovpt_set_tile_owner(self.h, tile_size, o.shape[1], o.shape[0], _p(o), rank))
+
+    # ---- shared frame of a multi-GPU job (include/fovpt.h, fovpt_peer_frame_*)
+    def peer_frame_create(self, npix, world, owner_rank=0):
+        """owner: allocate the shared RGBA8 frame; returns (128-byte handle for the other ranks, device pointer)"""
+        handle = (C.c_ubyte * 128)(); ptr = C.c_void_p()
+        self._chk(self.L.fovpt_peer_frame_create(self.h, npix, world, owner_rank, handle, C.byref(ptr)))
+        return bytes(handle), ptr.value
+
+    def peer_frame_open(self, handle: bytes, rank):
+        """contributor: map the owner's frame; returns the device pointer to put in LaunchParams.frame.frame_buffer"""
+        buf = (C.c_ubyte * 128).from_buffer_copy(handle); ptr = C.c_void_p()
+        self._chk(self.L.fovpt_peer_frame_open(self.h, buf, rank, C.byref(ptr)))
+        return ptr.value
+
+    def peer_frame_signal(self):
+        self._chk(self.L.fovpt_peer_frame_signal(self.h))
+
+    def peer_frame_wait(self):
+        self._chk(self.L.fovpt_peer_frame_wait(self.h))
+
+    def peer_frame_release(self):
+        self._chk(self.L.fovpt_peer_frame_release(self.h))
+
+    def peer_frame_close(self):
+        self._chk(self.L.fovpt_peer_frame_close(self.h))
 
     def stats(self) -> dict:
         s = Stats()

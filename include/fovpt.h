@@ -121,6 +121,27 @@ int fovpt_primary_hits(fovpt_ctx*, const void* launch_params248, unsigned lw, un
  *    owner: tiles_x*tiles_y bytes (row-major, tile (0,0) at pixel (0,0)); NULL clears. */
 int fovpt_set_tile_owner(fovpt_ctx*, int tile_size, int tiles_x, int tiles_y, const uint8_t* owner, int rank);
 
+/* -- multi-GPU frame gather over peer memory (SURVEY 8e "one collective per frame"; no reference counterpart).
+ *    One process per GPU.  The rank that displays the frame (the owner) allocates the shared RGBA8 frame with
+ *    fovpt_peer_frame_create and hands the 128-byte handle to the other ranks (any transport: a broadcast, a pipe);
+ *    they map it with fovpt_peer_frame_open (CUDA IPC, NVLink peer access).  Every rank passes the returned pointer
+ *    as LaunchParams.frame.frame_buffer: the resolve kernel of fovpt_render_frame then stores the pixels of the
+ *    rank's own tiles (fovpt_set_tile_owner) straight into the owner's memory -- the gather is fused into the
+ *    kernel that produces the pixels.  Ordering is device-side, no host synchronisation and no collective call:
+ *      contributor, per frame:  fovpt_render_frame; fovpt_peer_frame_signal      (arrival flag in the owner's memory)
+ *      owner, per frame:        fovpt_render_frame; fovpt_peer_frame_wait;       (its stream waits for every arrival)
+ *                               ...read / download the frame...; fovpt_peer_frame_release
+ *    and a contributor's next resolve kernel waits for that release before it overwrites the frame.  A rank that
+ *    does not show up within FOVPT_PEER_TIMEOUT_MS (environment, default 5000) makes the next fovpt_sync fail
+ *    instead of hanging the stream.  All calls are asynchronous on the context stream except create/open/close. */
+typedef struct fovpt_peer_handle { unsigned char opaque[128]; } fovpt_peer_handle;
+int fovpt_peer_frame_create(fovpt_ctx*, size_t npix, int world, int owner_rank, fovpt_peer_handle* handle_out, uint32_t** frame_out);
+int fovpt_peer_frame_open(fovpt_ctx*, const fovpt_peer_handle*, int rank, uint32_t** frame_out);
+int fovpt_peer_frame_signal(fovpt_ctx*);
+int fovpt_peer_frame_wait(fovpt_ctx*);
+int fovpt_peer_frame_release(fovpt_ctx*);
+int fovpt_peer_frame_close(fovpt_ctx*);
+
 int fovpt_get_stats(fovpt_ctx*, fovpt_stats*);
 int fovpt_reset_stats(fovpt_ctx*);
 /* BVH introspection for validity tests: branching factor (8 or 4) and node size in bytes (96 / 64, layout in

@@ -647,3 +647,106 @@ def test_full_size_c3_properties(gpu, port):
     expect = a0[..., :3] + (np.clip(s1[..., :3], 0, 10) - a0[..., :3]) * np.float32(0.5)
     assert np.allclose(a1[..., :3], expect, rtol=1e-5, atol=1e-6)
     r.close(); r2.close(); o.close(); o2.close()
+
+
+# ---- shared frame over peer memory (fovpt_peer_frame_*): one process per rank, here all on cuda:0 ----------------------
+def _peer_rank_main(rank, world, owner, w, h, ri, ro, frames, conn, never_signal):
+    """one rank of a multi-process job: renders its tiles of `frames` successive frames into the owner's frame"""
+    try:
+        from fovpathtracing_optixcodelatest_b200 import native, scenes as sc_
+        from fovpathtracing_optixcodelatest_b200.renderer import ProbeData, SampleRenderer
+        cfg = native.default_config(); cfg.inner_radius, cfg.outer_radius = ri, ro
+        r = SampleRenderer(sc_.cornell_box(), 0, cfg)
+        r.resize((w, h)); r.setCamera(sc_.CORNELL_CAMERA); r.setProbe(ProbeData(sc_.constant_probe(16, 8, 2.5)).BuildCDF())
+        r.launchParams.frame.c_x, r.launchParams.frame.c_y = w // 2, h // 2
+        r.ctx.set_tile_owner(32, owner, rank)
+        if rank == 0:
+            handle, ptr = r.ctx.peer_frame_create(w * h, world, 0)
+            conn.send(handle)
+        else:
+            ptr = r.ctx.peer_frame_open(conn.recv(), rank)
+        r.launchParams.frame.frame_buffer = ptr
+        out = []
+        for k in range(frames):
+            r.launchParams.frame.subframe_index = k
+            r.render_async()
+            if rank == 0:
+                r.ctx.peer_frame_wait()
+                out.append(r.downloadPixels().copy())         # reads the shared frame after every rank has arrived
+                r.ctx.peer_frame_release()
+            elif not never_signal:
+                r.ctx.peer_frame_signal()
+        err = None
+        try:
+            r.ctx.sync()
+        except RuntimeError as e:
+            err = str(e)
+        conn.send((out, err))
+        conn.recv()                                          # keep the mapping alive until the parent has everything
+        r.ctx.peer_frame_close(); r.close()
+    except Exception as e:                                   # noqa: BLE001 - report to the parent instead of hanging it
+        conn.send(([], "worker failed: " + repr(e)))
+
+
+def _run_peer_job(world, owner, w, h, ri, ro, frames, never_signal=False, env=None):
+    import multiprocessing as mp
+    import os
+    old = {k: os.environ.get(k) for k in (env or {})}
+    os.environ.update(env or {})
+    try:
+        ctx = mp.get_context("spawn")
+        pipes = [ctx.Pipe() for _ in range(world)]
+        procs = [ctx.Process(target=_peer_rank_main, args=(rk, world, owner, w, h, ri, ro, frames, pipes[rk][1], never_signal)) for rk in range(world)]
+        for p in procs:
+            p.start()
+        handle = pipes[0][0].recv()
+        for rk in range(1, world):
+            pipes[rk][0].send(handle)
+        res = []
+        for rk in range(world):
+            assert pipes[rk][0].poll(120), f"rank {rk} did not report"
+            res.append(pipes[rk][0].recv())
+        for rk in range(world):
+            pipes[rk][0].send("bye")
+        for p in procs:
+            p.join(60)
+        return res
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def test_peer_frame_gather_matches_single_rank(gpu, port):
+    """multi-GPU gather fused into the resolve kernel: three processes render their density-weighted tiles and store
+    the pixels straight into rank 0's frame through CUDA IPC (NVLink peer stores on a multi-GPU box; the same device
+    here); arrival / release flags order the frames on the device.  Every frame of the sequence equals the 1-rank frame."""
+    w, h, ri, ro, frames, world = 384, 216, 30, 96, 3, 3
+    sc, cam, probe = scenes.cornell_box(), scenes.CORNELL_CAMERA, scenes.constant_probe(16, 8, 2.5)
+    r, o, lp, _, _ = make_pair(gpu, port, sc, cam, w, h, probe, ri, ro)
+    want = []
+    for k in range(frames):
+        r.launchParams.frame.subframe_index = k
+        r.render(); want.append(r.downloadPixels().copy())
+    r.close(); o.close()
+    assert not (want[0] == want[1]).all()                    # the sequence really changes from frame to frame
+    owner, _ = partition.partition(w, h, (w // 2, h // 2), ri, ro, world, 32)
+    res = _run_peer_job(world, owner, w, h, ri, ro, frames)
+    for rk, (_, err) in enumerate(res):
+        assert err is None, f"rank {rk}: {err}"
+    got = res[0][0]
+    assert len(got) == frames
+    for k in range(frames):
+        assert (got[k] == want[k]).all(), f"frame {k}: {(got[k] != want[k]).sum()} pixels differ"
+
+
+def test_peer_frame_missing_rank_times_out(gpu):
+    """a contributor that never delivers must not hang the owner's stream: the wait gives up after
+    FOVPT_PEER_TIMEOUT_MS and the next fovpt_sync names the missing rank"""
+    w, h, ri, ro, world = 192, 108, 16, 48, 2
+    owner, _ = partition.partition(w, h, (w // 2, h // 2), ri, ro, world, 32)
+    res = _run_peer_job(world, owner, w, h, ri, ro, 1, never_signal=True, env={"FOVPT_PEER_TIMEOUT_MS": "300"})
+    assert res[0][1] is not None and "rank 1 did not deliver" in res[0][1], res[0][1]
+    assert res[1][1] is None

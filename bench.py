@@ -209,9 +209,16 @@ def native_arm(args):
     lp.frame.c_x, lp.frame.c_y = wl.gaze_xy()
     gather = args.gather if world > 1 else "none"
     frame_own = None
+    tile = args.tile
     if world > 1:
-        owner, loads = partition.partition(w, h, wl.gaze_xy(), wl.inner_radius, wl.outer_radius, world, args.tile, wl.spp, bool(wl.foveated), wl.spp_uniform)
-        r.ctx.set_tile_owner(args.tile, owner, rank)
+        if wl.view_at is not None:
+            # moving gaze (C4): a static interleaved partition balances wherever the gaze is (partition.interleaved); the
+            # density-weighted LPT assignment would cost ~150 ms of host time per gaze point
+            tile = 16
+            owner = partition.interleaved(w, h, world, tile)
+        else:
+            owner, loads = partition.partition(w, h, wl.gaze_xy(), wl.inner_radius, wl.outer_radius, world, tile, wl.spp, bool(wl.foveated), wl.spp_uniform)
+        r.ctx.set_tile_owner(tile, owner, rank)
         if gather == "peer":
             # the frame lives on rank 0; the other ranks map it (CUDA IPC over NVLink) and their resolve kernels store
             # their tiles straight into it -- include/fovpt.h fovpt_peer_frame_*; no collective call per frame
@@ -235,8 +242,6 @@ def native_arm(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     host_frame = torch.empty((h, w), dtype=torch.int32).pin_memory()
 
-    if wl.view_at is not None and world > 1:
-        raise RuntimeError(f"{wl.name} (moving gaze) is measured at --gpus 1 in this round: the tile partition would have to follow the gaze")
     step_no = [0]
 
     def step():
@@ -274,16 +279,23 @@ def native_arm(args):
     # the frame's own sample count (what one GPU traces for the whole frame); ranks re-trace the few splat blocks
     # that straddle their tile edges, those duplicates must not count as throughput
     if world > 1 or args.emulate_world > 1:
-        r.ctx.set_tile_owner(args.tile, None, 0)
+        r.ctx.set_tile_owner(tile, None, 0)
     r.ctx.reset_stats(); lp.frame.subframe_index = 0
     if rank == 0 or world == 1:
-        r.ctx.render_frame(lp); torch.cuda.synchronize()
-    frame_samples = float(r.ctx.stats()["samples"])
+        if wl.view_at is not None and world > 1:       # moving gaze: the count changes with the gaze point -> the K views of the timed region
+            for k in range(args.steps):
+                cam_k, gaze_k = wl.view_at(k)
+                r.setCamera(cam_k); lp.frame.c_x, lp.frame.c_y = gaze_k
+                r.ctx.render_frame(lp)
+            torch.cuda.synchronize()
+        else:
+            r.ctx.render_frame(lp); torch.cuda.synchronize()
+    frame_samples = float(r.ctx.stats()["samples"])    # (moving gaze at N>1: the total of the K timed frames)
     if world > 1:
         fs = torch.tensor([frame_samples], dtype=torch.float64, device="cuda"); dist.broadcast(fs, src=0); frame_samples = float(fs[0])
-        r.ctx.set_tile_owner(args.tile, owner, rank)
+        r.ctx.set_tile_owner(tile, owner, rank)
     elif args.emulate_world > 1:
-        r.ctx.set_tile_owner(args.tile, owner, 0)
+        r.ctx.set_tile_owner(tile, owner, 0)
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
@@ -364,6 +376,8 @@ def native_arm(args):
         traced_samples = samples                               # sum over ranks, incl. tile-edge duplicates
         if wl.view_at is None:
             samples = frame_samples * args.steps               # unique samples of the frames rendered
+        elif world > 1:                                        # moving gaze: unique samples of the K views, counted by rank 0 before timing
+            samples = frame_samples
         per_step_samples = samples / args.steps
         value = samples / (total_ms * 1e-3) / 1e6
         line = {
@@ -379,7 +393,8 @@ def native_arm(args):
             "clocks": clk, "wall_s_timed_region": t_wall, "step_ms": step_ms, "per_rank": per_rank,
         }
         if world > 1:
-            line["config"]["parallelism"] = f"{world} ranks, screen tiles of {args.tile} px weighted by foveal sample density"
+            line["config"]["parallelism"] = (f"{world} ranks, static interleaved {tile}-px screen tiles (gaze-independent)" if wl.view_at is not None
+                                             else f"{world} ranks, screen tiles of {tile} px weighted by foveal sample density")
             line["config"]["gather"] = ("peer stores into rank 0's frame over NVLink (CUDA IPC), fused into k_resolve_px; device-side arrival/release flags"
                                         if gather == "peer" else "one NCCL reduce(SUM) of zero-filled RGBA8 frames per step")
         ab = algorithmic_bytes(wl.name)

@@ -481,6 +481,42 @@ def test_tile_partition_union_is_the_frame(gpu, port):
         assert ns >= n_samples_full and ns < 1.15 * n_samples_full      # only splat blocks straddling tile edges are duplicated
 
 
+def test_interleaved_partition_follows_a_moving_gaze(gpu, port):
+    """C4 at N>1: the static interleaved partition (16-px tiles) with the gaze point moving between frames on the SAME
+    contexts -- the union of the ranks' frames stays bit-identical to the 1-rank frame for every gaze point"""
+    w, h, ri, ro, world = 320, 240, 24, 80, 4
+    sc, cam, probe = scenes.cornell_box(), scenes.CORNELL_CAMERA, scenes.constant_probe(16, 8, 2.5)
+    gazes = [(160, 120), (231, 77), (52, 190)]
+    full, o_full, _, _, _ = make_pair(gpu, port, sc, cam, w, h, probe, ri, ro)
+    o_full.close()
+    owner = partition.interleaved(w, h, world, 16)
+    ranks = []
+    for rank in range(world):
+        rr, oo, _, _, _ = make_pair(gpu, port, sc, cam, w, h, probe, ri, ro)
+        oo.close()
+        rr.ctx.set_tile_owner(16, owner, rank)
+        ranks.append(rr)
+    for k, g in enumerate(gazes):
+        for rr in [full] + ranks:
+            rr.launchParams.frame.c_x, rr.launchParams.frame.c_y = g
+            rr.launchParams.frame.subframe_index = k
+        full.render(); want = full.downloadPixels().copy(); want_acc = full.downloadAccum().copy()
+        for rr in ranks:
+            rr.render()
+        # a rank's buffers hold its own tiles only: assemble the frame from each rank's pixels (what the gather does)
+        own_px = np.repeat(np.repeat(owner, 16, axis=0), 16, axis=1)[:h, :w]
+        got = np.zeros((h, w), np.uint32); got_acc = np.zeros((h, w, 4), np.float32)
+        for rank, rr in enumerate(ranks):
+            m = own_px == rank
+            got[m] = rr.downloadPixels()[m]; got_acc[m] = rr.downloadAccum()[m]
+        written = want_acc[..., 3] != 0
+        assert (got[written] == want[written]).all(), f"gaze {g}: {(got[written] != want[written]).sum()} pixels differ"
+        assert (bits(got_acc[written]) == bits(want_acc[written])).all()
+    full.close()
+    for rr in ranks:
+        rr.close()
+
+
 def test_moving_gaze_stereo_pair(gpu, port):
     """BASELINE configs[3] scaled down: two eye cameras (+-IPD/2 along U), the gaze point moves every frame
     (PT_sv4_vmv/main.cpp:309-314 updates frame.c from the cursor each frame), no accumulation; one renderer per

@@ -222,16 +222,32 @@ def native_arm(args):
         if gather == "peer":
             # the frame lives on rank 0; the other ranks map it (CUDA IPC over NVLink) and their resolve kernels store
             # their tiles straight into it -- include/fovpt.h fovpt_peer_frame_*; no collective call per frame
+            ok, shared_ptr, why = 1, None, ""
+            hb = torch.zeros(128, dtype=torch.uint8, device="cuda")
             if rank == 0:
-                handle, shared_ptr = r.ctx.peer_frame_create(w * h, world, 0)
-                hb = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")
-            else:
-                hb = torch.empty(128, dtype=torch.uint8, device="cuda")
+                try:
+                    handle, shared_ptr = r.ctx.peer_frame_create(w * h, world, 0)
+                    hb = torch.tensor(list(handle), dtype=torch.uint8, device="cuda")
+                except RuntimeError as e:
+                    ok, why = 0, str(e)
             dist.broadcast(hb, src=0)
             if rank != 0:
-                shared_ptr = r.ctx.peer_frame_open(bytes(hb.cpu().tolist()), rank)
-            lp.frame.frame_buffer = shared_ptr
-        elif rank == 0:
+                try:
+                    shared_ptr = r.ctx.peer_frame_open(bytes(hb.cpu().tolist()), rank)
+                except RuntimeError as e:
+                    ok, why = 0, str(e)
+            okt = torch.tensor([ok], dtype=torch.int32, device="cuda")
+            dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+            if int(okt[0]) == 1:
+                lp.frame.frame_buffer = shared_ptr
+            else:
+                # CUDA IPC / peer access unavailable between these processes: every rank falls back to the NCCL reduce,
+                # and the result line says so (config.gather)
+                if why:
+                    print(f"[bench] rank {rank}: peer frame unavailable ({why}); using --gather nccl", file=sys.stderr)
+                r.ctx.peer_frame_close()
+                gather = "nccl"
+        if gather == "nccl" and rank == 0:
             # NCCL path: rank 0 renders its tiles into its own buffer; frame_t receives the sum over ranks
             frame_own = torch.zeros((h, w), dtype=torch.int32, device="cuda")
             lp.frame.frame_buffer = frame_own.data_ptr()

@@ -49,6 +49,9 @@ public:
     void setConfig(const fovpt_config& cfg);
     const fovpt_config& getConfig() const { return config; }
     fovpt_stats stats();
+    /*! the libfovpt context, for the entry points of include/fovpt.h that have no reference counterpart: the multi-GPU
+        tile ownership and shared-frame calls (fovpt_set_tile_owner, fovpt_peer_frame_*), ray queries, BVH introspection */
+    fovpt_ctx* context() const { return ctx; }
 
     // ---- public data, exactly as in the reference (SimplePathtracer.h:116,146)
     cudaStream_t stream = nullptr;

@@ -165,7 +165,9 @@ struct Traversal {
         }
     }
 
-    __device__ __forceinline__ void node_step(const DeviceBvh& bvh, const RayStack& stack)
+    // `unordered` (warp-uniform): every lane that takes this step is an any-hit ray, for which the visiting order does not
+    // matter -- skip the distance keys and the sorting network
+    __device__ __forceinline__ void node_step(const DeviceBvh& bvh, const RayStack& stack, bool unordered = false)
     {
         const uint4* np = bvh.nodes + 4 * (size_t)cur;
         const u8x A = ldg256(np), B = ldg256(np + 2);           // A = (n0, n1), B = (n2, n3)
@@ -183,7 +185,7 @@ struct Traversal {
         float tn0, tn1, tn2, tn3, tf0, tf1, tf2, tf3;
         FOVPT_SLAB(0, tn0, tf0); FOVPT_SLAB(1, tn1, tf1); FOVPT_SLAB(2, tn2, tf2); FOVPT_SLAB(3, tn3, tf3);
         const int c0 = (int)A.b.x, c1 = (int)A.b.y, c2 = (int)A.b.z, c3 = (int)A.b.w;
-        if (MODE == kAny) {
+        if (MODE == kAny || unordered) {
             // order is irrelevant for occlusion: enter the first hit child, push the others
             const bool h0 = tn0 <= tf0, h1 = tn1 <= tf1, h2 = tn2 <= tf2, h3 = tn3 <= tf3;
             int next = kDone;

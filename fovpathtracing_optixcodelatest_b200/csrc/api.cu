@@ -288,8 +288,7 @@ int run_frame(fovpt_ctx* c, const LaunchParamsBlob& lp, const std::vector<PassHo
             { Timed t(c, K_EXTEND); launch_trace(c->L, c->scene, c->ps, c->q, slot_prev, c->cfg.tmin, c->cfg.tmax, c->d_stats); }
             if (it == iters) break;                      // the last launch only drains the final shadow rays
             { Timed t(c, K_SHADE); launch_shade(c->L, F, c->scene, c->ps, c->q, slot_new, c->cfg.fast_math != 0); }
-            std::swap(c->q.cur, c->q.next);
-            { Timed t(c, 0); launch_swap(c->L, c->q.counts, slot_prev); }
+            std::swap(c->q.cur, c->q.next);                // the device-side counters are swapped by k_shade's last CTA
         }
         for (auto& ch : g) {
             Timed t(c, K_RESOLVE);

@@ -466,6 +466,17 @@ __global__ void __launch_bounds__(128, FOVPT_SHADE_BLOCKS) k_shade(FrameDev F, S
         }
         __syncthreads();                                   // s_cnt / s_base are rewritten by the next iteration
     }
+    // End of the wavefront iteration, done by the last CTA to finish instead of a launch of its own: next becomes cur,
+    // the fetch cursor rewinds, and the shadow counter that this iteration's k_trace consumed is cleared for the shading
+    // pass after next.  (Every CTA read counts[0] before it took its ticket, so nobody sees the new value.)
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&q.counts[6], 1u) == gridDim.x - 1u) {
+            __threadfence();
+            volatile uint32_t* cnt = q.counts;
+            cnt[0] = cnt[1]; cnt[1] = 0u; cnt[3] = 0u; cnt[shadow_slot == 2 ? 5 : 2] = 0u; cnt[6] = 0u;
+        }
+    }
 }
 
 // ------------------------------------------------------------------ k_resolve_li
@@ -617,13 +628,6 @@ __global__ void k_trace_query(SceneDev S, const float* __restrict__ rays, size_t
     }
 }
 
-// end of a wavefront iteration: next becomes cur, the fetch cursor rewinds, and the shadow counter that the
-// trace launch of this iteration consumed (`consumed_slot`) is cleared for the shading pass after next
-__global__ void k_swap_counts(uint32_t* counts, int consumed_slot)
-{
-    if (threadIdx.x == 0 && blockIdx.x == 0) { counts[0] = counts[1]; counts[1] = 0; counts[3] = 0; counts[consumed_slot] = 0; }
-}
-
 // ------------------------------------------------------------------ peer-frame flags (multi-GPU gather over NVLink peer memory)
 // The shared frame lives in the owner's memory; contributors store their tiles into it from k_resolve_px.  Ordering between
 // the processes is carried by 32-bit sequence numbers in the same allocation, written and polled at system scope: a
@@ -674,7 +678,6 @@ void launch_shade(const LaunchCfg& L, const FrameDev& F, const SceneDev& S, cons
     if (fast) k_shade<true><<<L.grid_shade, 128, 0, L.stream>>>(F, S, ps, q, shadow_slot);
     else k_shade<false><<<L.grid_shade, 128, 0, L.stream>>>(F, S, ps, q, shadow_slot);
 }
-void launch_swap(const LaunchCfg& L, uint32_t* counts, int consumed_slot) { k_swap_counts<<<1, 32, 0, L.stream>>>(counts, consumed_slot); }
 void launch_peer_signal(const LaunchCfg& L, uint32_t* flag, uint32_t seq) { k_peer_signal<<<1, 32, 0, L.stream>>>(flag, seq); }
 void launch_peer_wait(const LaunchCfg& L, const uint32_t* flags, int count, int skip, uint32_t seq, uint32_t* err, long long timeout_clocks)
 {

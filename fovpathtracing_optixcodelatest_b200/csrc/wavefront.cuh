@@ -94,7 +94,7 @@ struct Queues {
     RayBuf    cur, next;
     ShadowBuf shadow;
     float4*   hit;              // by slot of `cur`: t, u, v, bits(sorted triangle slot | kNoHit)
-    uint32_t* counts;   // [0] cur [1] next [2],[5] shadow (alternating per iteration) [3] fetch cursor of k_trace  (8 words)
+    uint32_t* counts;   // [0] cur [1] next [2],[5] shadow (alternating per iteration) [3] fetch cursor of k_trace [6] CTAs of k_shade done  (8 words)
 };
 
 struct DevStats {

@@ -21,7 +21,6 @@ void launch_raygen(const LaunchCfg&, const FrameDev&, int pass, unsigned row0, u
 // shadow_slot: index into Queues::counts (2 or 5, alternating per iteration) of the shadow-ray counter in use
 void launch_trace(const LaunchCfg&, const SceneDev&, const PathState&, const Queues&, int shadow_slot, float tmin, float tmax, DevStats*);
 void launch_shade(const LaunchCfg&, const FrameDev&, const SceneDev&, const PathState&, const Queues&, int shadow_slot, bool fast);
-void launch_swap(const LaunchCfg&, uint32_t* counts, int consumed_slot);
 // peer-frame flags (api.cu fovpt_peer_frame_*): raise *flag to seq / wait until flags[0..count) (except `skip`) reached seq
 void launch_peer_signal(const LaunchCfg&, uint32_t* flag, uint32_t seq);
 void launch_peer_wait(const LaunchCfg&, const uint32_t* flags, int count, int skip, uint32_t seq, uint32_t* err, long long timeout_clocks);

@@ -4,25 +4,14 @@
 // / __miss__radiance (:619-732, :253-282) are k_shade, optixTrace(OCCLUSION) + its three programs
 // (:224-300) are k_shadow.  All kernels are persistent grid-stride loops over device-resident
 // queues, so a whole frame is enqueued without a host round trip.
-#include <cooperative_groups.h>
 
 #include "shade.cuh"
 #include "wavefront.cuh"
 #include "wavefront_launch.h"
 
-namespace cg = cooperative_groups;
-
 namespace fovpt {
 
 // ------------------------------------------------------------------ small device helpers
-__device__ __forceinline__ uint32_t queue_push(uint32_t* counter)
-{
-    cg::coalesced_group g = cg::coalesced_threads();
-    uint32_t base = 0;
-    if (g.thread_rank() == 0) base = atomicAdd(counter, g.size());
-    return g.shfl(base, 0) + g.thread_rank();
-}
-
 __device__ __forceinline__ bool li_active(const FrameDev& F, const PassDev& P, unsigned lx, unsigned ly, uint32_t* px, uint32_t* py)
 {
     fx_launch_to_pixel(lx, ly, P.factor, P.factor, P.uoff_x, P.uoff_y, px, py);       // deviceProgram.cu:433
@@ -102,42 +91,66 @@ __global__ void k_raygen(FrameDev F, int pass, unsigned row0, unsigned row1, uns
                          const uint8_t* __restrict__ needed, PathState ps, Queues q, float4* __restrict__ li_backplate,
                          DevStats* __restrict__ stats)
 {
+    constexpr unsigned FULL = 0xffffffffu;
+    __shared__ uint32_t s_cnt[32];
+    __shared__ uint32_t s_base;
     const PassDev P = F.pass[pass];
     const size_t total = (size_t)(row1 - row0) * P.lw * P.spp;
+    const unsigned lane = threadIdx.x & 31u, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
     unsigned long long started = 0;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const unsigned k = (unsigned)(i % P.spp);
-        const size_t lloc = i / P.spp;
-        const unsigned lx = (unsigned)(lloc % P.lw), ly = row0 + (unsigned)(lloc / P.lw);
-        const uint32_t li = ly * P.lw + lx;
-        if (!needed[P.li_base + li]) continue;
-        uint32_t px, py;
-        fx_launch_to_pixel(lx, ly, P.factor, P.factor, P.uoff_x, P.uoff_y, &px, &py);
-        uint32_t seed = fx_tea4(ly * (unsigned)F.w + lx, P.subframe);                    // :411
-        seed = fx_seed_after(seed, k);
-        const fx_rng rng = fx_rng_init(seed);                                           // :464 (before the jitter draws)
-        const float jx = fx_rnd(&seed);                                                 // :479, x first
-        const float jy = fx_rnd(&seed);
-        const float3 dir = camera_dir(F, px, py, jx, jy);
-        const uint32_t pid = chunk_pid_base + (uint32_t)i;
-        const uint32_t slot = queue_push(&q.counts[0]);
-        q.cur.o[slot] = make_float4(F.eye[0], F.eye[1], F.eye[2], 0.f);
-        q.cur.d[slot] = make_float4(dir.x, dir.y, dir.z, 0.f);
-        q.cur.thr[slot] = make_float4(1.f, 1.f, 1.f, 1.f);                               // throughput 1, rayEta 1 (:467-468)
-        q.cur.rng[slot] = make_uint2(rng.s1, rng.s2);
-        q.cur.meta[slot] = make_uint2(pid, 0u);
-        ps.direct[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
-        ps.indirect[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
-        ps.alpha[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k == P.spp - 1) {                                                           // backplate of the LAST sample (:495)
-            const float4 bp = probe_eval(F.probe, probe_dir_to_uv(dir));
-            li_backplate[P.li_base + li] = bp;
+    // queue slots are claimed with ONE atomicAdd per CTA and iteration (a warp-level claim put ~70 k same-address atomics
+    // per frame on counts[0]); the trip count is CTA-uniform
+    for (size_t base = blockIdx.x * (size_t)blockDim.x; base < total; base += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = base + threadIdx.x;
+        unsigned k = 0, lx = 0, ly = 0; uint32_t li = 0;
+        bool active = i < total;
+        if (active) {
+            k = (unsigned)(i % P.spp);
+            const size_t lloc = i / P.spp;
+            lx = (unsigned)(lloc % P.lw); ly = row0 + (unsigned)(lloc / P.lw);
+            li = ly * P.lw + lx;
+            active = needed[P.li_base + li] != 0;
         }
-        ++started;
+        const unsigned m = __ballot_sync(FULL, active);
+        if (lane == 0) s_cnt[wib] = __popc(m);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t tot = 0;
+            for (unsigned w = 0; w < nw; ++w) tot += s_cnt[w];
+            s_base = tot ? atomicAdd(&q.counts[0], tot) : 0u;
+        }
+        __syncthreads();
+        if (active) {
+            uint32_t slot = s_base + __popc(m & ((1u << lane) - 1u));
+            for (unsigned w = 0; w < wib; ++w) slot += s_cnt[w];
+            uint32_t px, py;
+            fx_launch_to_pixel(lx, ly, P.factor, P.factor, P.uoff_x, P.uoff_y, &px, &py);
+            uint32_t seed = fx_tea4(ly * (unsigned)F.w + lx, P.subframe);                    // :411
+            seed = fx_seed_after(seed, k);
+            const fx_rng rng = fx_rng_init(seed);                                           // :464 (before the jitter draws)
+            const float jx = fx_rnd(&seed);                                                 // :479, x first
+            const float jy = fx_rnd(&seed);
+            const float3 dir = camera_dir(F, px, py, jx, jy);
+            const uint32_t pid = chunk_pid_base + (uint32_t)i;
+            q.cur.o[slot] = make_float4(F.eye[0], F.eye[1], F.eye[2], 0.f);
+            q.cur.d[slot] = make_float4(dir.x, dir.y, dir.z, 0.f);
+            q.cur.thr[slot] = make_float4(1.f, 1.f, 1.f, 1.f);                               // throughput 1, rayEta 1 (:467-468)
+            q.cur.rng[slot] = make_uint2(rng.s1, rng.s2);
+            q.cur.meta[slot] = make_uint2(pid, 0u);
+            ps.direct[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
+            ps.indirect[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
+            ps.alpha[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k == P.spp - 1) {                                                           // backplate of the LAST sample (:495)
+                const float4 bp = probe_eval(F.probe, probe_dir_to_uv(dir));
+                li_backplate[P.li_base + li] = bp;
+            }
+            ++started;
+        }
+        __syncthreads();                                   // s_cnt / s_base are rewritten by the next iteration
     }
-    // block-level count of started samples
-    for (int o = 16; o > 0; o >>= 1) started += __shfl_xor_sync(0xffffffffu, started, o);
-    if ((threadIdx.x & 31) == 0 && started) atomicAdd(&stats->samples, started);
+    // warp-level count of started samples
+    for (int o = 16; o > 0; o >>= 1) started += __shfl_xor_sync(FULL, started, o);
+    if (lane == 0 && started) atomicAdd(&stats->samples, started);
 }
 
 // the tail of SampleLights / SampleShadow once the occlusion bit is known (deviceProgram.cu:323-341, :367-384)

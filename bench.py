@@ -13,7 +13,8 @@ are K of the frames that make up the quoted 256 foveal spp.
 value   : Msamples/s with scene, BVH, probe and frame buffers resident in HBM (device-timed).
 e2e     : the same frames through the reference-facing API -- SampleRenderer.render() then
           downloadPixels() into host memory: launch parameters cross host->device every frame and
-          the RGBA8 frame comes back device->host inside the timed region.
+          the RGBA8 frame comes back device->host inside the timed region (per-kernel statistics off,
+          as in a host that only renders; `value` is measured with them on, ~1 % of a frame).
 roofline: traversal kernel k_trace against the HBM roofline, algorithmic bytes per ray from the
           CPU oracle's canonical BVH (profiles/algorithmic_bytes.json).
 cpu_baseline / --impl reference: the CPU checker (oracle/) on the same workload on host cores.
@@ -357,7 +358,10 @@ def native_arm(args):
         per_rank = None
     clk = clocks.stop() if clocks else None
 
-    # ---- end-to-end region: public API with host buffers (params in, pixels out) every step
+    # ---- end-to-end region: public API with host buffers (params in, pixels out) every step.  A host that renders and
+    # downloads does not read per-kernel statistics, so they are off here (include/fovpt.h fovpt_set_kernel_timing; they
+    # were on in the device-timed region above because the roofline needs k_trace's time)
+    r.ctx.set_kernel_timing(False)
     lp.frame.subframe_index = 0
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -22,7 +22,7 @@ struct HostMesh {
 };
 struct HostTex { int w, h; std::vector<uint32_t> px; };
 
-struct EventPair { cudaEvent_t a, b; int kind; };
+struct Mark { cudaEvent_t ev; int kind; };      // start of a timed interval on the context stream; it ends at the next mark
 
 }  // namespace
 
@@ -82,8 +82,9 @@ struct fovpt_ctx {
     uint64_t launches = 0, frames = 0;
     float build_ms = 0.f;
     cudaEvent_t ev_frame0 = nullptr, ev_frame1 = nullptr;
-    std::vector<EventPair> ev_pool; size_t ev_used = 0;
+    std::vector<Mark> marks; size_t marks_used = 0;
     float last_ms[6] = {0, 0, 0, 0, 0, 0};     // frame, raygen, extend, shade, shadow, resolve
+    bool kernel_timing = true;                  // per-kernel statistics (last_*_ms) through chained CUDA events: fovpt_set_kernel_timing
     bool frame_timed = false;
 };
 
@@ -100,19 +101,17 @@ int cuda_fail(fovpt_ctx* c, cudaError_t e, const char* what)
 
 template <typename T> cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, (n ? n : 1) * sizeof(T)); }
 
-struct Timed {       // records a CUDA-event pair around one kernel launch on the context stream
-    fovpt_ctx* c; EventPair* e;
-    Timed(fovpt_ctx* c_, int kind) : c(c_), e(nullptr)
-    {
-        if (c->ev_used == c->ev_pool.size()) {
-            EventPair p; cudaEventCreate(&p.a); cudaEventCreate(&p.b); p.kind = 0; c->ev_pool.push_back(p);
-        }
-        e = &c->ev_pool[c->ev_used++];
-        e->kind = kind;
-        cudaEventRecord(e->a, c->stream);
-    }
-    ~Timed() { cudaEventRecord(e->b, c->stream); c->launches++; }
-};
+// Per-kernel times come from ONE event between consecutive kernels (an interval runs from its mark to the next mark or to the
+// end of the frame, so it includes the launch gap behind the kernel): 22 event records per depth-8 frame.  A pair around every
+// launch (54 records) cost 127 us of a 4.7 ms C3 frame and 140 us of a 1.5 ms 1/8-frame share.
+void mark(fovpt_ctx* c, int kind)
+{
+    if (!c->kernel_timing) return;
+    if (c->marks_used == c->marks.size()) { Mark m; cudaEventCreate(&m.ev); m.kind = 0; c->marks.push_back(m); }
+    Mark& m = c->marks[c->marks_used++];
+    m.kind = kind;
+    cudaEventRecord(m.ev, c->stream);
+}
 
 void free_scene(fovpt_ctx* c)
 {
@@ -224,7 +223,7 @@ int run_frame(fovpt_ctx* c, const LaunchParamsBlob& lp, const std::vector<PassHo
     const size_t npix = (size_t)F.w * F.h;
     if (ensure_li(c, total_li) || ensure_px(c, npix)) return 1;
 
-    c->ev_used = 0;
+    c->marks_used = 0;
     cudaEventRecord(c->ev_frame0, c->stream);
 
     // owner map: recomputed only when the frame geometry / gaze / partition changes
@@ -242,7 +241,8 @@ int run_frame(fovpt_ctx* c, const LaunchParamsBlob& lp, const std::vector<PassHo
     }
     if (key != c->owner_key) {
         CU(cudaMemsetAsync(c->needed, 0, total_li, c->stream));
-        { Timed t(c, K_RESOLVE); launch_owner_map(c->L, F, c->owner_map, c->needed); }
+        mark(c, K_RESOLVE);
+        launch_owner_map(c->L, F, c->owner_map, c->needed); c->launches++;
         c->owner_key = key;
     }
 
@@ -276,29 +276,33 @@ int run_frame(fovpt_ctx* c, const LaunchParamsBlob& lp, const std::vector<PassHo
 
     const int iters = c->cfg.max_depth + 1 + (c->scene.any_catcher ? 4 : 0);
     for (auto& g : groups) {
+        mark(c, K_RAYGEN);
         CU(cudaMemsetAsync(c->q.counts, 0, 8 * sizeof(uint32_t), c->stream));
         for (auto& ch : g) {
-            Timed t(c, K_RAYGEN);
             launch_raygen(c->L, F, ch.pass, ch.row0, ch.row1, ch.pid_base, c->needed, c->ps, c->q, c->li_backplate, c->d_stats);
+            c->launches++;
         }
         // iteration i: k_trace extends the radiance rays of bounce i and resolves the shadow rays that
         // k_shade(i-1) emitted (counter slot alternates 2 / 5), k_shade(i) consumes the hits.
         for (int it = 0; it <= iters; ++it) {
             const int slot_prev = (it & 1) ? 2 : 5, slot_new = (it & 1) ? 5 : 2;
-            { Timed t(c, K_EXTEND); launch_trace(c->L, c->scene, c->ps, c->q, slot_prev, c->cfg.tmin, c->cfg.tmax, c->d_stats); }
+            mark(c, K_EXTEND);
+            launch_trace(c->L, c->scene, c->ps, c->q, slot_prev, c->cfg.tmin, c->cfg.tmax, c->d_stats); c->launches++;
             if (it == iters) break;                      // the last launch only drains the final shadow rays
-            { Timed t(c, K_SHADE); launch_shade(c->L, F, c->scene, c->ps, c->q, slot_new, c->cfg.fast_math != 0); }
+            mark(c, K_SHADE);
+            launch_shade(c->L, F, c->scene, c->ps, c->q, slot_new, c->cfg.fast_math != 0); c->launches++;
             std::swap(c->q.cur, c->q.next);                // the device-side counters are swapped by k_shade's last CTA
         }
+        mark(c, K_RESOLVE);
         for (auto& ch : g) {
-            Timed t(c, K_RESOLVE);
             launch_resolve_li(c->L, F, ch.pass, ch.row0, ch.row1, ch.pid_base, c->needed, c->ps, c->li_backplate, c->li_color);
+            c->launches++;
         }
     }
     // a contributor to a shared frame stores its pixels into the owner's memory: not before the owner released the last frame
     if (c->peer.open && !c->peer.owner)
         launch_peer_wait(c->L, c->peer.flags + kPeerRelease, 1, -1, c->peer.seq, c->peer.d_err, c->peer.timeout_clocks);
-    { Timed t(c, K_RESOLVE); launch_resolve_px(c->L, F, c->owner_map, c->li_color, c->needed, c->cfg.fast_math != 0); }
+    launch_resolve_px(c->L, F, c->owner_map, c->li_color, c->needed, c->cfg.fast_math != 0); c->launches++;
     cudaEventRecord(c->ev_frame1, c->stream);
     c->frame_timed = true;
     c->frames++;
@@ -315,11 +319,11 @@ void collect_times(fovpt_ctx* c)
     cudaEventElapsedTime(&ms, c->ev_frame0, c->ev_frame1);
     for (int i = 0; i < 6; ++i) c->last_ms[i] = 0.f;
     c->last_ms[0] = ms;
-    for (size_t i = 0; i < c->ev_used; ++i) {
-        EventPair& e = c->ev_pool[i];
-        if (e.kind <= 0 || e.kind > 5) continue;
+    for (size_t i = 0; i < c->marks_used; ++i) {
+        const Mark& m = c->marks[i];
+        if (m.kind <= 0 || m.kind > 5) continue;
         float t = 0.f;
-        if (cudaEventElapsedTime(&t, e.a, e.b) == cudaSuccess) c->last_ms[e.kind] += t;
+        if (cudaEventElapsedTime(&t, m.ev, i + 1 < c->marks_used ? c->marks[i + 1].ev : c->ev_frame1) == cudaSuccess) c->last_ms[m.kind] += t;
     }
     c->frame_timed = false;
 }
@@ -376,6 +380,7 @@ int fovpt_create(fovpt_ctx** out, int device, void* stream)
     cudaFree(0);
     if (stream) c->stream = (cudaStream_t)stream;
     else { if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return 4; } c->own_stream = true; }
+    if (const char* e = getenv("FOVPT_KERNEL_TIMING")) c->kernel_timing = atoi(e) != 0;
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, device);
     c->n_sm = prop.multiProcessorCount;
@@ -403,7 +408,7 @@ int fovpt_destroy(fovpt_ctx* c)
     cudaFree(c->fb_accum); cudaFree(c->fb_frame); cudaFree(c->li_backplate); cudaFree(c->li_color); cudaFree(c->needed);
     cudaFree(c->owner_map); cudaFree(c->q.counts); cudaFree(c->d_stats); cudaFree(c->d_tile_owner);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
-    for (auto& e : c->ev_pool) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    for (auto& m : c->marks) cudaEventDestroy(m.ev);
     cudaEventDestroy(c->ev_frame0); cudaEventDestroy(c->ev_frame1);
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -422,6 +427,12 @@ int fovpt_set_config(fovpt_ctx* c, const fovpt_config* k)
     if (k->filter < 0 || k->filter > 1) return fail(c, "filter must be 0 (box) or 1 (bilinear)");
     if (!(k->tmin >= 0.f) || !(k->tmax > k->tmin)) return fail(c, "need 0 <= tmin < tmax");
     c->cfg = *k;
+    return 0;
+}
+int fovpt_set_kernel_timing(fovpt_ctx* c, int on)
+{
+    if (!c) return 1;
+    c->kernel_timing = on != 0;
     return 0;
 }
 int fovpt_get_config(fovpt_ctx* c, fovpt_config* k) { if (!c || !k) return 1; *k = c->cfg; return 0; }

@@ -45,7 +45,7 @@ EXPORTS = [
     "fovpt_download_accum", "fovpt_trace", "fovpt_primary_hits", "fovpt_set_tile_owner", "fovpt_get_stats",
     "fovpt_reset_stats", "fovpt_bvh_info", "fovpt_bvh_layout", "fovpt_bvh_read",
     "fovpt_peer_frame_create", "fovpt_peer_frame_open", "fovpt_peer_frame_signal", "fovpt_peer_frame_wait",
-    "fovpt_peer_frame_release", "fovpt_peer_frame_close",
+    "fovpt_peer_frame_release", "fovpt_peer_frame_close", "fovpt_set_kernel_timing",
 ]
 
 _lib = None
@@ -88,6 +88,7 @@ def load_library():
     L.fovpt_bvh_info.argtypes = [vp, u64p, u64p]
     L.fovpt_bvh_layout.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
     L.fovpt_bvh_read.argtypes = [vp, vp, vp]
+    L.fovpt_set_kernel_timing.argtypes = [vp, i32]
     L.fovpt_peer_frame_create.argtypes = [vp, C.c_size_t, i32, i32, vp, C.POINTER(vp)]
     L.fovpt_peer_frame_open.argtypes = [vp, vp, i32, C.POINTER(vp)]
     for n in ("signal", "wait", "release", "close"):
@@ -259,6 +260,9 @@ class Context:
 
     def peer_frame_close(self):
         self._chk(self.L.fovpt_peer_frame_close(self.h))
+
+    def set_kernel_timing(self, on: bool):
+        self._chk(self.L.fovpt_set_kernel_timing(self.h, 1 if on else 0))
 
     def stats(self) -> dict:
         s = Stats()

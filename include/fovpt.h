@@ -142,6 +142,9 @@ int fovpt_peer_frame_wait(fovpt_ctx*);
 int fovpt_peer_frame_release(fovpt_ctx*);
 int fovpt_peer_frame_close(fovpt_ctx*);
 
+/* per-kernel statistics (fovpt_stats.last_extend_ms ... last_resolve_ms) cost one CUDA event record between consecutive
+ * kernels (~1 % of a C3 frame); on by default, a host that does not read them switches them off. */
+int fovpt_set_kernel_timing(fovpt_ctx*, int on);
 int fovpt_get_stats(fovpt_ctx*, fovpt_stats*);
 int fovpt_reset_stats(fovpt_ctx*);
 /* BVH introspection for validity tests: branching factor (8 or 4) and node size in bytes (96 / 64, layout in

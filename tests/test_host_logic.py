@@ -126,3 +126,27 @@ def test_interleaved_partition_balances_wherever_the_gaze_is(n):
         gaze = (int(1080 + 600 * math.cos(0.05 * k)), int(1080 + 600 * math.sin(0.05 * k)))
         loads = partition.loads_of(owner, 2160, 2160, gaze, 148, 482, n, 16)
         assert loads.max() / loads.mean() < 1.025, (k, loads)
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py contract: ONE JSON line on stdout (library banners go to stderr); the reference arm runs the CPU checker on
+    rank 0 only, other ranks exit 0 without output"""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--workload", "c1", "--steps", "1", "--warmup", "0"]
+    env = dict(os.environ); env.pop("RANK", None)
+    p = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, p.stdout
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] in ("port", "reference")
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    env["RANK"] = "1"
+    p = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=300)
+    assert p.returncode == 0 and p.stdout.strip() == ""

@@ -28,6 +28,15 @@
 #include <stdexcept>
 #include <tuple>
 
+// ---- ownership (the containers hold raw pointers, as the reference's callers expect)
+Texture::~Texture() { delete[] pixel; }
+
+Model::~Model()
+{
+    for (TriangleMesh* m : meshes) delete m;
+    for (Texture* t : textures) delete t;
+}
+
 namespace {
 
 struct MtlEntry {

@@ -1,40 +1,42 @@
-// Model.h -- scene container and OBJ loading; same types and free functions as the reference's
-// PT_sv5_/Model.h:10-47 (TriangleMesh, Texture, Model, loadOBJ, addBox).
+// Model.h -- host-side scene container of the drop-in: the type and member NAMES are the reference's
+// (PT_sv5_/Model.h:10-47: TriangleMesh, Texture, Model, loadOBJ, addBox) because main.cpp and
+// SampleRenderer address them by name; everything else (layout order, ownership code in Model.cpp,
+// the OBJ/MTL reader) is this repository's.
 #pragma once
+#include <cstdint>
 #include <string>
 #include <vector>
 
 #include "Material.h"
 
+// One (shape, material) group of an OBJ file -- what becomes one mesh of fovpt_scene_add_mesh.
 struct TriangleMesh {
+    Material material;                  // Disney parameters; loadOBJ sets color <- Kd and emission <- Ke only
+    int diffuseTextureID = 1;           // index into Model::textures or -1; 1 is the reference's odd default
+                                        // (Model.h:19), loadOBJ always overwrites it
+    std::vector<uint3>  index;          // triangles, indices into `vertex`
     std::vector<float3> vertex;
-    std::vector<float3> normal;
-    std::vector<float2> texcoord;
-    std::vector<uint3>  index;
-    Material            material;
-    int                 diffuseTextureID{1};     // reference default (Model.h:19); loadOBJ always overwrites it
+    std::vector<float3> normal;         // carried for API compatibility; shading uses geometric normals
+    std::vector<float2> texcoord;       // empty or one per vertex
 };
 
+// RGBA8 image, row 0 at the bottom (the loader flips, as reference Model.cpp:113-124 does).
 struct Texture {
-    ~Texture() { delete[] pixel; }
-    uint32_t* pixel{nullptr};                    // RGBA8, row 0 = bottom (loadTexture flips, Model.cpp:113-124)
-    int2      resolution{-1, -1};
+    ~Texture();
+    int2      resolution = {-1, -1};
+    uint32_t* pixel = nullptr;          // new[]-allocated, owned
 };
 
+// Owns its meshes and textures (raw pointers, as the reference's callers expect).
 struct Model {
-    ~Model()
-    {
-        for (auto mesh : meshes) delete mesh;
-        for (auto texture : textures) delete texture;
-    }
-    std::vector<TriangleMesh*> meshes;
+    ~Model();
     std::vector<Texture*>      textures;
+    std::vector<TriangleMesh*> meshes;
 };
 
-// One TriangleMesh per (shape, material) in shape order x ascending material id (Model.cpp:167-206);
-// Kd -> material.color, Ke -> material.emission, map_Kd -> diffuseTextureID (-1 if none).
-// Throws std::runtime_error when the file cannot be read (Model.cpp:160).
+// Meshes come out in shape order x ascending material id (reference Model.cpp:167-206); map_Kd ->
+// diffuseTextureID.  Throws std::runtime_error if the file cannot be read (Model.cpp:160).
 Model* loadOBJ(const std::string& objFile);
 
-// axis-aligned box: 8 vertices, 12 triangles (Model.cpp:219-291)
+// Appends an axis-aligned box (8 vertices, 12 triangles in the reference's order, Model.cpp:219-291).
 void addBox(Model* model, Material& mat, const float3& pos, const float3& extend);

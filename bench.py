@@ -152,19 +152,33 @@ def reference_arm(args):
         "impl": "reference", "metric": "Msamples/s (1080p foveated path tracing)", "value": msamples, "unit": "Msamples/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(wl),
+        "config": workload_config(wl, subframes_per_step(wl, args.subframes)),
         "rays_per_s": (cnt["radiance_rays"] + cnt["shadow_rays"]) / dt,
         "cpu_baseline": {"value": msamples, "unit": "Msamples/s", "cores": threads, "kind": kind,
-                         "sample": f"{args.steps} full frame(s) of {wl.name} ({cnt['samples']} samples) on {threads} host threads"},
+                         "sample": f"bounded sample: each step = ONE full subframe of {wl.name} (the GPU arm's step is "
+                                   f"{subframes_per_step(wl, args.subframes)} of them); {args.steps} step(s), {cnt['samples']} samples on {threads} host threads"},
         "e2e": {"value": msamples, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
 
 
-def workload_config(wl):
+def subframes_per_step(wl, requested=0):
+    """how many accumulated subframes one step renders (as ONE wavefront, fovpt_render_frames): all the subframes of the
+    quoted spp when they fit the path budget (C2: 2, C3: 8), one otherwise (C5: a subframe is 265 M samples already)"""
+    if requested > 0:
+        return requested
+    if not wl.accumulate or wl.view_at is not None:
+        return 1
+    passes = [(wl.width // 4) * (wl.height // 4) * wl.spp[0], (wl.outer_radius + 2) ** 2 * wl.spp[1], (2 * (wl.inner_radius + 1)) ** 2 * wl.spp[2]] \
+        if wl.foveated else [wl.width * wl.height * wl.spp_uniform]
+    return max(1, min(wl.frames, (48 << 20) // max(1, sum(passes))))
+
+
+def workload_config(wl, subframes=None):
     return {"workload": f"{wl.name}: {wl.description}", "scene_tris": wl.scene().n_tris, "width": wl.width, "height": wl.height,
             "gaze": list(wl.gaze_xy()), "radii": [wl.inner_radius, wl.outer_radius], "spp_per_frame": list(wl.spp),
             "max_depth": wl.max_depth, "frames_for_quoted_spp": wl.frames,
+            "subframes_per_step": subframes if subframes is not None else subframes_per_step(wl),
             "l2": "256 MiB memset between steps, outside the per-step CUDA-event pairs"}
 
 
@@ -185,6 +199,7 @@ def native_arm(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     wl = make_workload(args.workload)
     cfg = wl.apply(native.default_config())
+    S = subframes_per_step(wl, args.subframes)
 
     # the product renderer runs on a dedicated torch stream made current, so that torch's CUDA events and
     # NCCL collectives order with libfovpt's kernels (a NULL handle would make libfovpt create its own stream)
@@ -265,7 +280,7 @@ def native_arm(args):
         if wl.view_at is not None:                     # stereo / moving gaze: camera and gaze point change every step (host-side only)
             cam_k, gaze_k = wl.view_at(step_no[0]); step_no[0] += 1
             r.setCamera(cam_k); lp.frame.c_x, lp.frame.c_y = gaze_k
-        r.ctx.render_frame(lp)
+        r.ctx.render_frames(lp, S)
         gather_frame()
 
     def gather_frame(consume=None):
@@ -373,10 +388,10 @@ def native_arm(args):
             cam_k, gaze_k = wl.view_at(step_no[0]); step_no[0] += 1
             r.setCamera(cam_k); lp.frame.c_x, lp.frame.c_y = gaze_k
         if world == 1:
-            r.render()                                 # SampleRenderer::render(): LaunchParams host -> device, 3 passes, sync
+            r.renderSubframes(S)                       # SampleRenderer::render() x S as one submission: LaunchParams host -> device, 3 passes per subframe, sync
             r.downloadPixels(host_np)                  # SampleRenderer::downloadPixels(): RGBA8 frame device -> host, blocking
         else:
-            r.render_async()
+            r.renderSubframes(S, sync=False)
             if gather == "peer":
                 gather_frame(lambda: r.downloadPixels(host_np))          # blocking D2H of the shared frame on rank 0
             else:
@@ -395,7 +410,7 @@ def native_arm(args):
         hbm, peak_src = load_peaks()
         traced_samples = samples                               # sum over ranks, incl. tile-edge duplicates
         if wl.view_at is None:
-            samples = frame_samples * args.steps               # unique samples of the frames rendered
+            samples = frame_samples * S * args.steps           # unique samples of the subframes rendered
         elif world > 1:                                        # moving gaze: unique samples of the K views, counted by rank 0 before timing
             samples = frame_samples
         per_step_samples = samples / args.steps
@@ -404,7 +419,7 @@ def native_arm(args):
             "metric": "Msamples/s (1080p foveated path tracing)", "value": value, "unit": "Msamples/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(wl),
+            "config": workload_config(wl, S),
             "samples_per_step": per_step_samples, "traced_samples_per_step": traced_samples / args.steps,
             "rays_per_s": (rad + shw) / (total_ms * 1e-3), "radiance_rays_per_step": rad / args.steps, "shadow_rays_per_step": shw / args.steps,
             "gpu_launches": int(launches),
@@ -423,7 +438,7 @@ def native_arm(args):
             line["kernel_ms_per_step"] = {"k_trace": ext_ms / args.steps, "k_shade": shade_ms / args.steps}
             if ab:
                 b_closest, b_any = ab["closest"]["bytes_per_ray"], ab["any"]["bytes_per_ray"]
-                n_trace_launches = args.steps * (wl.max_depth + 2)
+                n_trace_launches = int(st["trace_launches"]) if world == 1 else args.steps * (wl.max_depth + 2)
                 alg_bytes = (rad / world) * b_closest + (shw / world) * b_any              # per GPU, whole timed region
                 achieved = alg_bytes / (ext_ms * 1e-3) / 1e9
                 line["roofline"] = {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": hbm, "unit": "GB/s",
@@ -455,6 +470,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--subframes", type=int, default=0,
+                    help="accumulated subframes per step, traced as one wavefront (default: all subframes of the workload's quoted spp "
+                         "that fit the path budget: C2 2, C3 8, C5 1)")
     ap.add_argument("--tile", type=int, default=32, help="screen tile edge of the multi-GPU partition")
     ap.add_argument("--gather", choices=("peer", "nccl"), default="peer",
                     help="N>1: how the ranks' tiles reach rank 0 -- peer: stores into rank 0's frame over NVLink peer memory, fused into "

@@ -8,6 +8,8 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>      // header-only; ranges are no-ops unless a profiler injects the NVTX library
+
 #include "../../include/fovpt.h"
 #include "bvh_build.h"
 #include "wavefront_launch.h"
@@ -61,7 +63,7 @@ struct fovpt_ctx {
     size_t path_cap = 0;
     PathState ps{};
     Queues q{};
-    size_t li_cap = 0; float4* li_backplate = nullptr; float4* li_color = nullptr; uint8_t* needed = nullptr;
+    size_t li_cap = 0, needed_cap = 0; float4* li_backplate = nullptr; float4* li_color = nullptr; uint8_t* needed = nullptr;
     size_t px_cap = 0; uint32_t* owner_map = nullptr;
     std::vector<unsigned char> owner_key;      // what the cached owner map was computed for
     DevStats* d_stats = nullptr;
@@ -71,15 +73,17 @@ struct fovpt_ctx {
     uint8_t* d_tile_owner = nullptr; int tile_size = 0, tiles_x = 0, tiles_y = 0, rank = 0;
 
     // shared frame of a multi-GPU job (fovpt_peer_frame_*): `base` is the owner's allocation (mapped through CUDA IPC on
-    // the contributors) = RGBA8 frame, then kPeerFlagWords u32: arrival[rank] | release | owner-side error
+    // the contributors) = RGBA8 frame, then kPeerFlagWords u32: arrival[rank] | release | owner-side error, then the float4 accumulation buffer
     struct PeerFrame {
         unsigned char* base = nullptr; uint32_t* flags = nullptr; uint32_t* d_err = nullptr;
+        float4* accum = nullptr;            // shared accumulation buffer behind the flags (every rank mirrors its pixels into it)
+        bool mirror_accum = true;
         bool open = false, owner = false; int world = 0, owner_rank = 0, rank = 0; uint32_t seq = 0; size_t npix = 0;
         long long timeout_clocks = 0;
     } peer;
 
     // stats
-    uint64_t launches = 0, frames = 0;
+    uint64_t launches = 0, frames = 0, trace_launches = 0;
     float build_ms = 0.f;
     cudaEvent_t ev_frame0 = nullptr, ev_frame1 = nullptr;
     std::vector<Mark> marks; size_t marks_used = 0;
@@ -146,14 +150,25 @@ int ensure_paths(fovpt_ctx* c, size_t n)
     return 0;
 }
 
-int ensure_li(fovpt_ctx* c, size_t n)
+// n: entries of the per-(layer, launch index) buffers; n_needed: launch indices of one layer (the `needed` bytes)
+int ensure_li(fovpt_ctx* c, size_t n, size_t n_needed)
 {
-    if (n <= c->li_cap) return 0;
-    cudaFree(c->li_backplate); cudaFree(c->li_color); cudaFree(c->needed);
-    CU(dmalloc(&c->li_backplate, n)); CU(dmalloc(&c->li_color, n)); CU(dmalloc(&c->needed, n));
-    c->li_cap = n; c->owner_key.clear();
+    if (n > c->li_cap) {
+        cudaFree(c->li_backplate); cudaFree(c->li_color);
+        c->li_backplate = nullptr; c->li_color = nullptr; c->li_cap = 0;
+        CU(dmalloc(&c->li_backplate, n)); CU(dmalloc(&c->li_color, n));
+        c->li_cap = n;
+    }
+    if (n_needed > c->needed_cap) {
+        cudaFree(c->needed); c->needed = nullptr; c->needed_cap = 0;
+        CU(dmalloc(&c->needed, n_needed));
+        c->needed_cap = n_needed; c->owner_key.clear();
+    }
     return 0;
 }
+
+void nvtx_push(const char* name) { nvtxRangePushA(name); }
+void nvtx_pop() { nvtxRangePop(); }
 
 int ensure_px(fovpt_ctx* c, size_t n)
 {
@@ -175,7 +190,7 @@ int ensure_pinned(fovpt_ctx* c, size_t n)
 }
 
 // One pass of the frame schedule, host side (SimplePathtracer.cpp:137-209)
-struct PassHost { unsigned lw, lh, factor; int fill; float r_inner, r_outer; unsigned spp, off_x, off_y, redraw, subframe; };
+struct PassHost { unsigned lw, lh, factor; int fill; float r_inner, r_outer; unsigned spp, off_x, off_y, redraw, subframe, sub_step; };
 
 void fill_frame(fovpt_ctx* c, const LaunchParamsBlob& lp, const std::vector<PassHost>& passes, FrameDev* F, size_t* total_li)
 {
@@ -193,20 +208,32 @@ void fill_frame(fovpt_ctx* c, const LaunchParamsBlob& lp, const std::vector<Pass
     for (size_t p = 0; p < passes.size(); ++p) {
         const PassHost& h = passes[p];
         PassDev& d = F->pass[p];
-        d.lw = h.lw; d.lh = h.lh; d.factor = h.factor; d.fill = (unsigned)h.fill; d.spp = h.spp; d.redraw = h.redraw; d.subframe = h.subframe;
+        d.lw = h.lw; d.lh = h.lh; d.factor = h.factor; d.fill = (unsigned)h.fill; d.spp = h.spp; d.redraw = h.redraw; d.subframe = h.subframe; d.sub_step = h.sub_step;
         d.uoff_x = h.off_x; d.uoff_y = h.off_y; d.off_x = (int)h.off_x; d.off_y = (int)h.off_y;
         d.r_inner = h.r_inner; d.r_outer = h.r_outer;
         d.pid_base = 0; d.li_base = (unsigned)li;
         li += (size_t)h.lw * h.lh;
     }
     *total_li = li;
+    F->nsub = 1; F->li_total = (unsigned)li;
     F->max_depth = c->cfg.max_depth; F->tmin = c->cfg.tmin; F->tmax = c->cfg.tmax; F->exposure = c->cfg.exposure;
     F->accumulate = c->cfg.accumulate; F->skip_wasted = c->cfg.skip_wasted_trace; F->filter = c->cfg.filter;
     F->tile_owner = c->d_tile_owner; F->tile_size = c->tile_size; F->tiles_x = c->tiles_x; F->tiles_y = c->tiles_y; F->rank = c->rank;
 }
 
-// runs the passes of one frame through the wavefront; asynchronous.
-int run_frame(fovpt_ctx* c, const LaunchParamsBlob& lp, const std::vector<PassHost>& passes)
+constexpr size_t kPathBudget = (size_t)48 << 20;      // at most this many paths in flight
+
+size_t paths_per_layer(const std::vector<PassHost>& passes)
+{
+    size_t n = 0;
+    for (auto& p : passes) n += (size_t)p.lw * p.lh * p.spp;
+    return n;
+}
+
+// Runs `nsub` accumulated subframes of the passes through ONE wavefront (layer s of pass p is seeded with
+// subframe + s * sub_step); asynchronous.  nsub > 1 requires nsub * paths_per_layer <= kPathBudget (fovpt_render_frames
+// splits longer batches); a single layer larger than the budget is cut into row chunks as before.
+int run_frame(fovpt_ctx* c, const LaunchParamsBlob& lp, const std::vector<PassHost>& passes, int nsub = 1)
 {
     if (!c->committed) return fail(c, "scene not committed");
     if (!lp.probe.data) return fail(c, "LaunchParams.probe is empty (call fovpt_probe_upload / setProbe first)");
@@ -217,12 +244,20 @@ int run_frame(fovpt_ctx* c, const LaunchParamsBlob& lp, const std::vector<PassHo
         if ((size_t)p.lw * p.lh >= (1u << 28)) return fail(c, "launch too large");
         if (p.factor == 0 || p.fill <= 0) return fail(c, "factor / fillSize must be positive");
     }
+    if (nsub < 1 || (nsub > 1 && (size_t)nsub * paths_per_layer(passes) > kPathBudget)) return fail(c, "subframe batch exceeds the path budget");
     cudaSetDevice(c->device);
     FrameDev F; size_t total_li = 0;
     fill_frame(c, lp, passes, &F, &total_li);
+    F.nsub = nsub;
     const size_t npix = (size_t)F.w * F.h;
-    if (ensure_li(c, total_li) || ensure_px(c, npix)) return 1;
+    // a tile table / shared frame that does not cover the frame would be read / written out of bounds by the kernels
+    if (F.tile_owner && ((size_t)F.tiles_x * F.tile_size < (size_t)F.w || (size_t)F.tiles_y * F.tile_size < (size_t)F.h))
+        return fail(c, "tile owner table does not cover the frame (fovpt_set_tile_owner after a resize?)");
+    if (c->peer.open && (unsigned char*)F.frame == c->peer.base && c->peer.npix < npix)
+        return fail(c, "the shared peer frame is smaller than the frame being rendered");
+    if (ensure_li(c, total_li * (size_t)nsub, total_li) || ensure_px(c, npix)) return 1;
 
+    nvtx_push("fovpt frame");
     c->marks_used = 0;
     cudaEventRecord(c->ev_frame0, c->stream);
 
@@ -233,7 +268,7 @@ int run_frame(fovpt_ctx* c, const LaunchParamsBlob& lp, const std::vector<PassHo
         int head[4] = {F.w, F.h, (int)F.cx, (int)F.cy};
         memcpy(k, head, sizeof(head)); k += sizeof(head);
         PassDev geo[kMaxPasses]; memset(geo, 0, sizeof(geo));
-        for (int p = 0; p < F.npass; ++p) { geo[p] = F.pass[p]; geo[p].spp = 0; geo[p].redraw = 0; geo[p].subframe = 0; }
+        for (int p = 0; p < F.npass; ++p) { geo[p] = F.pass[p]; geo[p].spp = 0; geo[p].redraw = 0; geo[p].subframe = 0; geo[p].sub_step = 0; }
         memcpy(k, geo, sizeof(geo)); k += sizeof(geo);
         const void* to = F.tile_owner; memcpy(k, &to, sizeof(void*)); k += sizeof(void*);
         int tail[5] = {F.tile_size, F.tiles_x, F.tiles_y, F.rank, F.npass};
@@ -246,67 +281,78 @@ int run_frame(fovpt_ctx* c, const LaunchParamsBlob& lp, const std::vector<PassHo
         c->owner_key = key;
     }
 
-    // chunking: at most path budget paths in flight
-    const size_t budget = (size_t)48 << 20;
-    struct Chunk { int pass; unsigned row0, row1; unsigned pid_base; };
-    std::vector<std::vector<Chunk>> groups;
+    // work groups: every group is one trip through the wavefront with at most kPathBudget paths in flight
+    struct Group { ChunkTable gen, res; size_t paths; };
+    std::vector<Group> groups;
     {
-        std::vector<Chunk> cur; size_t used = 0;
-        for (int p = 0; p < F.npass; ++p) {
+        Group cur{}; size_t used = 0, used_li = 0;
+        auto flush = [&]() { if (cur.gen.n) { cur.gen.total = (unsigned)used; cur.res.total = (unsigned)used_li; cur.paths = used; groups.push_back(cur); } cur = Group{}; used = 0; used_li = 0; };
+        auto push = [&](int p, unsigned row0, unsigned rows, unsigned ns) {
             const PassDev& P = F.pass[p];
-            const size_t per_row = (size_t)P.lw * P.spp;
-            unsigned row = 0;
-            while (row < P.lh) {
-                size_t room = budget > used ? budget - used : 0;
-                unsigned rows = (unsigned)std::min<size_t>(P.lh - row, per_row ? room / per_row : P.lh);
-                if (rows == 0) {
-                    if (cur.empty()) rows = 1;      // a single row larger than the budget: take it alone
-                    else { groups.push_back(cur); cur.clear(); used = 0; continue; }
+            ChunkDev g{p, row0, rows, 0u, ns, (unsigned)used, (unsigned)used};
+            ChunkDev r = g; r.first = (unsigned)used_li;
+            cur.res.c[cur.res.n++] = r; cur.gen.c[cur.gen.n++] = g;
+            used += (size_t)ns * rows * P.lw * P.spp; used_li += (size_t)ns * rows * P.lw;
+        };
+        if ((size_t)nsub * paths_per_layer(passes) <= kPathBudget) {
+            for (int p = 0; p < F.npass; ++p) push(p, 0u, F.pass[p].lh, (unsigned)nsub);
+            flush();
+        } else {
+            for (int p = 0; p < F.npass; ++p) {
+                const PassDev& P = F.pass[p];
+                const size_t per_row = (size_t)P.lw * P.spp;
+                unsigned row = 0;
+                while (row < P.lh) {
+                    const size_t room = kPathBudget > used ? kPathBudget - used : 0;
+                    unsigned rows = (unsigned)std::min<size_t>(P.lh - row, per_row ? room / per_row : P.lh);
+                    if (rows == 0 || cur.gen.n == kMaxChunks) {
+                        if (cur.gen.n == 0) rows = 1;      // a single row larger than the budget: take it alone
+                        else { flush(); continue; }
+                    }
+                    push(p, row, rows, 1u);
+                    row += rows;
                 }
-                cur.push_back({p, row, row + rows, (unsigned)used});
-                used += per_row * rows; row += rows;
             }
+            flush();
         }
-        if (!cur.empty()) groups.push_back(cur);
     }
     size_t max_paths = 0;
-    for (auto& g : groups) { size_t n = 0; for (auto& ch : g) n += (size_t)(ch.row1 - ch.row0) * F.pass[ch.pass].lw * F.pass[ch.pass].spp; max_paths = std::max(max_paths, n); }
-    if (max_paths >= 0xfffffff0ull) return fail(c, "path batch exceeds 32-bit ids");
+    for (auto& g : groups) max_paths = std::max(max_paths, g.paths);
+    if (max_paths >= 0xff000000ull) return fail(c, "path batch exceeds 32-bit ids");
     if (ensure_paths(c, max_paths)) return 1;
 
     const int iters = c->cfg.max_depth + 1 + (c->scene.any_catcher ? 4 : 0);
     for (auto& g : groups) {
         mark(c, K_RAYGEN);
         CU(cudaMemsetAsync(c->q.counts, 0, 8 * sizeof(uint32_t), c->stream));
-        for (auto& ch : g) {
-            launch_raygen(c->L, F, ch.pass, ch.row0, ch.row1, ch.pid_base, c->needed, c->ps, c->q, c->li_backplate, c->d_stats);
-            c->launches++;
-        }
+        launch_raygen(c->L, F, g.gen, c->needed, c->ps, c->q, c->li_backplate, c->d_stats); c->launches++;
         // iteration i: k_trace extends the radiance rays of bounce i and resolves the shadow rays that
         // k_shade(i-1) emitted (counter slot alternates 2 / 5), k_shade(i) consumes the hits.
         for (int it = 0; it <= iters; ++it) {
             const int slot_prev = (it & 1) ? 2 : 5, slot_new = (it & 1) ? 5 : 2;
             mark(c, K_EXTEND);
-            launch_trace(c->L, c->scene, c->ps, c->q, slot_prev, c->cfg.tmin, c->cfg.tmax, c->d_stats); c->launches++;
+            launch_trace(c->L, c->scene, c->ps, c->q, slot_prev, c->cfg.tmin, c->cfg.tmax, c->d_stats); c->launches++; c->trace_launches++;
             if (it == iters) break;                      // the last launch only drains the final shadow rays
             mark(c, K_SHADE);
             launch_shade(c->L, F, c->scene, c->ps, c->q, slot_new, c->cfg.fast_math != 0); c->launches++;
             std::swap(c->q.cur, c->q.next);                // the device-side counters are swapped by k_shade's last CTA
         }
         mark(c, K_RESOLVE);
-        for (auto& ch : g) {
-            launch_resolve_li(c->L, F, ch.pass, ch.row0, ch.row1, ch.pid_base, c->needed, c->ps, c->li_backplate, c->li_color);
-            c->launches++;
-        }
+        launch_resolve_li(c->L, F, g.res, c->needed, c->ps, c->li_backplate, c->li_color); c->launches++;
     }
     // a contributor to a shared frame stores its pixels into the owner's memory: not before the owner released the last frame
-    if (c->peer.open && !c->peer.owner)
-        launch_peer_wait(c->L, c->peer.flags + kPeerRelease, 1, -1, c->peer.seq, c->peer.d_err, c->peer.timeout_clocks);
-    launch_resolve_px(c->L, F, c->owner_map, c->li_color, c->needed, c->cfg.fast_math != 0); c->launches++;
+    float4* mirror = nullptr;
+    if (c->peer.open && (unsigned char*)F.frame == c->peer.base) {
+        if (!c->peer.owner)
+            launch_peer_wait(c->L, c->peer.flags + kPeerRelease, 1, -1, c->peer.seq, c->peer.d_err, c->peer.timeout_clocks);
+        if (c->peer.mirror_accum) mirror = c->peer.accum;
+    }
+    launch_resolve_px(c->L, F, c->owner_map, c->li_color, c->needed, mirror, c->cfg.fast_math != 0); c->launches++;
     cudaEventRecord(c->ev_frame1, c->stream);
+    nvtx_pop();
     c->frame_timed = true;
-    c->frames++;
-    c->last_frame_ptr = F.frame; c->last_accum_ptr = F.accum; c->last_npix = npix;
+    c->frames += (uint64_t)nsub;
+    c->last_frame_ptr = F.frame; c->last_accum_ptr = mirror ? mirror : F.accum; c->last_npix = npix;
     CU(cudaGetLastError());
     return 0;
 }
@@ -335,21 +381,21 @@ std::vector<PassHost> schedule(const fovpt_config& cfg, const LaunchParamsBlob& 
     const unsigned sub = lp.frame.subframe_index;
     const bool ext = cfg.seed_all_passes_with_subframe != 0;
     if (!cfg.foveated) {     // FOV_OFF block, SimplePathtracer.cpp:85-131
-        v.push_back({(unsigned)w, (unsigned)h, 1u, 1, 0.f, 1000000000.f, (unsigned)cfg.spp_uniform, 0u, 0u, 0u, ext ? sub : 0u});
+        v.push_back({(unsigned)w, (unsigned)h, 1u, 1, 0.f, 1000000000.f, (unsigned)cfg.spp_uniform, 0u, 0u, 0u, ext ? sub : 0u, ext ? 1u : 0u});
         return v;
     }
     const int ri = cfg.inner_radius, ro = cfg.outer_radius;
     const unsigned cx = lp.frame.c_x, cy = lp.frame.c_y;
     // periphery :137-157
-    v.push_back({(unsigned)(w / 4), (unsigned)(h / 4), 4u, 4, (float)ro, 1000000000.f, (unsigned)cfg.spp_periphery, 0u, 0u, 0u, sub});
+    v.push_back({(unsigned)(w / 4), (unsigned)(h / 4), 4u, 4, (float)ro, 1000000000.f, (unsigned)cfg.spp_periphery, 0u, 0u, 0u, sub, 1u});
     // mid ring :160-187 (launch dims are the float r_outer truncated)
     const float r2 = (float)(ro + 2);
     v.push_back({(unsigned)r2, (unsigned)r2, 2u, 2, (float)ri, r2, (unsigned)cfg.spp_mid, cx - (unsigned)(ro + 2), cy - (unsigned)(ro + 2),
-                 ext ? 0u : 1u, ext ? sub : 0u});
+                 ext ? 0u : 1u, ext ? sub : 0u, ext ? 1u : 0u});
     // fovea :189-209
     const float r3 = (float)(ri + 1);
     v.push_back({(unsigned)(r3 * 2), (unsigned)(r3 * 2), 1u, 1, 0.f, r3, (unsigned)cfg.spp_fovea, cx - (unsigned)(ri + 1), cy - (unsigned)(ri + 1),
-                 ext ? 0u : 1u, ext ? sub : 0u});
+                 ext ? 0u : 1u, ext ? sub : 0u, ext ? 1u : 0u});
     return v;
 }
 
@@ -598,28 +644,39 @@ int fovpt_launch(fovpt_ctx* c, const void* lp248, size_t size, unsigned lw, unsi
     if (lw == 0 || lh == 0) return 0;
     std::vector<PassHost> p;
     p.push_back({lw, lh, lp.frame.factor_x, lp.frame.fillSize, lp.frame.r_inner, lp.frame.r_outer, lp.samples_per_launch,
-                 lp.frame.offset_x, lp.frame.offset_y, lp.frame.redraw, lp.frame.subframe_index});
+                 lp.frame.offset_x, lp.frame.offset_y, lp.frame.redraw, lp.frame.subframe_index, 0u});
     return run_frame(c, lp, p);
 }
 
-int fovpt_render_frame(fovpt_ctx* c, void* lp248)
+int fovpt_render_frames(fovpt_ctx* c, void* lp248, int n_subframes)
 {
     if (!c) return 1;
     if (!lp248) return fail(c, "null launch params");
+    if (n_subframes < 1 || n_subframes > 65536) return fail(c, "n_subframes out of range");
     LaunchParamsBlob* lp = (LaunchParamsBlob*)lp248;
     if (lp->frame.size_x == 0) return 0;                  // SimplePathtracer.cpp:81-82
     std::vector<PassHost> p = schedule(c->cfg, *lp);
-    LaunchParamsBlob tmp; memcpy(&tmp, lp, sizeof(tmp));
-    int rc = run_frame(c, tmp, p);
-    if (rc) return rc;
+    // as many subframes per wavefront as the path budget holds (C3: all 8; C5: one, itself cut into row chunks)
+    const size_t per_layer = std::max<size_t>(paths_per_layer(p), 1);
+    const int per_batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_subframes, kPathBudget / per_layer));
+    for (int done = 0; done < n_subframes;) {
+        const int nsub = std::min(per_batch, n_subframes - done);
+        LaunchParamsBlob tmp; memcpy(&tmp, lp, sizeof(tmp));
+        int rc = run_frame(c, tmp, p, nsub);
+        if (rc) return rc;
+        done += nsub;
+        lp->frame.subframe_index += (unsigned)nsub;
+        for (auto& ph : p) ph.subframe += (unsigned)nsub * ph.sub_step;
+    }
     // what render() leaves behind in the host copy of the params (:137-211)
     const PassHost& last = p.back();
     lp->frame.factor_x = lp->frame.factor_y = last.factor; lp->frame.factor_z = 1;
     lp->frame.fillSize = last.fill; lp->frame.r_inner = last.r_inner; lp->frame.r_outer = last.r_outer;
     lp->samples_per_launch = last.spp; lp->frame.offset_x = last.off_x; lp->frame.offset_y = last.off_y; lp->frame.redraw = last.redraw;
-    lp->frame.subframe_index = lp->frame.subframe_index + 1;
     return 0;
 }
+
+int fovpt_render_frame(fovpt_ctx* c, void* lp248) { return fovpt_render_frames(c, lp248, 1); }
 
 int fovpt_sync(fovpt_ctx* c)
 {
@@ -662,6 +719,15 @@ int fovpt_download(fovpt_ctx* c, uint32_t* dst, size_t npix)
     return 0;
 }
 
+int fovpt_forget_frame(fovpt_ctx* c)
+{
+    if (!c) return 1;
+    cudaSetDevice(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    c->last_frame_ptr = c->fb_frame; c->last_accum_ptr = c->fb_accum; c->last_npix = (size_t)c->fb_w * c->fb_h;
+    return 0;
+}
+
 int fovpt_download_accum(fovpt_ctx* c, float* dst, size_t npix)
 {
     if (!c || !dst) return 1;
@@ -694,6 +760,43 @@ int fovpt_trace(fovpt_ctx* c, const float* rays, size_t n, int mode, int32_t* tr
     return 0;
 }
 
+int fovpt_texture_check(fovpt_ctx* c, int texture_id, const float* uv, size_t n, int mode, float* sw_rgba, float* hw_rgba)
+{
+    if (!c || !uv || !sw_rgba || !hw_rgba) return 1;
+    if (!c->committed) return fail(c, "scene not committed");
+    if (texture_id < 0 || texture_id >= (int)c->textures.size()) return fail(c, "no such texture");
+    if (n == 0) return 0;
+    cudaSetDevice(c->device);
+    const HostTex& t = c->textures[(size_t)texture_id];
+    // the reference's texture object, field by field (SimplePathtracer.cpp:748-799)
+    cudaChannelFormatDesc cd = cudaCreateChannelDesc<uchar4>();
+    cudaArray_t arr = nullptr;
+    CU(cudaMallocArray(&arr, &cd, (size_t)t.w, (size_t)t.h));
+    const size_t pitch = (size_t)t.w * 4;
+    CU(cudaMemcpy2DToArray(arr, 0, 0, t.px.data(), pitch, pitch, (size_t)t.h, cudaMemcpyHostToDevice));
+    cudaResourceDesc rd; memset(&rd, 0, sizeof(rd));
+    rd.resType = cudaResourceTypeArray; rd.res.array.array = arr;
+    cudaTextureDesc td; memset(&td, 0, sizeof(td));
+    td.addressMode[0] = cudaAddressModeWrap; td.addressMode[1] = cudaAddressModeWrap;
+    td.filterMode = cudaFilterModeLinear; td.readMode = cudaReadModeNormalizedFloat; td.normalizedCoords = 1;
+    td.maxAnisotropy = 1; td.maxMipmapLevelClamp = 99; td.minMipmapLevelClamp = 0; td.mipmapFilterMode = cudaFilterModePoint;
+    td.borderColor[0] = 1.0f; td.sRGB = 0;
+    cudaTextureObject_t tex = 0;
+    CU(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+    float2* d_uv = nullptr; float4 *d_sw = nullptr, *d_hw = nullptr;
+    CU(dmalloc(&d_uv, n)); CU(dmalloc(&d_sw, n)); CU(dmalloc(&d_hw, n));
+    CU(cudaMemcpyAsync(d_uv, uv, n * 8, cudaMemcpyHostToDevice, c->stream));
+    int4 info; CU(cudaMemcpy(&info, c->d_tex_info + texture_id, sizeof(int4), cudaMemcpyDeviceToHost));
+    launch_texture_probe(c->L, tex, c->d_texels + info.x, t.w, t.h, d_uv, n, mode, d_sw, d_hw);
+    c->launches++;
+    CU(cudaMemcpyAsync(sw_rgba, d_sw, n * 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(hw_rgba, d_hw, n * 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaGetLastError());
+    cudaDestroyTextureObject(tex); cudaFreeArray(arr); cudaFree(d_uv); cudaFree(d_sw); cudaFree(d_hw);
+    return 0;
+}
+
 int fovpt_primary_hits(fovpt_ctx* c, const void* lp248, unsigned lw, unsigned lh, int32_t* tri, float* tuv, float* dir)
 {
     if (!c || !lp248 || !tri || !tuv || !dir) return 1;
@@ -701,7 +804,7 @@ int fovpt_primary_hits(fovpt_ctx* c, const void* lp248, unsigned lw, unsigned lh
     LaunchParamsBlob lp; memcpy(&lp, lp248, sizeof(lp));
     std::vector<PassHost> p;
     p.push_back({lw, lh, lp.frame.factor_x, lp.frame.fillSize, lp.frame.r_inner, lp.frame.r_outer, lp.samples_per_launch,
-                 lp.frame.offset_x, lp.frame.offset_y, lp.frame.redraw, lp.frame.subframe_index});
+                 lp.frame.offset_x, lp.frame.offset_y, lp.frame.redraw, lp.frame.subframe_index, 0u});
     FrameDev F; size_t total_li = 0;
     fill_frame(c, lp, p, &F, &total_li);
     cudaSetDevice(c->device);
@@ -729,6 +832,7 @@ int fovpt_set_tile_owner(fovpt_ctx* c, int tile_size, int tiles_x, int tiles_y, 
     c->owner_key.clear();
     if (!owner) { c->tile_size = c->tiles_x = c->tiles_y = 0; c->rank = 0; return 0; }
     if (tile_size <= 0 || tiles_x <= 0 || tiles_y <= 0) return fail(c, "bad tile grid");
+    if (rank < 0 || rank > 255) return fail(c, "rank must be 0..255 (the owner table holds one byte per tile)");
     CU(dmalloc(&c->d_tile_owner, (size_t)tiles_x * tiles_y));
     CU(cudaMemcpy(c->d_tile_owner, owner, (size_t)tiles_x * tiles_y, cudaMemcpyHostToDevice));
     c->tile_size = tile_size; c->tiles_x = tiles_x; c->tiles_y = tiles_y; c->rank = rank;
@@ -754,7 +858,7 @@ int fovpt_get_stats(fovpt_ctx* c, fovpt_stats* s)
                 q[2], q[2] ? (double)q[3] / q[2] : 0., q[3] ? (double)q[4] / q[3] : 0., q[2] ? (double)q[5] / q[2] : 0., q[6]);
     }
 #endif
-    s->kernel_launches = c->launches; s->frames = c->frames;
+    s->kernel_launches = c->launches; s->frames = c->frames; s->trace_launches = c->trace_launches;
     s->bvh_nodes = c->bvh.n_nodes; s->bvh_tris = c->bvh.n_tris; s->bvh_build_ms = c->build_ms;
     s->last_frame_ms = c->last_ms[0]; s->last_raygen_ms = c->last_ms[K_RAYGEN]; s->last_extend_ms = c->last_ms[K_EXTEND];
     s->last_shade_ms = c->last_ms[K_SHADE]; s->last_shadow_ms = c->last_ms[K_SHADOW]; s->last_resolve_ms = c->last_ms[K_RESOLVE];
@@ -767,7 +871,7 @@ int fovpt_reset_stats(fovpt_ctx* c)
     cudaSetDevice(c->device);
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaMemset(c->d_stats, 0, sizeof(DevStats)));
-    c->launches = 0; c->frames = 0;
+    c->launches = 0; c->frames = 0; c->trace_launches = 0;
     return 0;
 }
 
@@ -820,15 +924,16 @@ int fovpt_peer_frame_create(fovpt_ctx* c, size_t npix, int world, int rank, fovp
     cudaSetDevice(c->device);
     const size_t fb = peer_frame_bytes(npix);
     unsigned char* base = nullptr;
-    CU(cudaMalloc((void**)&base, fb + kPeerFlagWords * 4));
-    CU(cudaMemset(base, 0, fb + kPeerFlagWords * 4));
+    CU(cudaMalloc((void**)&base, fb + kPeerFlagWords * 4 + npix * sizeof(float4)));
+    CU(cudaMemset(base, 0, fb + kPeerFlagWords * 4 + npix * sizeof(float4)));
     PeerHandleBlob h; memset(&h, 0, sizeof(h));
     cudaError_t e = cudaIpcGetMemHandle(&h.mem, base);
     if (e != cudaSuccess) { cudaFree(base); return cuda_fail(c, e, "cudaIpcGetMemHandle"); }
     h.npix = npix; h.world = world; h.owner_rank = rank; h.magic = kPeerMagic;
     memcpy(handle_out, &h, sizeof(h));
     c->peer = fovpt_ctx::PeerFrame{};
-    c->peer.base = base; c->peer.flags = (uint32_t*)(base + fb); c->peer.open = true; c->peer.owner = true;
+    c->peer.base = base; c->peer.flags = (uint32_t*)(base + fb); c->peer.accum = (float4*)(base + fb + kPeerFlagWords * 4);
+    c->peer.open = true; c->peer.owner = true;
     c->peer.world = world; c->peer.owner_rank = rank; c->peer.rank = rank; c->peer.npix = npix;
     c->peer.timeout_clocks = peer_timeout_clocks(c->device);
     *frame_out = (uint32_t*)base;
@@ -851,9 +956,19 @@ int fovpt_peer_frame_open(fovpt_ctx* c, const fovpt_peer_handle* handle, int ran
     if (e != cudaSuccess) { cudaIpcCloseMemHandle(base); return cuda_fail(c, e, "peer frame error word"); }
     c->peer = fovpt_ctx::PeerFrame{};
     c->peer.base = (unsigned char*)base; c->peer.flags = (uint32_t*)((unsigned char*)base + peer_frame_bytes(h.npix)); c->peer.d_err = d_err;
+    c->peer.accum = (float4*)((unsigned char*)base + peer_frame_bytes(h.npix) + kPeerFlagWords * 4);
     c->peer.open = true; c->peer.owner = false; c->peer.world = h.world; c->peer.owner_rank = h.owner_rank; c->peer.rank = rank;
     c->peer.npix = (size_t)h.npix; c->peer.timeout_clocks = peer_timeout_clocks(c->device);
     *frame_out = (uint32_t*)base;
+    return 0;
+}
+
+int fovpt_peer_frame_accum(fovpt_ctx* c, int mirror, float** accum_out)
+{
+    if (!c) return 1;
+    if (!c->peer.open) return fail(c, "peer frame: not open");
+    c->peer.mirror_accum = mirror != 0;
+    if (accum_out) *accum_out = (float*)c->peer.accum;
     return 0;
 }
 
@@ -900,6 +1015,7 @@ int fovpt_peer_frame_close(fovpt_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     if (c->last_frame_ptr == (uint32_t*)c->peer.base) { c->last_frame_ptr = nullptr; c->last_npix = 0; }
+    if (c->last_accum_ptr == c->peer.accum) c->last_accum_ptr = nullptr;
     if (c->peer.owner) cudaFree(c->peer.base);
     else { cudaIpcCloseMemHandle(c->peer.base); cudaFree(c->peer.d_err); }
     c->peer = fovpt_ctx::PeerFrame{};

@@ -318,28 +318,12 @@ template <bool FAST> __device__ __forceinline__ uint32_t tonemap_rgba8(float3 ac
     return quant8(srgb_oetf<FAST>(m.x)) | (quant8(srgb_oetf<FAST>(m.y)) << 8) | (quant8(srgb_oetf<FAST>(m.z)) << 16) | (255u << 24);
 }
 
-// RGBA8 texture, normalised coordinates, wrap, bilinear, /255 (sampler state SimplePathtracer.cpp:775-789;
-// software definition shared with the oracle, see DESIGN.md "textures")
+// RGBA8 texture through the reference's sampler (linear, wrap, normalised coordinates, normalised float;
+// SimplePathtracer.cpp:775-789): the texture unit's own fixed-point arithmetic, fx_tex_bilinear_rgba8 of fovpt_exact.h
 __device__ __forceinline__ float3 texture_bilinear(const uint32_t* __restrict__ texels, int w, int h, float x, float y)
 {
-    const float xb = x * (float)w - 0.5f, yb = y * (float)h - 0.5f;
-    const float fx = floorf(xb), fy = floorf(yb);
-    const float a = xb - fx, b = yb - fy;
-    long long ix = (long long)fx, iy = (long long)fy;
-    int x0 = (int)(ix % w); if (x0 < 0) x0 += w;
-    int y0 = (int)(iy % h); if (y0 < 0) y0 += h;
-    int x1 = x0 + 1 == w ? 0 : x0 + 1;
-    int y1 = y0 + 1 == h ? 0 : y0 + 1;
-    const uint32_t p00 = __ldg(&texels[(size_t)y0 * w + x0]), p10 = __ldg(&texels[(size_t)y0 * w + x1]);
-    const uint32_t p01 = __ldg(&texels[(size_t)y1 * w + x0]), p11 = __ldg(&texels[(size_t)y1 * w + x1]);
-    const float w00 = (1.f - a) * (1.f - b), w10 = a * (1.f - b), w01 = (1.f - a) * b, w11 = a * b;
-    float o[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        const float k = 1.0f / 255.0f;
-        o[c] = w00 * ((float)((p00 >> (8 * c)) & 255u) * k) + w10 * ((float)((p10 >> (8 * c)) & 255u) * k) +
-               w01 * ((float)((p01 >> (8 * c)) & 255u) * k) + w11 * ((float)((p11 >> (8 * c)) & 255u) * k);
-    }
+    float o[4];
+    fx_tex_bilinear_rgba8(texels, w, h, x, y, o);
     return f3(o[0], o[1], o[2]);
 }
 

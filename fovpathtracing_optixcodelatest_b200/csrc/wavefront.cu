@@ -86,29 +86,44 @@ __device__ __forceinline__ float3 camera_dir(const FrameDev& F, uint32_t px, uin
 }
 
 // ------------------------------------------------------------------ k_raygen
-// chunk = rows [row0,row1) of one pass.  One thread per (launch index, sample).
-__global__ void k_raygen(FrameDev F, int pass, unsigned row0, unsigned row1, unsigned chunk_pid_base,
-                         const uint8_t* __restrict__ needed, PathState ps, Queues q, float4* __restrict__ li_backplate,
-                         DevStats* __restrict__ stats)
+// which chunk of the table holds work item i (tables have <= kMaxChunks entries; first[] ascends)
+__device__ __forceinline__ int chunk_of(const ChunkTable& T, uint32_t i)
+{
+    int c = 0;
+#pragma unroll
+    for (int j = 1; j < kMaxChunks; ++j) c += (j < T.n && i >= T.c[j].first) ? 1 : 0;
+    return c;
+}
+
+// ONE launch for all passes (and all layers of a batch): one thread per (layer, launch index, sample).
+__global__ void k_raygen(FrameDev F, ChunkTable T, const uint8_t* __restrict__ needed, PathState ps, Queues q,
+                         float4* __restrict__ li_backplate, DevStats* __restrict__ stats)
 {
     constexpr unsigned FULL = 0xffffffffu;
     __shared__ uint32_t s_cnt[32];
     __shared__ uint32_t s_base;
-    const PassDev P = F.pass[pass];
-    const size_t total = (size_t)(row1 - row0) * P.lw * P.spp;
+    const uint32_t total = T.total;
     const unsigned lane = threadIdx.x & 31u, wib = threadIdx.x >> 5, nw = blockDim.x >> 5;
     unsigned long long started = 0;
     // queue slots are claimed with ONE atomicAdd per CTA and iteration (a warp-level claim put ~70 k same-address atomics
     // per frame on counts[0]); the trip count is CTA-uniform
-    for (size_t base = blockIdx.x * (size_t)blockDim.x; base < total; base += (size_t)gridDim.x * blockDim.x) {
-        const size_t i = base + threadIdx.x;
-        unsigned k = 0, lx = 0, ly = 0; uint32_t li = 0;
-        bool active = i < total;
+    for (uint32_t base = blockIdx.x * blockDim.x; base < total; base += gridDim.x * blockDim.x) {
+        const uint32_t i = base + threadIdx.x;
+        unsigned k = 0, lx = 0, ly = 0, layer = 0; uint32_t li = 0, pid = 0; int pass = 0;
+        bool active = i < total;                                   // (run_frame keeps total far enough below 2^32 for i not to wrap)
         if (active) {
-            k = (unsigned)(i % P.spp);
-            const size_t lloc = i / P.spp;
-            lx = (unsigned)(lloc % P.lw); ly = row0 + (unsigned)(lloc / P.lw);
+            const ChunkDev ch = T.c[chunk_of(T, i)];
+            pass = ch.pass;
+            const PassDev& P = F.pass[pass];
+            const uint32_t local = i - ch.first;
+            const uint32_t per_layer = ch.rows * P.lw * P.spp;
+            layer = ch.s0 + local / per_layer;
+            const uint32_t r = local % per_layer;
+            k = r % P.spp;
+            const uint32_t lloc = r / P.spp;
+            lx = lloc % P.lw; ly = ch.row0 + lloc / P.lw;
             li = ly * P.lw + lx;
+            pid = ch.pid_base + local;
             active = needed[P.li_base + li] != 0;
         }
         const unsigned m = __ballot_sync(FULL, active);
@@ -121,17 +136,17 @@ __global__ void k_raygen(FrameDev F, int pass, unsigned row0, unsigned row1, uns
         }
         __syncthreads();
         if (active) {
+            const PassDev& P = F.pass[pass];
             uint32_t slot = s_base + __popc(m & ((1u << lane) - 1u));
             for (unsigned w = 0; w < wib; ++w) slot += s_cnt[w];
             uint32_t px, py;
             fx_launch_to_pixel(lx, ly, P.factor, P.factor, P.uoff_x, P.uoff_y, &px, &py);
-            uint32_t seed = fx_tea4(ly * (unsigned)F.w + lx, P.subframe);                    // :411
+            uint32_t seed = fx_tea4(ly * (unsigned)F.w + lx, P.subframe + layer * P.sub_step);   // :411
             seed = fx_seed_after(seed, k);
             const fx_rng rng = fx_rng_init(seed);                                           // :464 (before the jitter draws)
             const float jx = fx_rnd(&seed);                                                 // :479, x first
             const float jy = fx_rnd(&seed);
             const float3 dir = camera_dir(F, px, py, jx, jy);
-            const uint32_t pid = chunk_pid_base + (uint32_t)i;
             q.cur.o[slot] = make_float4(F.eye[0], F.eye[1], F.eye[2], 0.f);
             q.cur.d[slot] = make_float4(dir.x, dir.y, dir.z, 0.f);
             q.cur.thr[slot] = make_float4(1.f, 1.f, 1.f, 1.f);                               // throughput 1, rayEta 1 (:467-468)
@@ -142,7 +157,7 @@ __global__ void k_raygen(FrameDev F, int pass, unsigned row0, unsigned row1, uns
             ps.alpha[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (k == P.spp - 1) {                                                           // backplate of the LAST sample (:495)
                 const float4 bp = probe_eval(F.probe, probe_dir_to_uv(dir));
-                li_backplate[P.li_base + li] = bp;
+                li_backplate[(size_t)layer * F.li_total + P.li_base + li] = bp;
             }
             ++started;
         }
@@ -453,6 +468,8 @@ __global__ void __launch_bounds__(128, FOVPT_SHADE_BLOCKS) k_shade(FrameDev F, S
     __shared__ uint32_t s_cnt[2][4];
     __shared__ uint32_t s_base[2];
     const uint32_t n = q.counts[0];
+    __syncthreads();      // every warp of the CTA has read counts[0] before thread 0 can take the end-of-iteration ticket below
+                          // (a CTA with zero loop iterations would otherwise let late warps see the rotated counters)
     const unsigned lane = threadIdx.x & 31u, wib = threadIdx.x >> 5;
     for (uint32_t base = blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {      // CTA-uniform trip count
         const uint32_t i = base + threadIdx.x;
@@ -493,18 +510,22 @@ __global__ void __launch_bounds__(128, FOVPT_SHADE_BLOCKS) k_shade(FrameDev F, S
 }
 
 // ------------------------------------------------------------------ k_resolve_li
-// per launch index: sum its spp samples in order, apply the backplate/alpha composite (:536-560)
-__global__ void k_resolve_li(FrameDev F, int pass, unsigned row0, unsigned row1, unsigned chunk_pid_base,
-                             const uint8_t* __restrict__ needed, PathState ps, const float4* __restrict__ li_backplate,
-                             float4* __restrict__ li_color)
+// per (layer, launch index): sum its spp samples in order, apply the backplate/alpha composite (:536-560).  One launch for
+// all passes and layers; work item i of chunk c = (layer - s0) * rows * lw + (ly - row0) * lw + lx.
+__global__ void k_resolve_li(FrameDev F, ChunkTable T, const uint8_t* __restrict__ needed, PathState ps,
+                             const float4* __restrict__ li_backplate, float4* __restrict__ li_color)
 {
-    const PassDev P = F.pass[pass];
-    const size_t total = (size_t)(row1 - row0) * P.lw;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t li = row0 * P.lw + (uint32_t)i;
+    const uint32_t total = T.total;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const ChunkDev ch = T.c[chunk_of(T, i)];
+        const PassDev& P = F.pass[ch.pass];
+        const uint32_t local = i - ch.first;
+        const uint32_t per_layer = ch.rows * P.lw;
+        const uint32_t layer = ch.s0 + local / per_layer;
+        const uint32_t li = ch.row0 * P.lw + local % per_layer;
         if (!needed[P.li_base + li]) continue;
         float3 result = f3(0.f), alpha = f3(0.f);
-        const uint32_t pid0 = chunk_pid_base + (uint32_t)i * P.spp;
+        const uint32_t pid0 = ch.pid_base + local * P.spp;
         for (unsigned k = 0; k < P.spp; ++k) {
             const float4 d = ps.direct[pid0 + k], in = ps.indirect[pid0 + k], a = ps.alpha[pid0 + k];
             result = result + (f3(d.x, d.y, d.z) + f3(in.x, in.y, in.z));
@@ -513,10 +534,11 @@ __global__ void k_resolve_li(FrameDev F, int pass, unsigned row0, unsigned row1,
         const float sppf = (float)P.spp;
         const float inv = 1.0f / sppf;
         alpha = alpha * inv;
-        const float4 bp = li_backplate[P.li_base + li];
+        const size_t at = (size_t)layer * F.li_total + P.li_base + li;
+        const float4 bp = li_backplate[at];
         const float3 color = (f3(bp.x, bp.y, bp.z) * sppf) * (f3(1.f) - alpha) + result;
         const float3 acc = color * inv;
-        li_color[P.li_base + li] = make_float4(acc.x, acc.y, acc.z, 1.0f);
+        li_color[at] = make_float4(acc.x, acc.y, acc.z, 1.0f);
     }
 }
 
@@ -549,23 +571,34 @@ __device__ __forceinline__ float3 filtered_color(const FrameDev& F, const PassDe
     return mix3(mix3(own, c10, wx), mix3(c01, c11, wx), wy);
 }
 
+// A batch (F.nsub > 1) replays, per pixel and in order, what nsub successive frames would have done to the accumulation
+// buffer: the result is bit-identical to rendering them one by one; only the final state is tonemapped.
 template <bool FAST>
 __global__ void k_resolve_px(FrameDev F, const uint32_t* __restrict__ owner_map, const float4* __restrict__ li_color,
-                             const uint8_t* __restrict__ needed)
+                             const uint8_t* __restrict__ needed, float4* __restrict__ accum_mirror)
 {
     const size_t npix = (size_t)F.w * F.h;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
         const uint32_t own = owner_map[i];
         if (own == kNoOwner) continue;
         const PassDev& P = F.pass[own >> 28];
-        float3 acc = filtered_color(F, P, own & 0x0fffffffu, (int)(i % F.w), (int)(i / F.w), li_color, needed);
-        if (F.accumulate && P.subframe > 0 && !P.redraw) {       // PT_sv4_vmv2/deviceProgram.cu:545-553
-            acc = f3(fmaxf(0.f, fminf(acc.x, 10.f)), fmaxf(0.f, fminf(acc.y, 10.f)), fmaxf(0.f, fminf(acc.z, 10.f)));
-            const float a = 1.0f / (float)(P.subframe + 1);
-            const float4 prev = F.accum[i];
-            acc = mix3(f3(prev.x, prev.y, prev.z), acc, a);
+        const bool lerps = F.accumulate && !P.redraw;
+        float3 acc = f3(0.f);
+        bool have = false;                                       // acc holds the running value (else it is still in F.accum)
+        for (int s = 0; s < F.nsub; ++s) {
+            float3 cur = filtered_color(F, P, own & 0x0fffffffu, (int)(i % F.w), (int)(i / F.w), li_color + (size_t)s * F.li_total, needed);
+            const unsigned sub = P.subframe + (unsigned)s * P.sub_step;
+            if (lerps && sub > 0) {                              // PT_sv4_vmv2/deviceProgram.cu:545-553
+                cur = f3(fmaxf(0.f, fminf(cur.x, 10.f)), fmaxf(0.f, fminf(cur.y, 10.f)), fmaxf(0.f, fminf(cur.z, 10.f)));
+                const float a = 1.0f / (float)(sub + 1);
+                if (!have) { const float4 prev = F.accum[i]; acc = f3(prev.x, prev.y, prev.z); }
+                cur = mix3(acc, cur, a);
+            }
+            acc = cur; have = true;
         }
-        F.accum[i] = make_float4(acc.x, acc.y, acc.z, 1.0f);
+        const float4 out = make_float4(acc.x, acc.y, acc.z, 1.0f);
+        F.accum[i] = out;
+        if (accum_mirror) accum_mirror[i] = out;                 // multi-GPU: the owner rank's shared accumulation buffer (peer memory)
         F.frame[i] = tonemap_rgba8<FAST>(acc, F.exposure);
     }
 }
@@ -641,6 +674,52 @@ __global__ void k_trace_query(SceneDev S, const float* __restrict__ rays, size_t
     }
 }
 
+// ------------------------------------------------------------------ texture-unit cross-check (test hook)
+// hw: the texture unit with the reference's sampler state (SimplePathtracer.cpp:775-789); sw: candidate software definitions
+//   mode 0 float weights | 1 frac rounded to 8 bits | 2 coordinate rounded to 1/256 texel (rni) | 3 frac truncated | 4 coordinate floored
+__device__ __forceinline__ void tex_axis(float x, int n, int mode, int* i0, int* i1, float* a)
+{
+    const float xs = x * (float)n;
+    long long i; float al;
+    if (mode == 2 || mode == 4) {
+        const float f = xs * 256.0f;
+        const long long fx = (mode == 2 ? (long long)rintf(f) : (long long)floorf(f)) - 128;
+        i = fx >> 8; al = (float)(fx & 255) * (1.0f / 256.0f);
+    } else {
+        const float xb = xs - 0.5f, fl = floorf(xb);
+        i = (long long)fl; al = xb - fl;
+        if (mode == 1) al = floorf(al * 256.0f + 0.5f) * (1.0f / 256.0f);
+        if (mode == 3) al = floorf(al * 256.0f) * (1.0f / 256.0f);
+    }
+    long long m = i % n; if (m < 0) m += n;
+    *i0 = (int)m; *i1 = (int)(m + 1 == n ? 0 : m + 1); *a = al;
+}
+__global__ void k_texture_probe(cudaTextureObject_t tex, const uint32_t* __restrict__ texels, int w, int h, const float2* __restrict__ uv, size_t n,
+                                int mode, float4* __restrict__ sw, float4* __restrict__ hw)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float2 t = uv[i];
+        hw[i] = tex2D<float4>(tex, t.x, t.y);
+        if (mode < 0) { const float3 c = texture_bilinear(texels, w, h, t.x, t.y); sw[i] = make_float4(c.x, c.y, c.z, 0.f); continue; }   // the product's fetch
+        int x0, x1, y0, y1; float a, b;
+        tex_axis(t.x, w, mode, &x0, &x1, &a); tex_axis(t.y, h, mode, &y0, &y1, &b);
+        const uint32_t p00 = texels[(size_t)y0 * w + x0], p10 = texels[(size_t)y0 * w + x1], p01 = texels[(size_t)y1 * w + x0], p11 = texels[(size_t)y1 * w + x1];
+        const float w00 = (1.f - a) * (1.f - b), w10 = a * (1.f - b), w01 = (1.f - a) * b, w11 = a * b;
+        float o[4];
+        for (int c = 0; c < 4; ++c) {
+            const float k = 1.0f / 255.0f;
+            o[c] = w00 * ((float)((p00 >> (8 * c)) & 255u) * k) + w10 * ((float)((p10 >> (8 * c)) & 255u) * k) +
+                   w01 * ((float)((p01 >> (8 * c)) & 255u) * k) + w11 * ((float)((p11 >> (8 * c)) & 255u) * k);
+        }
+        sw[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+void launch_texture_probe(const LaunchCfg& L, cudaTextureObject_t tex, const uint32_t* texels, int w, int h, const float2* uv, size_t n, int mode,
+                          float4* sw, float4* hw)
+{
+    k_texture_probe<<<L.grid_light, 256, 0, L.stream>>>(tex, texels, w, h, uv, n, mode, sw, hw);
+}
+
 // ------------------------------------------------------------------ peer-frame flags (multi-GPU gather over NVLink peer memory)
 // The shared frame lives in the owner's memory; contributors store their tiles into it from k_resolve_px.  Ordering between
 // the processes is carried by 32-bit sequence numbers in the same allocation, written and polled at system scope: a
@@ -677,10 +756,10 @@ void launch_owner_map(const LaunchCfg& L, const FrameDev& F, uint32_t* owner_map
 {
     k_owner_map<<<L.grid_light, 256, 0, L.stream>>>(F, owner_map, needed);
 }
-void launch_raygen(const LaunchCfg& L, const FrameDev& F, int pass, unsigned row0, unsigned row1, unsigned pid_base,
-                   const uint8_t* needed, const PathState& ps, const Queues& q, float4* li_backplate, DevStats* stats)
+void launch_raygen(const LaunchCfg& L, const FrameDev& F, const ChunkTable& T, const uint8_t* needed, const PathState& ps, const Queues& q,
+                   float4* li_backplate, DevStats* stats)
 {
-    k_raygen<<<L.grid_light, 256, 0, L.stream>>>(F, pass, row0, row1, pid_base, needed, ps, q, li_backplate, stats);
+    k_raygen<<<L.grid_light, 256, 0, L.stream>>>(F, T, needed, ps, q, li_backplate, stats);
 }
 void launch_trace(const LaunchCfg& L, const SceneDev& S, const PathState& ps, const Queues& q, int shadow_slot, float tmin, float tmax, DevStats* stats)
 {
@@ -696,15 +775,16 @@ void launch_peer_wait(const LaunchCfg& L, const uint32_t* flags, int count, int 
 {
     k_peer_wait<<<1, 64, 0, L.stream>>>(flags, count, skip, seq, err, timeout_clocks);
 }
-void launch_resolve_li(const LaunchCfg& L, const FrameDev& F, int pass, unsigned row0, unsigned row1, unsigned pid_base,
-                       const uint8_t* needed, const PathState& ps, const float4* li_backplate, float4* li_color)
+void launch_resolve_li(const LaunchCfg& L, const FrameDev& F, const ChunkTable& T, const uint8_t* needed, const PathState& ps,
+                       const float4* li_backplate, float4* li_color)
 {
-    k_resolve_li<<<L.grid_light, 256, 0, L.stream>>>(F, pass, row0, row1, pid_base, needed, ps, li_backplate, li_color);
+    k_resolve_li<<<L.grid_light, 256, 0, L.stream>>>(F, T, needed, ps, li_backplate, li_color);
 }
-void launch_resolve_px(const LaunchCfg& L, const FrameDev& F, const uint32_t* owner_map, const float4* li_color, const uint8_t* needed, bool fast)
+void launch_resolve_px(const LaunchCfg& L, const FrameDev& F, const uint32_t* owner_map, const float4* li_color, const uint8_t* needed,
+                       float4* accum_mirror, bool fast)
 {
-    if (fast) k_resolve_px<true><<<L.grid_light, 256, 0, L.stream>>>(F, owner_map, li_color, needed);
-    else k_resolve_px<false><<<L.grid_light, 256, 0, L.stream>>>(F, owner_map, li_color, needed);
+    if (fast) k_resolve_px<true><<<L.grid_light, 256, 0, L.stream>>>(F, owner_map, li_color, needed, accum_mirror);
+    else k_resolve_px<false><<<L.grid_light, 256, 0, L.stream>>>(F, owner_map, li_color, needed, accum_mirror);
 }
 void launch_probe_guides(const LaunchCfg& L, const ProbeBlob& p, uint16_t* gy, uint16_t* gx)
 {

@@ -65,6 +65,7 @@ struct SceneDev {
 
 struct PassDev {
     unsigned lw, lh, factor, fill, spp, redraw, subframe;
+    unsigned sub_step;                // subframe of layer s of a batch = subframe + s * sub_step (0: the pass reseeds with the same subframe)
     int      off_x, off_y;            // offset as a signed number (uint2 offset wraps)
     unsigned uoff_x, uoff_y;          // the same offset, raw
     float    r_inner, r_outer;
@@ -81,6 +82,10 @@ struct FrameDev {
     uint32_t* frame;
     int       npass;
     PassDev   pass[kMaxPasses];
+    // a batch of nsub accumulated subframes traced as ONE wavefront (fovpt_render_frames): per-launch-index buffers hold
+    // nsub layers of li_total entries, k_resolve_px replays the per-frame accumulation over the layers in order
+    int       nsub;
+    unsigned  li_total;
     // config
     int   max_depth;
     float tmin, tmax, exposure;
@@ -89,6 +94,13 @@ struct FrameDev {
     const uint8_t* tile_owner;
     int   tile_size, tiles_x, tiles_y, rank;
 };
+
+// Work of one raygen / resolve launch: up to kMaxChunks row ranges of passes, each over a range of batch layers.  Item i of
+// chunk c (first[c] <= i < first[c+1]) decomposes as ((layer - s0) * rows * lw + (ly - row0) * lw + lx) * spp + k, and the
+// path slot is pid_base + (i - first[c]), so the spp samples of one (layer, launch index) are adjacent.
+constexpr int kMaxChunks = 8;
+struct ChunkDev { int pass; unsigned row0, rows, s0, ns, pid_base, first; };
+struct ChunkTable { int n; unsigned total; ChunkDev c[kMaxChunks]; };
 
 struct Queues {
     RayBuf    cur, next;

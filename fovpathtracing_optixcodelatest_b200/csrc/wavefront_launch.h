@@ -16,20 +16,24 @@ struct LaunchCfg {
 };
 
 void launch_owner_map(const LaunchCfg&, const FrameDev&, uint32_t* owner_map, uint8_t* needed);
-void launch_raygen(const LaunchCfg&, const FrameDev&, int pass, unsigned row0, unsigned row1, unsigned pid_base,
-                   const uint8_t* needed, const PathState&, const Queues&, float4* li_backplate, DevStats*);
+void launch_raygen(const LaunchCfg&, const FrameDev&, const ChunkTable&, const uint8_t* needed, const PathState&, const Queues&,
+                   float4* li_backplate, DevStats*);
 // shadow_slot: index into Queues::counts (2 or 5, alternating per iteration) of the shadow-ray counter in use
 void launch_trace(const LaunchCfg&, const SceneDev&, const PathState&, const Queues&, int shadow_slot, float tmin, float tmax, DevStats*);
 void launch_shade(const LaunchCfg&, const FrameDev&, const SceneDev&, const PathState&, const Queues&, int shadow_slot, bool fast);
 // peer-frame flags (api.cu fovpt_peer_frame_*): raise *flag to seq / wait until flags[0..count) (except `skip`) reached seq
 void launch_peer_signal(const LaunchCfg&, uint32_t* flag, uint32_t seq);
 void launch_peer_wait(const LaunchCfg&, const uint32_t* flags, int count, int skip, uint32_t seq, uint32_t* err, long long timeout_clocks);
-void launch_resolve_li(const LaunchCfg&, const FrameDev&, int pass, unsigned row0, unsigned row1, unsigned pid_base,
-                       const uint8_t* needed, const PathState&, const float4* li_backplate, float4* li_color);
-void launch_resolve_px(const LaunchCfg&, const FrameDev&, const uint32_t* owner_map, const float4* li_color, const uint8_t* needed, bool fast);
+void launch_resolve_li(const LaunchCfg&, const FrameDev&, const ChunkTable&, const uint8_t* needed, const PathState&,
+                       const float4* li_backplate, float4* li_color);
+// accum_mirror: second destination of the accumulation value (the owner rank's shared buffer of a multi-GPU job) or null
+void launch_resolve_px(const LaunchCfg&, const FrameDev&, const uint32_t* owner_map, const float4* li_color, const uint8_t* needed,
+                       float4* accum_mirror, bool fast);
 void launch_probe_guides(const LaunchCfg&, const ProbeBlob&, uint16_t* gy, uint16_t* gx);
 void launch_primary_hits(const LaunchCfg&, const FrameDev&, const SceneDev&, int32_t* tri, float* tuv, float* dir);
 void launch_trace_query(const LaunchCfg&, const SceneDev&, const float* rays, size_t n, int mode, int32_t* tri, float* tuv);
+void launch_texture_probe(const LaunchCfg&, cudaTextureObject_t tex, const uint32_t* texels, int w, int h, const float2* uv, size_t n, int mode,
+                          float4* sw, float4* hw);
 void query_occupancy(int* extend_blocks_per_sm, int* shade_blocks_per_sm);
 
 }  // namespace fovpt

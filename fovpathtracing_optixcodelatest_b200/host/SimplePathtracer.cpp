@@ -57,11 +57,23 @@ void SampleRenderer::render()
     check(fovpt_sync(ctx));                                        // CUDA_SYNC_CHECK (:212)
 }
 
+void SampleRenderer::renderSubframes(int n)
+{
+    if (launchParams.frame.size.x == 0) return;
+    check(fovpt_render_frames(ctx, &launchParams, n));
+    check(fovpt_sync(ctx));
+}
+
 void SampleRenderer::render(sutil::CUDAOutputBuffer<uint32_t>& renderTarget)
 {
     launchParams.frame.frame_buffer = (uchar4*)renderTarget.map();  // SimplePathtracer.cpp:218-219
     render();
     renderTarget.unmap();
+    // The reference leaves frame_buffer pointing at the display buffer, which its main loop maps again every frame
+    // (main.cpp:417-423).  Here the target may be gone by the next render() / downloadPixels(): fall back to the
+    // buffer resize() allocated, and let the context forget the borrowed pointer.
+    launchParams.frame.frame_buffer = ownFrameBuffer;
+    fovpt_forget_frame(ctx);
 }
 
 void SampleRenderer::resize(const int2& newSize)

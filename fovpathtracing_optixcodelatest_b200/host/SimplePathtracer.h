@@ -32,6 +32,10 @@ public:
     /*! render one frame: the three foveation passes (or the single FOV_OFF pass), then a device sync
         (SimplePathtracer.cpp:77-214).  A no-op until resize() has been called (:81-82). */
     void render();
+    /*! extension: n successive render() calls of a progressive loop (subframe_index advancing, main.cpp:402-423) as ONE
+        submission -- the subframes share one wavefront (fovpt_render_frames); accumulation and frame buffer end up
+        bit-identical to calling render() n times */
+    void renderSubframes(int n);
     /*! render into an external display buffer (SimplePathtracer.cpp:216-226) */
     void render(sutil::CUDAOutputBuffer<uint32_t>& renderTarget);
     /*! resize the frame buffers; drops the accumulation (SimplePathtracer.cpp:228-274) */

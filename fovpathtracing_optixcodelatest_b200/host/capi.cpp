@@ -110,6 +110,7 @@ int fovpth_set_probe(SampleRenderer* r, int w, int h, const float* rgba, int bui
 }
 void* fovpth_launch_params(SampleRenderer* r) { return &r->launchParams; }      // the public member, as main.cpp uses it
 int fovpth_render(SampleRenderer* r) { GUARD(r->render()); }
+int fovpth_render_subframes(SampleRenderer* r, int n) { GUARD(r->renderSubframes(n)); }
 int fovpth_render_to_output_buffer(SampleRenderer* r, uint32_t* host_out)
 {
     GUARD({

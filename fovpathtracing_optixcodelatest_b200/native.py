@@ -31,7 +31,7 @@ class Stats(C.Structure):
         ("kernel_launches", C.c_uint64), ("frames", C.c_uint64), ("bvh_nodes", C.c_uint64), ("bvh_tris", C.c_uint64),
         ("bvh_build_ms", C.c_float), ("last_frame_ms", C.c_float), ("last_extend_ms", C.c_float),
         ("last_shade_ms", C.c_float), ("last_shadow_ms", C.c_float), ("last_raygen_ms", C.c_float),
-        ("last_resolve_ms", C.c_float),
+        ("last_resolve_ms", C.c_float), ("trace_launches", C.c_uint64),
     ]
 
     def asdict(self):
@@ -46,6 +46,7 @@ EXPORTS = [
     "fovpt_reset_stats", "fovpt_bvh_info", "fovpt_bvh_layout", "fovpt_bvh_read",
     "fovpt_peer_frame_create", "fovpt_peer_frame_open", "fovpt_peer_frame_signal", "fovpt_peer_frame_wait",
     "fovpt_peer_frame_release", "fovpt_peer_frame_close", "fovpt_set_kernel_timing",
+    "fovpt_render_frames", "fovpt_peer_frame_accum", "fovpt_forget_frame", "fovpt_texture_check",
 ]
 
 _lib = None
@@ -77,6 +78,10 @@ def load_library():
     L.fovpt_resize.argtypes = [vp, i32, i32, C.POINTER(vp), C.POINTER(vp)]
     L.fovpt_launch.argtypes = [vp, vp, C.c_size_t, C.c_uint, C.c_uint]
     L.fovpt_render_frame.argtypes = [vp, vp]
+    L.fovpt_render_frames.argtypes = [vp, vp, i32]
+    L.fovpt_forget_frame.argtypes = [vp]
+    L.fovpt_texture_check.argtypes = [vp, i32, vp, C.c_size_t, i32, vp, vp]
+    L.fovpt_peer_frame_accum.argtypes = [vp, i32, C.POINTER(vp)]
     L.fovpt_sync.argtypes = [vp]
     L.fovpt_download.argtypes = [vp, vp, C.c_size_t]
     L.fovpt_download_accum.argtypes = [vp, vp, C.c_size_t]
@@ -201,6 +206,10 @@ class Context:
     def render_frame(self, lp: LaunchParams):
         self._chk(self.L.fovpt_render_frame(self.h, C.byref(lp)))
 
+    def render_frames(self, lp: LaunchParams, n_subframes: int):
+        """n accumulated subframes traced as one wavefront (bit-identical to n render_frame calls)"""
+        self._chk(self.L.fovpt_render_frames(self.h, C.byref(lp), n_subframes))
+
     def sync(self):
         self._chk(self.L.fovpt_sync(self.h))
 
@@ -222,6 +231,13 @@ class Context:
         tri = np.zeros(len(r), np.int32); tuv = np.zeros((len(r), 3), np.float32)
         self._chk(self.L.fovpt_trace(self.h, _p(r), len(r), mode, _p(tri), _p(tuv)))
         return tri, tuv
+
+    def texture_check(self, texture_id, uv, mode=-1):
+        """(software fetch, hardware texture-unit fetch) of texture `texture_id` at uv[n,2]; both n x 4 float32"""
+        u = np.ascontiguousarray(uv, dtype=np.float32).reshape(-1, 2)
+        sw = np.zeros((len(u), 4), np.float32); hw = np.zeros((len(u), 4), np.float32)
+        self._chk(self.L.fovpt_texture_check(self.h, texture_id, _p(u), len(u), mode, _p(sw), _p(hw)))
+        return sw, hw
 
     def primary_hits(self, lp: LaunchParams, lw, lh):
         n = lw * lh
@@ -247,6 +263,12 @@ class Context:
         """contributor: map the owner's frame; returns the device pointer to put in LaunchParams.frame.frame_buffer"""
         buf = (C.c_ubyte * 128).from_buffer_copy(handle); ptr = C.c_void_p()
         self._chk(self.L.fovpt_peer_frame_open(self.h, buf, rank, C.byref(ptr)))
+        return ptr.value
+
+    def peer_frame_accum(self, mirror=True):
+        """device pointer of the shared float4 accumulation buffer; mirror: every rank stores its pixels' accumulation there"""
+        ptr = C.c_void_p()
+        self._chk(self.L.fovpt_peer_frame_accum(self.h, 1 if mirror else 0, C.byref(ptr)))
         return ptr.value
 
     def peer_frame_signal(self):

@@ -99,6 +99,14 @@ class SampleRenderer:
         self.ctx.render_frame(self.launchParams)
         self.ctx.sync()                                    # CUDA_SYNC_CHECK, :212
 
+    def renderSubframes(self, n, sync=True):
+        """n successive render() calls of a progressive loop as one submission (include/fovpt.h fovpt_render_frames)"""
+        if self.launchParams.frame.size_x == 0:
+            return
+        self.ctx.render_frames(self.launchParams, int(n))
+        if sync:
+            self.ctx.sync()
+
     def render_async(self):
         if self.launchParams.frame.size_x == 0:
             return

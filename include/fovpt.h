@@ -59,6 +59,7 @@ typedef struct fovpt_stats {
     float    bvh_build_ms;
     float    last_frame_ms;    /* CUDA-event time of the last fovpt_render_frame / fovpt_launch         */
     float    last_extend_ms, last_shade_ms, last_shadow_ms, last_raygen_ms, last_resolve_ms;
+    uint64_t trace_launches;   /* launches of the traversal kernel since the last reset (roofline: bytes per launch) */
 } fovpt_stats;
 
 /* -- context: SampleRenderer::initOptix/createContext, SimplePathtracer.cpp:310-340.  `stream` is a
@@ -100,11 +101,21 @@ int fovpt_launch(fovpt_ctx*, const void* launch_params248, size_t size, unsigned
  *    configured schedule share one wavefront; advances frame.subframe_index in the caller's blob
  *    exactly as render() does.  Asynchronous; pair with fovpt_sync (CUDA_SYNC_CHECK, :212). */
 int fovpt_render_frame(fovpt_ctx*, void* launch_params248_inout);
+/* -- n_subframes successive render() calls of a progressive host loop (main.cpp:402-423 with frame.subframe_index
+ *    advancing, PT_original/main.cpp:259,286) as ONE submission: the subframes share one wavefront -- path = (subframe,
+ *    launch index, sample), seeds depend only on those (deviceProgram.cu:411) -- so the late, thin bounces of all
+ *    subframes fill the machine together, and the per-frame accumulation (fovpt_config.accumulate) is replayed per pixel
+ *    in subframe order.  Accumulation and frame buffer are bit-identical to n_subframes calls of fovpt_render_frame;
+ *    only the intermediate RGBA8 frames are never materialised.  Batches larger than the path budget are split. */
+int fovpt_render_frames(fovpt_ctx*, void* launch_params248_inout, int n_subframes);
 int fovpt_sync(fovpt_ctx*);
 
 /* -- SampleRenderer::downloadPixels (SimplePathtracer.cpp:276-280): blocking D2H of npix RGBA8
  *    pixels from the frame buffer most recently rendered into. */
 int fovpt_download(fovpt_ctx*, uint32_t* dst, size_t npix);
+/* the frame buffer of the last render was borrowed (render(CUDAOutputBuffer&), SimplePathtracer.cpp:216-226) and is about
+ * to go away: fovpt_download falls back to the buffers of fovpt_resize instead of reading freed memory. */
+int fovpt_forget_frame(fovpt_ctx*);
 int fovpt_download_accum(fovpt_ctx*, float* dst_rgba, size_t npix);
 
 /* -- ray queries (optixTrace equivalents, deviceProgram.cu:196-248), for parity tests and tools.
@@ -112,6 +123,11 @@ int fovpt_download_accum(fovpt_ctx*, float* dst_rgba, size_t npix);
  *    triangle id or -1, tuv = t,u,v.  mode 1: any front-facing hit -> tri = 1/0.  modes 2 / 3: as 0 / 1
  *    but tuv = (inner nodes visited, leaves visited, triangles tested) -- BVH-quality introspection. */
 int fovpt_trace(fovpt_ctx*, const float* rays, size_t n, int mode, int32_t* tri, float* tuv);
+/* texture-filter cross-check (test hook): fetches texture `texture_id` of the committed scene at n (u,v) pairs twice -- hw:
+ * through a cudaTextureObject_t built exactly like the reference's (createTextures, SimplePathtracer.cpp:748-799; fetch
+ * deviceProgram.cu:655-665), sw: through the software fetch (mode < 0: the product's own; modes 0..4: candidate weight
+ * quantisations used to pin the definition).  Both outputs are n x RGBA floats. */
+int fovpt_texture_check(fovpt_ctx*, int texture_id, const float* uv, size_t n, int mode, float* sw_rgba, float* hw_rgba);
 /* sample-0 primary hit of every launch index of one launch (host outputs, lw*lh entries):
  * tri = global triangle id, -1 miss, -2 outside the ring; tuv = t,u,v; dir = camera direction. */
 int fovpt_primary_hits(fovpt_ctx*, const void* launch_params248, unsigned lw, unsigned lh,
@@ -137,6 +153,11 @@ int fovpt_set_tile_owner(fovpt_ctx*, int tile_size, int tiles_x, int tiles_y, co
 typedef struct fovpt_peer_handle { unsigned char opaque[128]; } fovpt_peer_handle;
 int fovpt_peer_frame_create(fovpt_ctx*, size_t npix, int world, int owner_rank, fovpt_peer_handle* handle_out, uint32_t** frame_out);
 int fovpt_peer_frame_open(fovpt_ctx*, const fovpt_peer_handle*, int rank, uint32_t** frame_out);
+/* the shared allocation also holds a float4 accumulation buffer (north_star: "gather of the accumulation buffer"): with
+ * mirror != 0 (the default while a peer frame is open) every rank's resolve kernel stores the accumulation value of its own
+ * pixels into it next to the RGBA8 pixel, so after fovpt_peer_frame_wait the owner holds the complete float image of the
+ * N-GPU job (fovpt_download_accum reads it).  *accum_out (may be NULL) receives the device pointer. */
+int fovpt_peer_frame_accum(fovpt_ctx*, int mirror, float** accum_out);
 int fovpt_peer_frame_signal(fovpt_ctx*);
 int fovpt_peer_frame_wait(fovpt_ctx*);
 int fovpt_peer_frame_release(fovpt_ctx*);

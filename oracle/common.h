@@ -9,6 +9,7 @@
 #include <thread>
 #include <vector>
 
+#include "../include/fovpt_exact.h"
 #include "bvh.h"
 #include "orc_api.h"
 
@@ -24,28 +25,12 @@ struct HostMesh {
     int                   texture_id = -1;
 };
 
-// RGBA8 texture, normalized coordinates, wrap addressing, bilinear filter, values /255, no sRGB
-// decode, no mip maps: the sampler state of SimplePathtracer.cpp:775-789.  (The GPU's texture
-// unit quantises the filter weights to 8 fractional bits; this software definition keeps full
-// float weights -- the product kernel implements this same definition, see DESIGN.md.)
+// RGBA8 texture, normalized coordinates, wrap addressing, bilinear filter, normalized float read, no sRGB
+// decode, no mip maps: the sampler state of SimplePathtracer.cpp:775-789, evaluated with the texture unit's
+// fixed-point arithmetic as pinned against a real cudaTextureObject_t (include/fovpt_exact.h).
 inline void tex_bilinear(const HostTexture& t, float x, float y, float out[4])
 {
-    float xb = x * (float)t.w - 0.5f, yb = y * (float)t.h - 0.5f;
-    float fx = floorf(xb), fy = floorf(yb);
-    float a = xb - fx, b = yb - fy;
-    auto wrap = [](long long i, int n) { long long m = i % n; return (int)(m < 0 ? m + n : m); };
-    int x0 = wrap((long long)fx, t.w), x1 = wrap((long long)fx + 1, t.w);
-    int y0 = wrap((long long)fy, t.h), y1 = wrap((long long)fy + 1, t.h);
-    uint32_t p00 = t.px[(size_t)y0 * t.w + x0], p10 = t.px[(size_t)y0 * t.w + x1];
-    uint32_t p01 = t.px[(size_t)y1 * t.w + x0], p11 = t.px[(size_t)y1 * t.w + x1];
-    float w00 = (1.f - a) * (1.f - b), w10 = a * (1.f - b), w01 = (1.f - a) * b, w11 = a * b;
-    for (int c = 0; c < 4; ++c) {
-        float v00 = (float)((p00 >> (8 * c)) & 255u) * (1.0f / 255.0f);
-        float v10 = (float)((p10 >> (8 * c)) & 255u) * (1.0f / 255.0f);
-        float v01 = (float)((p01 >> (8 * c)) & 255u) * (1.0f / 255.0f);
-        float v11 = (float)((p11 >> (8 * c)) & 255u) * (1.0f / 255.0f);
-        out[c] = w00 * v00 + w10 * v10 + w01 * v01 + w11 * v11;
-    }
+    fx_tex_bilinear_rgba8(t.px.data(), t.w, t.h, x, y, out);
 }
 
 inline int resolve_threads(int req)

@@ -23,6 +23,8 @@ RMSE_TOL = 1e-6        # relative MSE of the float accumulation buffer vs the or
 RMSE_TOL_DEEP = 2e-4   # depth-8 paths: one last-ulp difference between CUDA's and glibc's sinf/cosf/powf can send a
                        # bounce to a different triangle, which changes that one sample completely (north_star: 1e-3)
 MEAN_TOL = 1e-5        # relative difference of the frame's mean radiance
+TEX_TOL = 1.0 / 255    # |software texture fetch - texture unit| per channel ...
+TEX_IDENTICAL = 0.99   # ... and the share of fetches that must be bit-identical to the texture unit
 
 
 def close_fraction(a, g, rel=1e-4):
@@ -786,3 +788,89 @@ def test_peer_frame_missing_rank_times_out(gpu):
     res = _run_peer_job(world, owner, w, h, ri, ro, 1, never_signal=True, env={"FOVPT_PEER_TIMEOUT_MS": "300"})
     assert res[0][1] is not None and "rank 1 did not deliver" in res[0][1], res[0][1]
     assert res[1][1] is None
+
+
+# ------------------------------------------------------------------------------------------- subframe batches
+@pytest.mark.parametrize("mode", ["ext", "sv5_accumulate", "ext_filter_tiles", "uniform"])
+def test_subframe_batch_is_bit_identical_to_successive_frames(gpu, port, mode):
+    """fovpt_render_frames(n): n accumulated subframes traced as ONE wavefront.  Accumulation buffer, RGBA8 frame, sample and ray
+    counts and the caller's subframe_index must equal n successive fovpt_render_frame calls bit for bit -- in the extension
+    mode every ring accumulates, in sv5's literal schedule only the periphery does (mid / fovea reseed with subframe 0 and
+    redraw, SimplePathtracer.cpp:162,174,196), with the bilinear reconstruction filter and a tile partition, and for FOV_OFF."""
+    w, h, ri, ro, n = 384, 216, 30, 96, 5
+    kw = dict(max_depth=6, accumulate=1, seed_all_passes_with_subframe=1)
+    if mode == "sv5_accumulate":
+        kw = dict(max_depth=4, accumulate=1, seed_all_passes_with_subframe=0)
+    elif mode == "ext_filter_tiles":
+        kw["filter"] = 1
+    elif mode == "uniform":
+        kw.update(foveated=0, spp_uniform=3)
+    sc = scenes.atrium(detail=0.2)
+    out = []
+    for batched in (False, True):
+        r, o, lp, _, _ = make_pair(gpu, port, sc, scenes.SPONZA_CAMERA, w, h, scenes.sky_probe(64, 32, 2), ri, ro, **kw)
+        o.close()
+        if mode == "ext_filter_tiles":
+            owner, _ = partition.partition(w, h, (w // 2, h // 2), ri, ro, 3, 32)
+            r.ctx.set_tile_owner(32, owner, 1)
+        r.launchParams.frame.subframe_index = 2            # start in the middle of a sequence: the first layer already lerps
+        r.render()                                          # (and there is a previous accumulation value to lerp against)
+        launches_before = r.stats()["kernel_launches"]
+        if batched:
+            r.renderSubframes(n)
+        else:
+            for _ in range(n):
+                r.render()
+        st = r.stats()
+        out.append((r.downloadAccum().copy(), r.downloadPixels().copy(), st["samples"], st["radiance_rays"], st["shadow_rays"],
+                    r.launchParams.frame.subframe_index, st["kernel_launches"] - launches_before))
+        r.close()
+    (a0, f0, s0, rr0, sr0, i0, l0), (a1, f1, s1, rr1, sr1, i1, l1) = out
+    assert (bits(a0) == bits(a1)).all(), f"{(bits(a0) != bits(a1)).any(axis=2).sum()} pixels of the accumulation buffer differ"
+    assert (f0 == f1).all()
+    assert (s0, rr0, sr0, i0) == (s1, rr1, sr1, i1) and i0 == 3 + n
+    assert l1 * n == l0                                     # one wavefront instead of n
+
+
+def test_subframe_batch_larger_than_the_path_budget_is_split(gpu, port):
+    """a batch that does not fit the path budget (48 Mi paths in flight) is cut into several wavefronts; same bits"""
+    w, h = 1024, 1024
+    sc = scenes.cornell_box()
+    out = []
+    for batched in (False, True):
+        r, o, lp, _, _ = make_pair(gpu, port, sc, scenes.CORNELL_CAMERA, w, h, scenes.constant_probe(16, 8, 2.5), 74, 241,
+                                   foveated=0, spp_uniform=20, max_depth=2, accumulate=1, seed_all_passes_with_subframe=1)
+        o.close()
+        if batched:
+            r.renderSubframes(5)                            # 5 x 21 M paths: two wavefronts of 2 subframes and one of 1
+        else:
+            for _ in range(5):
+                r.render()
+        out.append((r.downloadAccum().copy(), r.downloadPixels().copy()))
+        r.close()
+    assert (bits(out[0][0]) == bits(out[1][0])).all() and (out[0][1] == out[1][1]).all()
+
+
+# ------------------------------------------------------------------------------------------- texture unit
+@pytest.mark.parametrize("shape", [(53, 37), (64, 64), (600, 1000), (1024, 2048), (1, 7)])
+def test_software_texture_fetch_matches_the_texture_unit(gpu, shape):
+    """R-TEX: the reference samples albedo through a cudaTextureObject_t (linear filter, wrap, normalised coordinates,
+    normalised-float read, SimplePathtracer.cpp:748-799, fetch deviceProgram.cu:655-665).  The product fetches in software
+    with the texture unit's fixed-point arithmetic (include/fovpt_exact.h fx_tex_bilinear_rgba8); this compares it BIT FOR BIT
+    with a REAL texture object built with the reference's descriptor on this GPU: wrapped, negative, texel-centre and
+    texel-corner coordinates of power-of-two, odd-sized and degenerate random RGBA8 textures."""
+    rng = np.random.default_rng(11)
+    sc = scenes.cornell_box()
+    h, w = shape
+    sc.textures.append(rng.integers(0, 2 ** 32, shape, dtype=np.uint64).astype(np.uint32))
+    ctx = gpu.native.Context(0); ctx.upload_scene(sc)
+    uv = np.concatenate([rng.uniform(-2.0, 3.0, (150000, 2)), rng.uniform(0.0, 1.0, (150000, 2)), rng.uniform(-300.0, 300.0, (20000, 2)),
+                         (rng.integers(-40, 80, (20000, 2)) + 0.5) / np.array([w, h], np.float64),             # texel centres
+                         rng.integers(-40, 80, (20000, 2)) / np.array([w, h], np.float64)]).astype(np.float32)  # texel corners
+    sw, hw = ctx.texture_check(0, uv)
+    err = np.abs(sw - hw)
+    same = (bits(sw) == bits(hw)).all(axis=1)
+    print("texture unit vs software fetch %s: bit-identical %.6f, max abs err %.3g" % (shape, same.mean(), err.max()))
+    assert err.max() <= TEX_TOL
+    assert same.mean() >= TEX_IDENTICAL
+    ctx.close()

@@ -887,7 +887,7 @@ int fovpt_bvh_layout(fovpt_ctx* c, int* wide, int* node_bytes)
 {
     if (!c) return 1;
     if (wide) *wide = kBvhWide;
-    if (node_bytes) *node_bytes = kBvhWide == 8 ? 96 : 64;
+    if (node_bytes) *node_bytes = 64;
     return 0;
 }
 
@@ -895,7 +895,7 @@ int fovpt_bvh_read(fovpt_ctx* c, void* nodes64, uint32_t* sorted_tri_ids)
 {
     if (!c || !c->committed) return 1;
     cudaSetDevice(c->device);
-    if (nodes64 && c->bvh.n_nodes) CU(cudaMemcpy(nodes64, c->bvh.nodes, (size_t)c->bvh.n_nodes * (kBvhWide == 8 ? 96 : 64), cudaMemcpyDeviceToHost));
+    if (nodes64 && c->bvh.n_nodes) CU(cudaMemcpy(nodes64, c->bvh.nodes, (size_t)c->bvh.n_nodes * 64, cudaMemcpyDeviceToHost));
     if (sorted_tri_ids && c->bvh.n_tris) CU(cudaMemcpy(sorted_tri_ids, c->bvh.sorted_ids, (size_t)c->bvh.n_tris * 4, cudaMemcpyDeviceToHost));
     return 0;
 }

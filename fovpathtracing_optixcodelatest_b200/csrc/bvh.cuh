@@ -14,7 +14,8 @@
 //           Two sectors per node instead of four: the traversal kernels are bound by L1 sector
 //           throughput (profiles/), so bytes per visited node are what buys speed.
 //   tris  : 48 B per triangle in leaf (Morton) order = 3 x float4
-//             (v0.xyz, bits(global id)), (e1.xyz, bits(mesh id)), (e2.xyz, 0)      [fx_make_tri of fovpt_exact.h]
+//             (v0.xyz, bits(global id)), (v1.xyz, bits(mesh id)), (v2.xyz, 0)      [the vertices, unmodified: the
+//             watertight test of fovpt_exact.h needs bit-identical end points on both sides of a shared edge]
 // Algorithmic bytes per ray are counted on the oracle's canonical binary tree:
 // 64 per node visit + 48 per triangle test + 48 (ray in, hit out); see DESIGN.md section 5.
 #pragma once
@@ -23,15 +24,11 @@
 
 #include "../../include/fovpt_exact.h"
 
-#ifndef FOVPT_WIDE
-#define FOVPT_WIDE 4          // branching factor of the device BVH: 4 (default) or 8 (compressed wide nodes; measured
-                              // 16 % slower on C3: octant-ordered visiting and no pop-time culling cost more node visits
-                              // than the wider nodes save)
-#endif
-
 namespace fovpt {
 
-constexpr int kBvhWide = FOVPT_WIDE;
+constexpr int kBvhWide = 4;   // branching factor of the device BVH (an 8-wide compressed layout was built and measured in round 1:
+                              // 16 % slower on C3 -- octant-ordered visiting without pop-time culling costs more node visits
+                              // than the wider nodes save, DESIGN.md section 6 -- and removed in round 2)
 
 struct DeviceBvh {
     const uint4*  nodes = nullptr;
@@ -121,7 +118,8 @@ constexpr int kClosest = 0, kAny = 1, kMixed = 2;
 
 template <int MODE>
 struct Traversal {
-    float3 o, d, idir, ood;
+    float3 o, idir, ood;
+    fx_shear sh;            // per-ray constants of the watertight triangle test (fovpt_exact.h); the direction itself is not kept
     float tmin, tmax;
     float best_t, best_u, best_v;
     uint32_t best_gid, best_k;
@@ -134,9 +132,11 @@ struct Traversal {
     {
         // tmax finite: unused child slots sit at +inf.  The caller guarantees tmin >= 0 (fovpt_set_config enforces it, the
         // query kernels clamp): every entry distance is then >= 0 and its bit pattern orders like the float (node_step keys).
-        o = o_; d = d_; tmin = tmin_; tmax = fminf(tmax_, 3.0e38f);
-        idir = make_float3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
+        o = o_; tmin = tmin_; tmax = fminf(tmax_, 3.0e38f);
+        idir = make_float3(safe_rcp(d_.x), safe_rcp(d_.y), safe_rcp(d_.z));
         ood = make_float3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
+        const fx_vec3 D = {d_.x, d_.y, d_.z};
+        sh = fx_shear_init(D);
         best_t = __int_as_float(0x7f800000); best_u = best_v = 0.f; best_gid = 0xffffffffu; best_k = 0;
         cur = 0; sp = 0;
     }
@@ -220,7 +220,8 @@ struct Traversal {
     __device__ __forceinline__ void leaf_step(const DeviceBvh& bvh, const RayStack& stack, uint32_t nmax)
     {
         const uint32_t first = leaf_first(cur), count = leaf_count(cur);
-        const fx_vec3 O = {o.x, o.y, o.z}, D = {d.x, d.y, d.z};
+        const fx_vec3 O = {o.x, o.y, o.z};
+        const fx_basis rb = fx_shear_basis(sh);                // once per step, not per triangle
         bool occluded = false;
         for (uint32_t i = 0; i < nmax; ++i) {
             if (i < count) {
@@ -228,10 +229,10 @@ struct Traversal {
                 const float4 a = ldg4(tp), b = ldg4(tp + 1), c = ldg4(tp + 2);
                 fx_tri tr;
                 tr.v0.x = a.x; tr.v0.y = a.y; tr.v0.z = a.z;
-                tr.e1.x = b.x; tr.e1.y = b.y; tr.e1.z = b.z;
-                tr.e2.x = c.x; tr.e2.y = c.y; tr.e2.z = c.z;
+                tr.v1.x = b.x; tr.v1.y = b.y; tr.v1.z = b.z;
+                tr.v2.x = c.x; tr.v2.y = c.y; tr.v2.z = c.z;
                 float t, u, v;
-                const int side = fx_ray_tri_nb(O, D, tr, &t, &u, &v);
+                const int side = fx_ray_tri_wt(O, rb, tr, &t, &u, &v);
                 const bool in_range = t > tmin && t < tmax;
                 if (MODE != kClosest) occluded = occluded || (side == 1 && in_range);
                 if (MODE != kAny) {
@@ -256,141 +257,7 @@ struct Traversal {
     }
 };
 
-// ------------------------------------------------------------------ 8-wide compressed nodes (FOVPT_WIDE == 8)
-// 96 B per node = 6 x uint4 (3 sectors, three 256-bit loads), after Ylitie, Karras, Laine 2017:
-//   n0 = (bits(p.x), bits(p.y), bits(p.z), e.x | e.y << 8 | e.z << 16 | imask << 24)
-//   n1 = (child_base, tri_base, meta[0..3], meta[4..7])
-//   n2 = (qlo.x[0..3], qlo.x[4..7], qhi.x[0..3], qhi.x[4..7])    n3: same for y    n4: same for z    n5 = 0
-// Child boxes are 8-bit planes on the grid p + q * 2^(e-127), snapped outward.  imask bit s: slot s holds an inner
-// node; inner children sit consecutively from child_base in slot order.  meta[s] = 0 (empty) |
-// 0b001_sssss with sssss = 24 + s (inner) | unary(triangle count 1..3) << 5 | offset from tri_base (leaf); a node's
-// leaf triangles are consecutive from tri_base (at most 24).  Slots are assigned at build time so that slot number ~
-// octant of the child relative to the node centre; XOR-ing with the inverted ray octant turns "highest set bit first"
-// into an approximate front-to-back order without sorting distances.
-// Per-ray state: a node group (child_base, hit bits 24..31 | imask) and a triangle group (tri_base, 24 hit bits); the
-// stack holds node groups only, so a node step pushes at most ONE entry.  A leaf step tests ONE triangle.
-template <int MODE>
-struct Traversal8 {
-    float3 o, d, idir, ood;
-    float tmin, tmax;
-    float best_t, best_u, best_v;
-    uint32_t best_gid, best_k;
-    uint2 ng, tg;
-    int sp;
-    uint32_t octinv4;                 // (7 - ray octant) replicated into the four bytes
-    bool any = (MODE == kAny);
-
-    __device__ __forceinline__ bool is_any() const { return MODE == kMixed ? any : MODE == kAny; }
-    __device__ __forceinline__ void begin(float3 o_, float3 d_, float tmin_, float tmax_)
-    {
-        o = o_; d = d_; tmin = tmin_; tmax = fminf(tmax_, 3.0e38f);
-        idir = make_float3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
-        ood = make_float3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
-        best_t = __int_as_float(0x7f800000); best_u = best_v = 0.f; best_gid = 0xffffffffu; best_k = 0;
-        const uint32_t oct = (idir.x < 0.f ? 4u : 0u) | (idir.y < 0.f ? 2u : 0u) | (idir.z < 0.f ? 1u : 0u);
-        octinv4 = (7u - oct) * 0x01010101u;
-        ng = make_uint2(0u, 0x80000000u);          // "the root is child 0 of a virtual parent"
-        tg = make_uint2(0u, 0u);
-        sp = 0;
-    }
-    __device__ __forceinline__ void reset() { ng = make_uint2(0u, 0u); tg = make_uint2(0u, 0u); sp = 0; }
-    __device__ __forceinline__ bool found() const { return best_gid != 0xffffffffu; }
-    __device__ __forceinline__ bool at_leaf() const { return tg.y != 0u; }
-    __device__ __forceinline__ bool at_node() const { return tg.y == 0u && (ng.y & 0xff000000u) != 0u; }
-    __device__ __forceinline__ bool done() const { return (tg.y | (ng.y & 0xff000000u)) == 0u; }
-    __device__ __forceinline__ uint32_t leaf_work() const { return 1u; }
-    // nothing pending in registers: continue with the youngest deferred node group
-    __device__ __forceinline__ void settle(const RayStack& stack)
-    {
-        if ((tg.y | (ng.y & 0xff000000u)) == 0u) {
-            if (sp > 0) { const int2 e = stack.get(--sp); ng = make_uint2((uint32_t)e.x, (uint32_t)e.y); }
-            else ng.y = 0u;
-        }
-    }
-
-    __device__ __forceinline__ void node_step(const DeviceBvh& bvh, const RayStack& stack)
-    {
-        const uint32_t bit = 31u - (uint32_t)__clz((int)ng.y);
-        ng.y &= ~(1u << bit);
-        if (ng.y & 0xff000000u) stack.put(sp++, make_int2((int)ng.x, (int)ng.y));
-        const uint32_t slot = (bit - 24u) ^ (octinv4 & 7u);
-        const uint32_t node = ng.x + (uint32_t)__popc(ng.y & 0xffu & ((1u << slot) - 1u));
-        const uint4* np = bvh.nodes + 6 * (size_t)node;
-        const u8x A = ldg256(np), B = ldg256(np + 2), C = ldg256(np + 4);      // A = (n0, n1), B = (n2, n3), C = (n4, n5)
-        const float tlimit = is_any() ? tmax : fminf(tmax, best_t);
-        const float ax = __uint_as_float((A.a.w & 0xffu) << 23) * idir.x;
-        const float ay = __uint_as_float(((A.a.w >> 8) & 0xffu) << 23) * idir.y;
-        const float az = __uint_as_float(((A.a.w >> 16) & 0xffu) << 23) * idir.z;
-        const float bx = fmaf(__uint_as_float(A.a.x), idir.x, -ood.x);
-        const float by = fmaf(__uint_as_float(A.a.y), idir.y, -ood.y);
-        const float bz = fmaf(__uint_as_float(A.a.z), idir.z, -ood.z);
-        const bool px = idir.x >= 0.f, py = idir.y >= 0.f, pz = idir.z >= 0.f;
-        uint32_t hitmask = 0u;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            const uint32_t lx = half ? B.a.y : B.a.x, hx = half ? B.a.w : B.a.z;
-            const uint32_t ly = half ? B.b.y : B.b.x, hy = half ? B.b.w : B.b.z;
-            const uint32_t lz = half ? C.a.y : C.a.x, hz = half ? C.a.w : C.a.z;
-            const uint32_t nxw = px ? lx : hx, fxw = px ? hx : lx;
-            const uint32_t nyw = py ? ly : hy, fyw = py ? hy : ly;
-            const uint32_t nzw = pz ? lz : hz, fzw = pz ? hz : lz;
-            const uint32_t meta4 = half ? A.b.w : A.b.z;
-            const uint32_t inner4 = ((meta4 & (meta4 << 1)) & 0x10101010u) >> 4;          // 0x01 per inner slot
-            const uint32_t bit_index4 = (meta4 ^ (octinv4 & (inner4 * 0xffu))) & 0x1f1f1f1fu;
-            const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-#define FOVPT_CHILD8(J)                                                                                                   \
-            {                                                                                                             \
-                float tn, tf;                                                                                             \
-                FOVPT_SLAB(J, tn, tf);                                                                                    \
-                if (tn <= tf) hitmask |= ((child_bits4 >> (8 * (J))) & 0xffu) << ((bit_index4 >> (8 * (J))) & 0xffu);     \
-            }
-            FOVPT_CHILD8(0) FOVPT_CHILD8(1) FOVPT_CHILD8(2) FOVPT_CHILD8(3)
-#undef FOVPT_CHILD8
-        }
-        ng = make_uint2(A.b.x, (hitmask & 0xff000000u) | (A.a.w >> 24));
-        tg = make_uint2(A.b.y, hitmask & 0x00ffffffu);
-        settle(stack);
-    }
-
-    __device__ __forceinline__ void leaf_step(const DeviceBvh& bvh, const RayStack& stack, uint32_t /*nmax*/)
-    {
-        const uint32_t idx = 31u - (uint32_t)__clz((int)tg.y);
-        tg.y &= ~(1u << idx);
-        const uint32_t slot = tg.x + idx;
-        const float4* tp = bvh.tris + 3 * (size_t)slot;
-        const float4 a = ldg4(tp), b = ldg4(tp + 1), c = ldg4(tp + 2);
-        fx_tri tr;
-        tr.v0.x = a.x; tr.v0.y = a.y; tr.v0.z = a.z;
-        tr.e1.x = b.x; tr.e1.y = b.y; tr.e1.z = b.z;
-        tr.e2.x = c.x; tr.e2.y = c.y; tr.e2.z = c.z;
-        const fx_vec3 O = {o.x, o.y, o.z}, D = {d.x, d.y, d.z};
-        float t, u, v;
-        const int side = fx_ray_tri_nb(O, D, tr, &t, &u, &v);
-        const bool in_range = t > tmin && t < tmax;
-        if (MODE != kClosest && is_any() && side == 1 && in_range) { best_gid = 0; reset(); return; }
-        if (MODE != kAny) {
-            const uint32_t gid = (uint32_t)__float_as_int(a.w);
-            if (!is_any() && side != 0 && in_range && fx_hit_better(t, gid, best_t, best_gid)) {
-                best_t = t; best_gid = gid; best_k = slot; best_u = u; best_v = v;
-            }
-        }
-        settle(stack);
-    }
-
-    __device__ __forceinline__ void run(const DeviceBvh& bvh, const RayStack& stack)
-    {
-        while (!done()) {
-            if (at_leaf()) leaf_step(bvh, stack, 1u);
-            else node_step(bvh, stack);
-        }
-    }
-};
-
-#if FOVPT_WIDE == 4
 #define FOVPT_TRAV(MODE) Traversal<MODE>
-#else
-#define FOVPT_TRAV(MODE) Traversal8<MODE>
-#endif
 
 __device__ __forceinline__ bool trace_closest(const DeviceBvh& bvh, float3 o, float3 d, float tmin, float tmax, HitRec& out)
 {

@@ -65,8 +65,8 @@ __global__ void k_tri_setup(const float* __restrict__ vtx, const uint32_t* __res
         fx_vec3 C = {vtx[3 * (size_t)ic], vtx[3 * (size_t)ic + 1], vtx[3 * (size_t)ic + 2]};
         fx_tri t = fx_make_tri(A, B, C);
         tri_rec[3 * (size_t)i + 0] = make_float4(t.v0.x, t.v0.y, t.v0.z, __int_as_float((int)i));
-        tri_rec[3 * (size_t)i + 1] = make_float4(t.e1.x, t.e1.y, t.e1.z, __int_as_float((int)tri_mesh[i]));   // mesh id rides along: saves the shading kernel a dependent load
-        tri_rec[3 * (size_t)i + 2] = make_float4(t.e2.x, t.e2.y, t.e2.z, 0.f);
+        tri_rec[3 * (size_t)i + 1] = make_float4(t.v1.x, t.v1.y, t.v1.z, __int_as_float((int)tri_mesh[i]));   // mesh id rides along: saves the shading kernel a dependent load
+        tri_rec[3 * (size_t)i + 2] = make_float4(t.v2.x, t.v2.y, t.v2.z, 0.f);
         lo[0] = fminf(A.x, fminf(B.x, C.x)); hi[0] = fmaxf(A.x, fmaxf(B.x, C.x));
         lo[1] = fminf(A.y, fminf(B.y, C.y)); hi[1] = fmaxf(A.y, fmaxf(B.y, C.y));
         lo[2] = fminf(A.z, fminf(B.z, C.z)); hi[2] = fmaxf(A.z, fmaxf(B.z, C.z));
@@ -455,151 +455,6 @@ __global__ void k_collapse4(const CollapseItem* __restrict__ items_in, CollapseI
     }
 }
 
-// ------------------------------------------------------------------ 8-wide collapse (compressed wide BVH)
-// Node layout and traversal: bvh.cuh.  A wide node absorbs binary nodes (largest surface area first) until it
-// has 8 children or only leaves (<= 3 triangles) are left; children are then assigned to the 8 slots so that
-// slot number ~ octant of the child's centre relative to the node's centre (greedy on the dot product with the
-// slot's sign vector), which is what lets the traversal visit children front to back by XOR-ing the slot
-// number with the ray's direction octant instead of sorting distances (Ylitie et al. 2017).
-constexpr int kLeafMax8 = 3;
-
-__device__ __forceinline__ void write_node8(uint4* __restrict__ o, const float4 lo[8], const float4 hi[8], const bool used[8],
-                                            const uint32_t meta[8], uint32_t imask, uint32_t child_base, uint32_t tri_base, float pad)
-{
-    float p[3] = {3.0e38f, 3.0e38f, 3.0e38f}, top[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-    for (int j = 0; j < 8; ++j) {
-        if (!used[j]) continue;
-        p[0] = fminf(p[0], lo[j].x - pad); p[1] = fminf(p[1], lo[j].y - pad); p[2] = fminf(p[2], lo[j].z - pad);
-        top[0] = fmaxf(top[0], hi[j].x + pad); top[1] = fmaxf(top[1], hi[j].y + pad); top[2] = fmaxf(top[2], hi[j].z + pad);
-    }
-    uint32_t ebits[3]; double scale[3];
-    for (int a = 0; a < 3; ++a) {
-        const double ext = (double)top[a] - (double)p[a];
-        int e = 0;
-        (void)frexp(fmax(ext, 1e-30) / 255.0, &e);
-        e = max(-120, min(e, 120));
-        ebits[a] = (uint32_t)(e + 127);
-        scale[a] = ldexp(1.0, e);
-    }
-    uint32_t qlo[3][2] = {{0, 0}, {0, 0}, {0, 0}}, qhi[3][2] = {{0, 0}, {0, 0}, {0, 0}};
-    for (int j = 0; j < 8; ++j) {
-        uint32_t l3[3] = {255u, 255u, 255u}, h3[3] = {0u, 0u, 0u};          // unused slot: inverted box
-        if (used[j]) {
-            const float cl[3] = {lo[j].x - pad, lo[j].y - pad, lo[j].z - pad}, ch[3] = {hi[j].x + pad, hi[j].y + pad, hi[j].z + pad};
-            for (int a = 0; a < 3; ++a) {
-                int ql = (int)floor(((double)cl[a] - (double)p[a]) / scale[a]);
-                int qh = (int)ceil(((double)ch[a] - (double)p[a]) / scale[a]);
-                ql = max(0, min(ql, 255)); qh = max(0, min(qh, 255));
-                while (ql > 0 && (double)p[a] + ql * scale[a] > (double)cl[a]) --ql;
-                while (qh < 255 && (double)p[a] + qh * scale[a] < (double)ch[a]) ++qh;
-                l3[a] = (uint32_t)ql; h3[a] = (uint32_t)qh;
-            }
-        }
-        for (int a = 0; a < 3; ++a) { qlo[a][j >> 2] |= l3[a] << (8 * (j & 3)); qhi[a][j >> 2] |= h3[a] << (8 * (j & 3)); }
-    }
-    const uint32_t m0 = meta[0] | (meta[1] << 8) | (meta[2] << 16) | (meta[3] << 24);
-    const uint32_t m1 = meta[4] | (meta[5] << 8) | (meta[6] << 16) | (meta[7] << 24);
-    o[0] = make_uint4(__float_as_uint(p[0]), __float_as_uint(p[1]), __float_as_uint(p[2]), ebits[0] | (ebits[1] << 8) | (ebits[2] << 16) | (imask << 24));
-    o[1] = make_uint4(child_base, tri_base, m0, m1);
-    o[2] = make_uint4(qlo[0][0], qlo[0][1], qhi[0][0], qhi[0][1]);
-    o[3] = make_uint4(qlo[1][0], qlo[1][1], qhi[1][0], qhi[1][1]);
-    o[4] = make_uint4(qlo[2][0], qlo[2][1], qhi[2][0], qhi[2][1]);
-    o[5] = make_uint4(0u, 0u, 0u, 0u);
-}
-
-__global__ void k_collapse8(const CollapseItem* __restrict__ items_in, CollapseItem* __restrict__ items_out,
-                            uint32_t* __restrict__ counts, int level, uint32_t* __restrict__ node_counter,
-                            const int* __restrict__ left, const int* __restrict__ right, const uint32_t* __restrict__ cnt,
-                            const float4* __restrict__ box_lo, const float4* __restrict__ box_hi,
-                            const float4* __restrict__ nlo, const float4* __restrict__ nhi,
-                            float pad, uint4* __restrict__ nodes8, uint32_t* __restrict__ sorted_ids)
-{
-    const uint32_t n = counts[level];
-    for (uint32_t it = blockIdx.x * blockDim.x + threadIdx.x; it < n; it += gridDim.x * blockDim.x) {
-        const CollapseItem item = items_in[it];
-        int c[8]; int nc = 2;
-        c[0] = left[item.bvh2]; c[1] = right[item.bvh2];
-        for (int j = 2; j < 8; ++j) c[j] = 0;
-        while (nc < 8) {
-            int pick = -1; float best = -1.f;
-            for (int j = 0; j < nc; ++j) {
-                if (c[j] < 0 || (int)cnt[c[j]] <= kLeafMax8) continue;
-                const float a = box_area(nlo[c[j]], nhi[c[j]]);
-                if (a > best) { best = a; pick = j; }
-            }
-            if (pick < 0) break;
-            const int x = c[pick];
-            c[pick] = left[x]; c[nc++] = right[x];
-        }
-        // boxes, node centre
-        float4 clo[8], chi[8];
-        float3 nl = make_float3(3.0e38f, 3.0e38f, 3.0e38f), nh = make_float3(-3.0e38f, -3.0e38f, -3.0e38f);
-        for (int j = 0; j < nc; ++j) {
-            if (c[j] < 0) { const uint32_t id = (uint32_t)~c[j]; clo[j] = box_lo[id]; chi[j] = box_hi[id]; }
-            else { clo[j] = nlo[c[j]]; chi[j] = nhi[c[j]]; }
-            nl = make_float3(fminf(nl.x, clo[j].x), fminf(nl.y, clo[j].y), fminf(nl.z, clo[j].z));
-            nh = make_float3(fmaxf(nh.x, chi[j].x), fmaxf(nh.y, chi[j].y), fmaxf(nh.z, chi[j].z));
-        }
-        const float3 nc3 = make_float3(0.5f * (nl.x + nh.x), 0.5f * (nl.y + nh.y), 0.5f * (nl.z + nh.z));
-        // greedy child -> slot assignment
-        int slot_of[8], child_at[8];
-        for (int j = 0; j < 8; ++j) { slot_of[j] = -1; child_at[j] = -1; }
-        for (int round = 0; round < nc; ++round) {
-            float best = -3.0e38f; int bj = -1, bs = -1;
-            for (int j = 0; j < nc; ++j) {
-                if (slot_of[j] >= 0) continue;
-                const float dx = 0.5f * (clo[j].x + chi[j].x) - nc3.x, dy = 0.5f * (clo[j].y + chi[j].y) - nc3.y, dz = 0.5f * (clo[j].z + chi[j].z) - nc3.z;
-                for (int sl = 0; sl < 8; ++sl) {
-                    if (child_at[sl] >= 0) continue;
-                    const float cost = ((sl & 4) ? dx : -dx) + ((sl & 2) ? dy : -dy) + ((sl & 1) ? dz : -dz);
-                    if (cost > best) { best = cost; bj = j; bs = sl; }
-                }
-            }
-            slot_of[bj] = bs; child_at[bs] = bj;
-        }
-        // classify, allocate, lay out
-        uint32_t n_inner = 0, n_leaf_tris = 0;
-        for (int j = 0; j < nc; ++j) {
-            if (c[j] >= 0 && (int)cnt[c[j]] > kLeafMax8) ++n_inner; else n_leaf_tris += c[j] < 0 ? 1u : cnt[c[j]];
-        }
-        uint32_t base = 0, qbase = 0;
-        if (n_inner) { base = atomicAdd(node_counter, n_inner); qbase = atomicAdd(&counts[level + 1], n_inner); }
-        float4 slo[8], shi[8]; bool used[8]; uint32_t meta[8]; uint32_t imask = 0;
-        uint32_t k = 0, tri_off = 0, inner_first = item.first + n_leaf_tris;
-        for (int sl = 0; sl < 8; ++sl) {
-            const int j = child_at[sl];
-            used[sl] = j >= 0; meta[sl] = 0u;
-            slo[sl] = make_float4(0.f, 0.f, 0.f, 0.f); shi[sl] = slo[sl];
-            if (j < 0) continue;
-            slo[sl] = clo[j]; shi[sl] = chi[j];
-            const uint32_t ntri = c[j] < 0 ? 1u : cnt[c[j]];
-            if (c[j] >= 0 && (int)ntri > kLeafMax8) {
-                imask |= 1u << sl;
-                meta[sl] = (1u << 5) | (24u + (uint32_t)sl);
-                items_out[qbase + k] = CollapseItem{c[j], (int)(base + k), inner_first, 0u};
-                inner_first += ntri; ++k;
-            } else {
-                meta[sl] = (((1u << ntri) - 1u) << 5) | tri_off;            // unary count, offset from tri_base
-                emit_leaf_ids(c[j], item.first + tri_off, left, right, sorted_ids);
-                tri_off += ntri;
-            }
-        }
-        write_node8(nodes8 + 6 * (size_t)item.node4, slo, shi, used, meta, imask, base, item.first, pad);
-    }
-}
-
-// scenes with <= 3 triangles: a root whose slot 0 is the only leaf, boxed by the scene bounds
-__global__ void k_emit_single8(int n, const int* __restrict__ bounds, float pad, uint4* __restrict__ nodes8)
-{
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    float4 lo[8], hi[8]; bool used[8]; uint32_t meta[8];
-    for (int j = 0; j < 8; ++j) { lo[j] = make_float4(0.f, 0.f, 0.f, 0.f); hi[j] = lo[j]; used[j] = false; meta[j] = 0u; }
-    lo[0] = make_float4(ordered_as_float(bounds[0]), ordered_as_float(bounds[1]), ordered_as_float(bounds[2]), 0.f);
-    hi[0] = make_float4(ordered_as_float(bounds[3]), ordered_as_float(bounds[4]), ordered_as_float(bounds[5]), 0.f);
-    used[0] = true; meta[0] = (((1u << n) - 1u) << 5) | 0u;
-    write_node8(nodes8, lo, hi, used, meta, 0u, 0u, 0u, pad);
-}
-
 // scenes with <= leaf_max triangles: a root whose slot 0 is the only leaf, boxed by the scene bounds
 __global__ void k_emit_single4(int n, const int* __restrict__ bounds, float pad, uint4* __restrict__ nodes4)
 {
@@ -646,8 +501,7 @@ static void scan_u32(uint32_t* data, uint32_t n, uint32_t* total_out, uint32_t* 
 cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, const uint32_t* d_tri_mesh, uint32_t ntri, int leaf_max, int wide, cudaStream_t st,
                       BuiltBvh* out, uint64_t* launches)
 {
-    const size_t nstride = wide == 8 ? 6 : 4;          // uint4 per node
-    if (wide == 8) leaf_max = kLeafMax8;
+    const size_t nstride = 4;                          // uint4 per node
     out->wide = wide;
     out->nodes = nullptr; out->tris = nullptr; out->tri_rec = nullptr; out->sorted_ids = nullptr;
     out->n_nodes = 0; out->n_tris = ntri; out->max_depth = 0;
@@ -705,8 +559,7 @@ cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, const uint32_t*
     CK(dalloc(&tri_sorted, 3 * (size_t)ntri));
     if ((int)ntri <= leaf_max) {
         CK(dalloc(&nodes, nstride));
-        if (wide == 8) k_emit_single8<<<1, 32, 0, st>>>((int)ntri, bounds, pad, nodes);
-        else k_emit_single4<<<1, 32, 0, st>>>((int)ntri, bounds, pad, nodes);
+        k_emit_single4<<<1, 32, 0, st>>>((int)ntri, bounds, pad, nodes);
         CK(cudaMemcpyAsync(sorted, vals[cur], ntri * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
         *launches += 1;
         out->n_nodes = 1; out->max_depth = 1;
@@ -743,12 +596,8 @@ cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, const uint32_t*
         k_seed_collapse<<<1, 32, 0, st>>>(items[0], lvl_counts, scal + 2, cid[cb]);
         const int cgrid = (int)std::min<uint32_t>((cap + 127) / 128, 148u * 8u);
         for (uint32_t lvl = 0; lvl < max_levels; ++lvl) {
-            if (wide == 8)
-                k_collapse8<<<cgrid, 128, 0, st>>>(items[lvl & 1], items[(lvl + 1) & 1], lvl_counts, (int)lvl, scal + 2, left, right, cnt,
-                                                  box_lo, box_hi, nlo, nhi, pad, nodes, sorted);
-            else
-                k_collapse4<<<cgrid, 128, 0, st>>>(items[lvl & 1], items[(lvl + 1) & 1], lvl_counts, (int)lvl, scal + 2, left, right, cnt,
-                                                  box_lo, box_hi, nlo, nhi, leaf_max, pad, nodes, sorted);
+            k_collapse4<<<cgrid, 128, 0, st>>>(items[lvl & 1], items[(lvl + 1) & 1], lvl_counts, (int)lvl, scal + 2, left, right, cnt,
+                                              box_lo, box_hi, nlo, nhi, leaf_max, pad, nodes, sorted);
             *launches += 1;
         }
         std::vector<uint32_t> hc((size_t)max_levels + 2);

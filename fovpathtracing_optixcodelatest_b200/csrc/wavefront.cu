@@ -359,8 +359,9 @@ __device__ __forceinline__ void shade_path(const FrameDev& F, const SceneDev& S,
     const float4* tp = S.bvh.tris + 3 * (size_t)slot;
     const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
     const uint32_t gid = (uint32_t)__float_as_int(ta.w);
-    // geometric normal, flipped toward the viewer (:632-634); e1,e2 are exactly v1-v0, v2-v0
-    const float3 n0 = unit3<FAST>(cross3(f3(tb.x, tb.y, tb.z), f3(tc.x, tc.y, tc.z)));
+    // geometric normal, flipped toward the viewer (:632-634)
+    const float3 v0 = f3(ta.x, ta.y, ta.z);
+    const float3 n0 = unit3<FAST>(cross3(f3(tb.x, tb.y, tb.z) - v0, f3(tc.x, tc.y, tc.z) - v0));
     const float3 wo = -rd;
     const float3 N = n0 * copysignf(1.0f, dot3(wo, n0));
     const float3 P = ro + h4.x * rd;                         // :636-638

@@ -296,6 +296,65 @@ def _icosphere(level):
     return v, f
 
 
+def closed_sphere(level=5, radius=100.0, center=(3.0, -7.0, 11.0)) -> Scene:
+    """a closed, consistently wound icosphere (20 * 4^level triangles, every edge shared by exactly two of them)"""
+    v, f = _icosphere(level)
+    sc = Scene()
+    sc.add((v * radius + np.asarray(center)).astype(np.float32), f.astype(np.uint32), _disney((.7, .7, .7)))
+    return sc
+
+
+def closed_cube(n=24, half=50.0, center=(1.5, 2.5, -3.5)) -> Scene:
+    """a closed axis-aligned cube whose faces are n x n grids with shared vertices: axis-parallel edges and rays are where
+    edge functions become exactly zero"""
+    g = np.linspace(-half, half, n + 1)
+    pts = {}
+    verts, tris = [], []
+
+    def vid(p):
+        k = tuple(np.round(p, 6))
+        if k not in pts:
+            pts[k] = len(verts); verts.append(p)
+        return pts[k]
+    for axis in range(3):
+        for sgn in (-1.0, 1.0):
+            a1, a2 = (axis + 1) % 3, (axis + 2) % 3
+            for i in range(n):
+                for j in range(n):
+                    q = []
+                    for (u, w) in ((g[i], g[j]), (g[i + 1], g[j]), (g[i + 1], g[j + 1]), (g[i], g[j + 1])):
+                        p = np.zeros(3); p[axis] = sgn * half; p[a1] = u; p[a2] = w
+                        q.append(vid(p))
+                    if sgn > 0:
+                        tris += [(q[0], q[1], q[2]), (q[0], q[2], q[3])]
+                    else:
+                        tris += [(q[0], q[2], q[1]), (q[0], q[3], q[2])]
+    sc = Scene()
+    sc.add((np.array(verts) + np.asarray(center)).astype(np.float32), np.array(tris, np.uint32), _disney((.7, .7, .7)))
+    return sc
+
+
+def edge_and_vertex_rays(scene: Scene, n, seed, origins):
+    """rays from the given origins aimed EXACTLY (to float32 rounding) at points on the shared edges (90 %) and at the
+    vertices (10 %) of the scene's first mesh; returns (rays[n*len(origins), 8], per-ray target)"""
+    rng = np.random.default_rng(seed)
+    m = scene.meshes[0]
+    v = m.vtx.astype(np.float64); f = m.idx.astype(np.int64)
+    tri = f[rng.integers(0, len(f), n)]
+    e = rng.integers(0, 3, n)
+    a = v[tri[np.arange(n), e]]; b = v[tri[np.arange(n), (e + 1) % 3]]
+    s = rng.random(n)[:, None]
+    s[: n // 10] = 0.0
+    tgt = a + (b - a) * s
+    out = []
+    for o in origins:
+        o = np.asarray(o, np.float64)
+        d = tgt - o; d /= np.linalg.norm(d, axis=1, keepdims=True)
+        r = np.zeros((n, 8), np.float32); r[:, 0:3] = o; r[:, 3] = 0.01; r[:, 4:7] = d; r[:, 7] = 1e16
+        out.append(r)
+    return np.concatenate(out), np.concatenate([tgt] * len(origins))
+
+
 def _value_noise3(p, seed, freq):
     """cheap deterministic lattice noise in [-1,1] evaluated at points p (n,3)."""
     q = p * freq

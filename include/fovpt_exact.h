@@ -161,26 +161,61 @@ FX_HD fx_vec3 fx_camera_dir(uint32_t px, uint32_t py, float jx, float jy, int w,
 
 /* ------------------------------------------------------------------ ray / triangle */
 
-/* Triangle record as stored on the device: v0 and the two edges, computed ONCE (by
- * fx_make_tri, one exact subtraction per component) so that both sides test the same numbers. */
-typedef struct { fx_vec3 v0, e1, e2; } fx_tri;
+/* Triangle record as stored on the device: the three vertices, unmodified. */
+typedef struct { fx_vec3 v0, v1, v2; } fx_tri;
 
 FX_HD fx_tri fx_make_tri(fx_vec3 a, fx_vec3 b, fx_vec3 c)
 {
     fx_tri t;
-    t.v0 = a;
-    t.e1.x = FX_SUB(b.x, a.x); t.e1.y = FX_SUB(b.y, a.y); t.e1.z = FX_SUB(b.z, a.z);
-    t.e2.x = FX_SUB(c.x, a.x); t.e2.y = FX_SUB(c.y, a.y); t.e2.z = FX_SUB(c.z, a.z);
+    t.v0 = a; t.v1 = b; t.v2 = c;
     return t;
 }
 
-FX_HD fx_vec3 fx_cross3(fx_vec3 a, fx_vec3 b)
+/* WATERTIGHT ray/triangle test after Woop, Benthin, Wald, "Watertight Ray/Triangle Intersection" (JCGT 2013) -- the
+ * property OptiX's built-in triangle test has and Moeller-Trumbore has not (round 1 used the latter: of rays aimed at
+ * the shared edges of a closed mesh about 20 % slipped between the two triangles).
+ *
+ * Per ray: the dominant direction axis kz and the shear constants that map the ray onto the +z axis of a "ray space".
+ * Per vertex: its ray-space coordinates, a deterministic function of (vertex, ray) ONLY -- so two triangles that share
+ * an edge see bit-identical end points.  Per edge: the 2-D edge function  p - q  with two separately rounded products,
+ * which is exactly antisymmetric in its end points: the triangle on the other side of the edge computes exactly the
+ * negated value.  A ray therefore never falls between two triangles that share an edge (or a vertex fan), and a value
+ * of exactly zero (the ray meets the edge) is accepted by both, the closest-hit tie-break picks one.  Differences from
+ * the paper: no double-precision re-evaluation of zero edge functions (over-acceptance on the edge itself is harmless
+ * here), no kx/ky swap (the facing rule carries the sign of d[kz] instead), and the shear is applied as a sparse dot
+ * product so that SIMT code needs no per-vertex component selects. */
+#define FX_FRONT_SIGN 1
+typedef struct { float sx, sy, sz; int kz; } fx_shear;           /* per ray */
+typedef struct { fx_vec3 ex, ey, ez; float face; } fx_basis;     /* per ray: rows of the ray-space transform */
+
+FX_HD fx_shear fx_shear_init(fx_vec3 d)
 {
-    fx_vec3 r;
-    r.x = FX_FMA(a.y, b.z, -FX_MUL(a.z, b.y));
-    r.y = FX_FMA(a.z, b.x, -FX_MUL(a.x, b.z));
-    r.z = FX_FMA(a.x, b.y, -FX_MUL(a.y, b.x));
-    return r;
+    const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    fx_shear s;
+    s.kz = (ax >= ay) ? (ax >= az ? 0 : 2) : (ay >= az ? 1 : 2);
+    const float dz = s.kz == 0 ? d.x : (s.kz == 1 ? d.y : d.z);
+    const float dx = s.kz == 0 ? d.y : (s.kz == 1 ? d.z : d.x);   /* kx = kz + 1 (mod 3) */
+    const float dy = s.kz == 0 ? d.z : (s.kz == 1 ? d.x : d.y);   /* ky = kz + 2 (mod 3) */
+    s.sx = FX_DIV(dx, dz); s.sy = FX_DIV(dy, dz); s.sz = FX_DIV(1.0f, dz);
+    return s;
+}
+
+/* x' = v[kx] - sx*v[kz], y' = v[ky] - sy*v[kz], z' = sz*v[kz], written as dot products with sparse rows */
+FX_HD fx_basis fx_shear_basis(fx_shear s)
+{
+    fx_basis b;
+    const float nx = -s.sx, ny = -s.sy;
+    b.ex.x = s.kz == 0 ? nx : (s.kz == 2 ? 1.0f : 0.0f);
+    b.ex.y = s.kz == 1 ? nx : (s.kz == 0 ? 1.0f : 0.0f);
+    b.ex.z = s.kz == 2 ? nx : (s.kz == 1 ? 1.0f : 0.0f);
+    b.ey.x = s.kz == 0 ? ny : (s.kz == 1 ? 1.0f : 0.0f);
+    b.ey.y = s.kz == 1 ? ny : (s.kz == 2 ? 1.0f : 0.0f);
+    b.ey.z = s.kz == 2 ? ny : (s.kz == 0 ? 1.0f : 0.0f);
+    b.ez.x = s.kz == 0 ? s.sz : 0.0f;
+    b.ez.y = s.kz == 1 ? s.sz : 0.0f;
+    b.ez.z = s.kz == 2 ? s.sz : 0.0f;
+    b.face = s.sz;            /* sign of d[kz]: orients the ray-space winding */
+    return b;
 }
 
 FX_HD float fx_dot3_fma(fx_vec3 a, fx_vec3 b)
@@ -188,52 +223,39 @@ FX_HD float fx_dot3_fma(fx_vec3 a, fx_vec3 b)
     return FX_FMA(a.z, b.z, FX_FMA(a.y, b.y, FX_MUL(a.x, b.x)));
 }
 
-/* Moeller-Trumbore with a fixed operation sequence.
- *   returns 0: no intersection.
- *   returns +1: hit, ray sees the front face (vertices counter-clockwise from the ray origin,
- *               i.e. dot(cross(e1,e2), dir) < 0  <=>  det > 0) -- OptiX's front-face rule.
+/* The test, without early returns (SIMT-friendly; the host uses the same code so that both sides produce the same
+ * bits): every operation is executed, the rejections are folded into one predicate at the end.
+ *   returns 0: no intersection (outputs unspecified).
+ *   returns +1: hit, the ray sees the front face (vertices counter-clockwise from the ray origin, OptiX's rule).
  *   returns -1: hit on the back face.
- * (u,v) are the barycentric weights of vertex 1 and vertex 2 (optixGetTriangleBarycentrics
- * convention, used at deviceProgram.cu:656-661).  The caller applies the open interval
- * tmin < t < tmax.  */
-FX_HD int fx_ray_tri(fx_vec3 o, fx_vec3 d, const fx_tri tr, float* t_out, float* u_out, float* v_out)
+ * (u,v) are the barycentric weights of vertex 1 and vertex 2 (optixGetTriangleBarycentrics convention, used at
+ * deviceProgram.cu:656-661).  The caller applies the open interval tmin < t < tmax. */
+FX_HD int fx_ray_tri_wt(fx_vec3 o, const fx_basis rb, const fx_tri tr, float* t_out, float* u_out, float* v_out)
 {
-    fx_vec3 p = fx_cross3(d, tr.e2);
-    float det = fx_dot3_fma(tr.e1, p);
-    if (det == 0.0f) return 0;
-    float inv = FX_RCP(det);
-    fx_vec3 tv;
-    tv.x = FX_SUB(o.x, tr.v0.x); tv.y = FX_SUB(o.y, tr.v0.y); tv.z = FX_SUB(o.z, tr.v0.z);
-    float u = FX_MUL(fx_dot3_fma(tv, p), inv);
-    if (!(u >= 0.0f && u <= 1.0f)) return 0;
-    fx_vec3 q = fx_cross3(tv, tr.e1);
-    float v = FX_MUL(fx_dot3_fma(d, q), inv);
-    if (!(v >= 0.0f && FX_ADD(u, v) <= 1.0f)) return 0;
-    float t = FX_MUL(fx_dot3_fma(tr.e2, q), inv);
-    if (!(t == t)) return 0;
-    *t_out = t; *u_out = u; *v_out = v;
-    return det > 0.0f ? 1 : -1;
+    fx_vec3 A, B, C;
+    A.x = FX_SUB(tr.v0.x, o.x); A.y = FX_SUB(tr.v0.y, o.y); A.z = FX_SUB(tr.v0.z, o.z);
+    B.x = FX_SUB(tr.v1.x, o.x); B.y = FX_SUB(tr.v1.y, o.y); B.z = FX_SUB(tr.v1.z, o.z);
+    C.x = FX_SUB(tr.v2.x, o.x); C.y = FX_SUB(tr.v2.y, o.y); C.z = FX_SUB(tr.v2.z, o.z);
+    const float Ax = fx_dot3_fma(A, rb.ex), Ay = fx_dot3_fma(A, rb.ey), Az = fx_dot3_fma(A, rb.ez);
+    const float Bx = fx_dot3_fma(B, rb.ex), By = fx_dot3_fma(B, rb.ey), Bz = fx_dot3_fma(B, rb.ez);
+    const float Cx = fx_dot3_fma(C, rb.ex), Cy = fx_dot3_fma(C, rb.ey), Cz = fx_dot3_fma(C, rb.ez);
+    const float U = FX_SUB(FX_MUL(Cx, By), FX_MUL(Cy, Bx));      /* edge v1 -> v2: weight of v0 */
+    const float V = FX_SUB(FX_MUL(Ax, Cy), FX_MUL(Ay, Cx));      /* edge v2 -> v0: weight of v1 */
+    const float W = FX_SUB(FX_MUL(Bx, Ay), FX_MUL(By, Ax));      /* edge v0 -> v1: weight of v2 */
+    const float det = FX_ADD(FX_ADD(U, V), W);
+    const float T = FX_FMA(W, Cz, FX_FMA(V, Bz, FX_MUL(U, Az)));
+    const float inv = FX_RCP(det);
+    const float t = FX_MUL(T, inv);
+    const int neg = (U < 0.0f) | (V < 0.0f) | (W < 0.0f), pos = (U > 0.0f) | (V > 0.0f) | (W > 0.0f);
+    const int ok = !(neg & pos) & (det != 0.0f) & (t == t);
+    *t_out = t; *u_out = FX_MUL(V, inv); *v_out = FX_MUL(W, inv);
+    return ok ? (((det > 0.0f) == (rb.face > 0.0f)) ? FX_FRONT_SIGN : -FX_FRONT_SIGN) : 0;
 }
 
-/* The same test without early returns, for SIMT code: every operation of fx_ray_tri is executed in
- * the same order on the same operands, only the rejections are folded into one predicate at the
- * end, so whenever fx_ray_tri accepts, the outputs are bit-identical; when it rejects, this returns
- * 0 and the outputs are unspecified.  (det == 0 makes inv infinite and u/v/t infinite or NaN, which
- * the comparisons reject exactly as the early return does.) */
-FX_HD int fx_ray_tri_nb(fx_vec3 o, fx_vec3 d, const fx_tri tr, float* t_out, float* u_out, float* v_out)
+/* one-off convenience (tests, tools): builds the per-ray constants each call */
+FX_HD int fx_ray_tri(fx_vec3 o, fx_vec3 d, const fx_tri tr, float* t_out, float* u_out, float* v_out)
 {
-    fx_vec3 p = fx_cross3(d, tr.e2);
-    float det = fx_dot3_fma(tr.e1, p);
-    float inv = FX_RCP(det);
-    fx_vec3 tv;
-    tv.x = FX_SUB(o.x, tr.v0.x); tv.y = FX_SUB(o.y, tr.v0.y); tv.z = FX_SUB(o.z, tr.v0.z);
-    float u = FX_MUL(fx_dot3_fma(tv, p), inv);
-    fx_vec3 q = fx_cross3(tv, tr.e1);
-    float v = FX_MUL(fx_dot3_fma(d, q), inv);
-    float t = FX_MUL(fx_dot3_fma(tr.e2, q), inv);
-    int ok = (det != 0.0f) & (u >= 0.0f) & (u <= 1.0f) & (v >= 0.0f) & (FX_ADD(u, v) <= 1.0f) & (t == t);
-    *t_out = t; *u_out = u; *v_out = v;
-    return ok ? (det > 0.0f ? 1 : -1) : 0;
+    return fx_ray_tri_wt(o, fx_shear_basis(fx_shear_init(d)), tr, t_out, u_out, v_out);
 }
 
 /* ------------------------------------------------------------------ RGBA8 texture fetch

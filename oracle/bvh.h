@@ -78,10 +78,10 @@ struct Scene {
     {
         Box b;
         float v0[3] = {t.v0.x, t.v0.y, t.v0.z};
-        float v1[3] = {t.v0.x + t.e1.x, t.v0.y + t.e1.y, t.v0.z + t.e1.z};
-        float v2[3] = {t.v0.x + t.e2.x, t.v0.y + t.e2.y, t.v0.z + t.e2.z};
+        float v1[3] = {t.v1.x, t.v1.y, t.v1.z};
+        float v2[3] = {t.v2.x, t.v2.y, t.v2.z};
         b.grow(v0); b.grow(v1); b.grow(v2);
-        // v0+e may differ from the original vertex by one rounding; widen by an ulp-scale margin
+        // an ulp-scale margin on top of the exact vertex bounds (the global pad of commit() is what absorbs the tolerance of the ray/triangle test)
         for (int a = 0; a < 3; ++a) {
             float m = std::max(std::fabs(b.lo[a]), std::fabs(b.hi[a])) * 2.4e-7f;
             b.lo[a] -= m; b.hi[a] += m;
@@ -205,28 +205,29 @@ struct Scene {
         return t0 <= t1 * 1.0000012f + 0.0f;
     }
 
-    inline void leaf_closest(uint32_t first, int count, const fx_vec3& o, const fx_vec3& d, float tmin, float tmax,
+    inline void leaf_closest(uint32_t first, int count, const fx_vec3& o, const fx_basis& d, float tmin, float tmax,
                              float& best_t, uint32_t& best_id, float& bu, float& bv, uint64_t& ntri) const
     {
         for (int i = 0; i < count; ++i) {
             uint32_t id = order[first + i];
             float t, u, v;
             ++ntri;
-            if (fx_ray_tri(o, d, tris[id], &t, &u, &v) == 0) continue;
+            if (fx_ray_tri_wt(o, d, tris[id], &t, &u, &v) == 0) continue;
             if (!(t > tmin && t < tmax)) continue;
             if (fx_hit_better(t, id, best_t, best_id)) { best_t = t; best_id = id; bu = u; bv = v; }
         }
     }
 
-    bool closest(const fx_vec3& o, const fx_vec3& d, float tmin, float tmax, Hit* hit, Counters* ctr = nullptr) const
+    bool closest(const fx_vec3& o, const fx_vec3& dir, float tmin, float tmax, Hit* hit, Counters* ctr = nullptr) const
     {
+        const fx_basis d = fx_shear_basis(fx_shear_init(dir));      // per-ray constants of the watertight triangle test
         float best_t = INFINITY, bu = 0, bv = 0; uint32_t best_id = 0xffffffffu;
         uint64_t nnode = 0, ntri = 0;
         if (!tris.empty()) {
             if (single_leaf) {
                 leaf_closest(0, (int)order.size(), o, d, tmin, tmax, best_t, best_id, bu, bv, ntri);
             } else {
-                RayPrep r = {{o.x, o.y, o.z}, {1.0f / d.x, 1.0f / d.y, 1.0f / d.z}};
+                RayPrep r = {{o.x, o.y, o.z}, {1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z}};
                 int stack[128]; int sp = 0; stack[sp++] = 0;
                 while (sp) {
                     const Node& nd = nodes[stack[--sp]];
@@ -261,26 +262,27 @@ struct Scene {
     // popped nodes are re-tested against the shrunken interval implicitly: the slab test above
     // was done with the limit at push time; a stale entry only costs work, never correctness.
 
-    inline bool leaf_any(uint32_t first, int count, const fx_vec3& o, const fx_vec3& d, float tmin, float tmax, uint64_t& ntri) const
+    inline bool leaf_any(uint32_t first, int count, const fx_vec3& o, const fx_basis& d, float tmin, float tmax, uint64_t& ntri) const
     {
         for (int i = 0; i < count; ++i) {
             uint32_t id = order[first + i];
             float t, u, v;
             ++ntri;
-            if (fx_ray_tri(o, d, tris[id], &t, &u, &v) != 1) continue;     // front faces only
+            if (fx_ray_tri_wt(o, d, tris[id], &t, &u, &v) != 1) continue;     // front faces only
             if (t > tmin && t < tmax) return true;
         }
         return false;
     }
 
-    bool any_front(const fx_vec3& o, const fx_vec3& d, float tmin, float tmax, Counters* ctr = nullptr) const
+    bool any_front(const fx_vec3& o, const fx_vec3& dir, float tmin, float tmax, Counters* ctr = nullptr) const
     {
+        const fx_basis d = fx_shear_basis(fx_shear_init(dir));
         uint64_t nnode = 0, ntri = 0; bool occ = false;
         if (!tris.empty()) {
             if (single_leaf) {
                 occ = leaf_any(0, (int)order.size(), o, d, tmin, tmax, ntri);
             } else {
-                RayPrep r = {{o.x, o.y, o.z}, {1.0f / d.x, 1.0f / d.y, 1.0f / d.z}};
+                RayPrep r = {{o.x, o.y, o.z}, {1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z}};
                 int stack[128]; int sp = 0; stack[sp++] = 0;
                 while (sp && !occ) {
                     const Node& nd = nodes[stack[--sp]];

@@ -152,6 +152,36 @@ def test_large_mesh_random_rays(gpu, port):
     ctx.close(); o.close()
 
 
+@pytest.mark.parametrize("mesh", ["sphere", "cube"])
+def test_traversal_is_watertight(gpu, port, mesh):
+    """R-TRACE property: no ray fired from inside a closed mesh exactly at its shared edges / vertices leaks through the
+    device BVH (quantised boxes + watertight triangle test), any-hit rays from outside are all occluded, and every result
+    equals the oracle's bit for bit"""
+    sc = scenes.closed_sphere(5) if mesh == "sphere" else scenes.closed_cube(24)
+    c = np.asarray([3.0, -7.0, 11.0] if mesh == "sphere" else [1.5, 2.5, -3.5])
+    o = port.Oracle("port"); o.add_scene(sc); o.commit()
+    ctx = gpu.native.Context(0); ctx.upload_scene(sc)
+    rays, _ = scenes.edge_and_vertex_rays(sc, 400000, 1, [c, c + [17.0, 5.0, -11.0], c + [-30.0, 20.0, 9.0]])
+    gt, gtuv = ctx.trace(rays, 0)
+    assert (gt >= 0).all(), f"{(gt < 0).sum()} of {len(gt)} edge/vertex rays leaked through the closed mesh"
+    ot, otuv = o.trace(rays[:300000], 0)
+    assert (ot == gt[:300000]).all() and (bits(otuv) == bits(gtuv[:300000])).all()
+    if mesh == "sphere":      # from outside, at edges that face the origin (on the silhouette a grazing ray may legitimately miss)
+        eye = c + [400.0, 130.0, -220.0]
+        outside, tgt = scenes.edge_and_vertex_rays(sc, 200000, 2, [eye])
+        facing = ((tgt - c) * (eye - tgt)).sum(1) / (np.linalg.norm(tgt - c, axis=1) * np.linalg.norm(eye - tgt, axis=1)) > 0.1
+        go, _ = ctx.trace(outside[facing], 0)
+        assert facing.sum() > 40000 and (go >= 0).all(), f"{(go < 0).sum()} rays from outside leaked"
+    ctx.close(); o.close()
+    # occlusion rays cull back faces (deviceProgram.cu:242): seen from inside, the mesh must be wound inwards to be front-facing
+    inward = scenes.Scene(); m = sc.meshes[0]
+    inward.add(m.vtx, m.idx[:, ::-1].copy(), m.material)
+    ctx = gpu.native.Context(0); ctx.upload_scene(inward)
+    ga, _ = ctx.trace(rays, 1)
+    assert (ga == 1).all(), f"{(ga == 0).sum()} shadow rays leaked"
+    ctx.close()
+
+
 def test_degenerate_rays_and_geometry(gpu, port):
     """axis-parallel rays (zero direction components), rays starting on a surface, zero-area and
     duplicated triangles (ties -> lowest global id)"""
@@ -874,3 +904,181 @@ def test_software_texture_fetch_matches_the_texture_unit(gpu, shape):
     assert err.max() <= TEX_TOL
     assert same.mean() >= TEX_IDENTICAL
     ctx.close()
+
+
+# ------------------------------------------------------------------------------------------- BASELINE configs at their stated size
+def _frame_parity(accum, g, frame, gf, tol=2e-4):
+    """the parity bar of this suite on one frame pair: same pixels written, relative MSE (north_star: < 1e-3), mean radiance, RGBA8 identity"""
+    assert (g[..., 3] == accum[..., 3]).all()
+    wr = accum[..., 3] == 1.0
+    a3, g3 = accum[wr][:, :3].astype(np.float64), g[wr][:, :3].astype(np.float64)
+    rm = ((a3 - g3) ** 2).mean() / a3.mean() ** 2
+    assert rm < 1e-3 and rm < tol, rm                                              # north_star tolerance, then what this build achieves
+    assert abs(a3.mean() - g3.mean()) < 1e-3 * a3.mean()
+    assert (np.abs(a3 - g3).max(axis=1) <= 1e-3 * (1.0 + np.abs(a3).max(axis=1))).mean() > 0.98
+    assert (gf[wr] == frame[wr]).mean() > 0.98
+    return rm
+
+
+def test_full_size_c2_against_the_oracle(gpu, port):
+    """BASELINE configs[1] at its stated size: Cornell box 1920x1080 foveated, radii 148/482, depth 8, Lambertian + Disney,
+    64 foveal spp = 2 accumulated subframes of (8,16,32) -- rendered as ONE batch on the GPU (fovpt_render_frames) and frame
+    by frame by the oracle"""
+    wl = workloads.c2()
+    w, h, ri, ro = wl.width, wl.height, wl.inner_radius, wl.outer_radius
+    assert (w, h, ri, ro, wl.max_depth, wl.frames) == (1920, 1080, 148, 482, 8, 2)
+    r, o, lp, accum, frame = make_pair(gpu, port, wl.scene(), wl.camera, w, h, wl.probe(), ri, ro, max_depth=8, accumulate=1, seed_all_passes_with_subframe=1)
+    fc = wl.apply(port.FovCfg.sv5()); op = wl.apply(port.Opts.sv5())
+    for _ in range(wl.frames):
+        o.render(lp, fc, op)
+    r.renderSubframes(wl.frames)
+    _frame_parity(accum, r.downloadAccum(), frame, r.downloadPixels())
+    assert r.stats()["samples"] == o.counters()["samples"] == 2 * 5571224            # SURVEY 8d closed form for r = 148/482
+    assert check_primary(port, r, o, lp, w, h, (w // 2, h // 2), ri, ro) > 500000     # every primary hit of the three passes, bit-exact
+    r.close(); o.close()
+
+
+def test_full_size_c4_eye_against_the_oracle(gpu, port):
+    """BASELINE configs[3] at its stated size: one eye of the stereo pair, 2160x2160, radii 148/482, depth 4, at two points of
+    the moving-gaze path (the first puts the mid ring across the right frame border: clamped splats); same renderer reused,
+    as a VR loop would"""
+    wl = workloads.c4()
+    w, h, ri, ro = wl.width, wl.height, wl.inner_radius, wl.outer_radius
+    assert (w, h, ri, ro) == (2160, 2160, 148, 482)
+    cam0, gaze0 = wl.view_at(0)
+    r, o, lp, accum, frame = make_pair(gpu, port, wl.scene(), cam0, w, h, wl.probe(), ri, ro, gaze=gaze0)
+    for k in (0, 21):                                        # k = 0: eye 0, gaze (1680, 1080); k = 21: eye 1 of stereo frame 10, gaze (1606, 1367)
+        cam, gaze = wl.view_at(k)
+        U, V, W = o.camera_uvw(cam.eye, cam.lookat, cam.up, cam.fovy, w / h)
+        lp.camera.eye.set(cam.eye); lp.camera.U.set(U); lp.camera.V.set(V); lp.camera.W.set(W)
+        r.setCamera(cam)
+        lp.frame.c_x, lp.frame.c_y = gaze; r.launchParams.frame.c_x, r.launchParams.frame.c_y = gaze
+        lp.frame.subframe_index = k; r.launchParams.frame.subframe_index = k
+        accum[:] = 0; frame[:] = 0
+        o.render(lp, wl.apply(port.FovCfg.sv5()), wl.apply(port.Opts.sv5()))
+        r.render()
+        _frame_parity(accum, r.downloadAccum(), frame, r.downloadPixels(), tol=1e-4)
+    r.close(); o.close()
+
+
+def test_full_size_c5_against_the_oracle(gpu, port):
+    """BASELINE configs[4] at its stated size: the 10 M-triangle procedural mesh (tree larger than L2) at 3840x2160, depth 4.
+    (i) closest / any-hit of random rays bit-exact against the oracle's own SAH tree over all 10 M triangles;
+    (ii) a 256x128 region of the 4K frame (one launch at that offset, 8 spp) against the oracle: primary hits bit-exact,
+    radiance within the suite's bar; (iii) the batch of subframes equals frame-by-frame rendering on a band of the frame."""
+    wl = workloads.c5()
+    sc = wl.scene(); w, h = wl.width, wl.height
+    assert sc.n_tris >= 10_000_000 and (w, h) == (3840, 2160)
+    r, o, lp, accum, frame = make_pair(gpu, port, sc, wl.camera, w, h, wl.probe(), 74, 241, foveated=0, spp_uniform=8, max_depth=4)
+    assert r.stats()["bvh_tris"] == sc.n_tris
+    rays = random_rays(sc, 60000, 9)
+    rays[:, 1] = np.abs(rays[:, 1]) + 50.0; rays[:30000, 5] = -np.abs(rays[:30000, 5])
+    ot, otuv = o.trace(rays, 0); gt, gtuv = r.ctx.trace(rays, 0)
+    assert (ot == gt).all() and (bits(otuv) == bits(gtuv)).all() and (ot >= 0).mean() > 0.2
+    oa, _ = o.trace(rays, 1); ga, _ = r.ctx.trace(rays, 1)
+    assert (oa == ga).all()
+    # one launch over a window of the 4K frame: launch index (x, y) -> pixel (x + 1800, y + 1000)  (deviceProgram.cu:433)
+    lw, lh, offx, offy = 256, 128, 1800, 1000
+    for L in (lp, r.launchParams):
+        L.frame.factor_x = L.frame.factor_y = 1; L.frame.factor_z = 1; L.frame.fillSize = 1
+        L.frame.r_inner, L.frame.r_outer = 0.0, 1e9; L.frame.offset_x, L.frame.offset_y = offx, offy
+        L.samples_per_launch = 8; L.frame.subframe_index = 0; L.frame.redraw = 0
+    n = lw * lh
+    tri = np.zeros(n, np.int32); tuv = np.zeros((n, 3), np.float32)
+    op = wl.apply(port.Opts.sv5()); op.primary_tri, op.primary_tuv = tri.ctypes.data, tuv.ctypes.data
+    o.launch(lp, lw, lh, op)
+    r.ctx.launch(r.launchParams, lw, lh); r.ctx.sync()
+    g = r.downloadAccum(); gf = r.downloadPixels()
+    win = (slice(offy, offy + lh), slice(offx, offx + lw))
+    assert (accum[..., 3] == 1.0).sum() == n and (g[..., 3] == accum[..., 3]).all()
+    _frame_parity(accum[win], g[win], frame[win], gf[win], tol=1e-4)
+    lp1 = LaunchParams(); C.memmove(C.byref(lp1), C.byref(r.launchParams), C.sizeof(lp1)); lp1.samples_per_launch = 1
+    gtri, gtuv2, _ = r.ctx.primary_hits(lp1, lw, lh)
+    assert (tri == gtri).all() and (bits(tuv) == bits(gtuv2)).all() and (tri >= 0).mean() > 0.5
+    r.close(); o.close()
+
+
+# ------------------------------------------------------------------------------------------- real multi-GPU
+def _mgpu_rank_main(rank, world, owner, tile, wl_name, scale, subframes, batches, conn):
+    """one rank of a REAL multi-GPU job (device = rank): renders its tiles, `batches` batches of `subframes` subframes each,
+    into rank 0's shared frame / accumulation buffer over NVLink peer memory"""
+    try:
+        from fovpathtracing_optixcodelatest_b200 import native, workloads as wls
+        from fovpathtracing_optixcodelatest_b200.renderer import ProbeData, SampleRenderer
+        wl = wls.BY_NAME[wl_name]()
+        if scale is not None:
+            wl = wls.scaled(wl, *scale)
+        r = SampleRenderer(wl.scene(), rank, wl.apply(native.default_config()))
+        r.resize((wl.width, wl.height)); r.setCamera(wl.camera); r.setProbe(ProbeData(wl.probe()).BuildCDF())
+        r.launchParams.frame.c_x, r.launchParams.frame.c_y = wl.gaze_xy()
+        r.ctx.set_tile_owner(tile, owner, rank)
+        if rank == 0:
+            handle, ptr = r.ctx.peer_frame_create(wl.width * wl.height, world, 0)
+            conn.send(handle)
+        else:
+            ptr = r.ctx.peer_frame_open(conn.recv(), rank)
+        r.launchParams.frame.frame_buffer = ptr
+        out = []
+        for k in range(batches):
+            r.ctx.render_frames(r.launchParams, subframes)
+            if rank == 0:
+                r.ctx.peer_frame_wait()
+                out.append((r.downloadPixels().copy(), r.downloadAccum().copy()))     # the shared RGBA8 frame and the shared float accumulation
+                r.ctx.peer_frame_release()
+            else:
+                r.ctx.peer_frame_signal()
+        err = None
+        try:
+            r.ctx.sync()
+        except RuntimeError as e:
+            err = str(e)
+        conn.send((out, err))
+        conn.recv()
+        r.ctx.peer_frame_close(); r.close()
+    except Exception as e:                                   # noqa: BLE001
+        conn.send(([], "worker failed: " + repr(e)))
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_multi_gpu_frame_and_accumulation_equal_one_gpu_per_pixel(gpu, world):
+    """the multi-GPU path on REAL devices (one process per GPU, peer stores over NVLink): C3 at full size, tiles weighted by
+    foveal sample density, two batches of 4 accumulated subframes.  Every pixel of the RGBA8 frame AND of the float4
+    accumulation buffer gathered on rank 0 must equal the 1-GPU render bit for bit.  Skipped on boxes with fewer GPUs."""
+    import multiprocessing as mp
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} CUDA devices, this box has {torch.cuda.device_count()}")
+    wl = workloads.c3()
+    w, h = wl.width, wl.height
+    r = gpu.SampleRenderer(wl.scene(), 0, wl.apply(gpu.native.default_config()))
+    r.resize((w, h)); r.setCamera(wl.camera); r.setProbe(gpu.ProbeData(wl.probe()).BuildCDF())
+    r.launchParams.frame.c_x, r.launchParams.frame.c_y = wl.gaze_xy()
+    want = []
+    for _ in range(2):
+        r.renderSubframes(4); want.append((r.downloadPixels().copy(), r.downloadAccum().copy()))
+    r.close()
+    owner, _ = partition.partition(w, h, wl.gaze_xy(), wl.inner_radius, wl.outer_radius, world, 32, wl.spp)
+    ctx = mp.get_context("spawn")
+    pipes = [ctx.Pipe() for _ in range(world)]
+    procs = [ctx.Process(target=_mgpu_rank_main, args=(rk, world, owner, 32, "c3", None, 4, 2, pipes[rk][1])) for rk in range(world)]
+    for p in procs:
+        p.start()
+    handle = pipes[0][0].recv()
+    assert not isinstance(handle, tuple), handle
+    for rk in range(1, world):
+        pipes[rk][0].send(handle)
+    res = []
+    for rk in range(world):
+        assert pipes[rk][0].poll(300), f"rank {rk} did not report"
+        res.append(pipes[rk][0].recv())
+    for rk in range(world):
+        pipes[rk][0].send("bye")
+    for p in procs:
+        p.join(60)
+    for rk, (_, err) in enumerate(res):
+        assert err is None, f"rank {rk}: {err}"
+    got = res[0][0]
+    assert len(got) == 2
+    for k in range(2):
+        assert (got[k][0] == want[k][0]).all(), f"batch {k}: {(got[k][0] != want[k][0]).sum()} RGBA8 pixels differ from the 1-GPU frame"
+        assert (bits(got[k][1]) == bits(want[k][1])).all(), f"batch {k}: accumulation buffer differs from the 1-GPU render"

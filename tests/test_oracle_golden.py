@@ -157,3 +157,32 @@ def test_empty_and_tiny_scenes(P):
     P.commit()
     tri, _ = P.trace(np.array([[0, 0, -5, 0.01, 0, 0, 1, 1e16], [5, 5, -5, 0.01, 0, 0, 1, 1e16]], np.float32), 0)
     assert list(tri) == [0, -1]
+
+
+@pytest.mark.parametrize("mesh", ["sphere", "cube"])
+def test_ray_triangle_test_is_watertight(P, mesh):
+    """R-TRACE property (OptiX's triangle test is watertight; the reference has no source for it): rays fired from inside a
+    CLOSED mesh exactly at its shared edges and vertices must hit something -- none may slip between two triangles -- both
+    by brute force over all triangles and through the BVH; any-hit rays from outside aimed the same way are all occluded.
+    (Round 1's Moeller-Trumbore test lost ~20 % of such rays on the sphere.)"""
+    sc = scenes.closed_sphere(4) if mesh == "sphere" else scenes.closed_cube(12)
+    c = np.asarray([3.0, -7.0, 11.0] if mesh == "sphere" else [1.5, 2.5, -3.5])
+    P.add_scene(sc); P.commit()
+    rays, _ = scenes.edge_and_vertex_rays(sc, 100000, 1, [c, c + [17.0, 5.0, -11.0], c + [-30.0, 20.0, 9.0]])
+    t, _ = P.trace(rays, 0)
+    assert (t >= 0).all(), f"{(t < 0).sum()} of {len(t)} edge/vertex rays leaked through the closed mesh (BVH)"
+    tb, _ = P.trace(rays[:20000], 2)
+    assert (tb >= 0).all(), f"{(tb < 0).sum()} rays leaked (brute force)"
+    if mesh == "sphere":      # from outside, at edges that face the origin (on the silhouette a grazing ray may legitimately miss)
+        eye = c + [400.0, 130.0, -220.0]
+        outside, tgt = scenes.edge_and_vertex_rays(sc, 50000, 2, [eye])
+        facing = ((tgt - c) * (eye - tgt)).sum(1) / (np.linalg.norm(tgt - c, axis=1) * np.linalg.norm(eye - tgt, axis=1)) > 0.1
+        to, _ = P.trace(outside[facing], 0)
+        assert facing.sum() > 10000 and (to >= 0).all(), f"{(to < 0).sum()} rays from outside leaked"
+    # occlusion rays cull back faces (deviceProgram.cu:242): seen from inside, the mesh must be wound inwards to be front-facing
+    P2 = type(P)("port")
+    m = sc.meshes[0]
+    P2.add_mesh(m.vtx, m.idx[:, ::-1].copy(), m.material); P2.commit()
+    occ, _ = P2.trace(rays, 1)
+    P2.close()
+    assert (occ == 1).all(), f"{(occ == 0).sum()} shadow rays leaked"

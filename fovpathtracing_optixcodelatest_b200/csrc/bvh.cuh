@@ -58,6 +58,21 @@ struct RayStack {
 };
 __device__ __forceinline__ RayStack local_stack(int2* local) { return RayStack{local, nullptr, 0, 0}; }
 
+// Per-ray constants of the watertight triangle test (fx_rayspace of fovpt_exact.h): the nine row coefficients are written
+// once per ray and read once per leaf step; k_trace keeps them in shared memory (coefficient-major, one column per thread:
+// bank = thread), which costs the persistent warps no registers.  The three offsets stay in registers (they replace the
+// ray origin, which the slab test does not need: it uses o * idir).
+struct RayRows {
+    float* p; int stride;
+    __device__ __forceinline__ void put(const fx_rayspace& r) const
+    {
+        p[0] = r.ex.x; p[stride] = r.ex.y; p[2 * stride] = r.ex.z;
+        p[3 * stride] = r.ey.x; p[4 * stride] = r.ey.y; p[5 * stride] = r.ey.z;
+        p[6 * stride] = r.ez.x; p[7 * stride] = r.ez.y; p[8 * stride] = r.ez.z;
+    }
+    __device__ __forceinline__ fx_vec3 row(int k) const { fx_vec3 r; r.x = p[3 * k * stride]; r.y = p[(3 * k + 1) * stride]; r.z = p[(3 * k + 2) * stride]; return r; }
+};
+
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 
 struct u8x { uint4 a, b; };
@@ -118,8 +133,9 @@ constexpr int kClosest = 0, kAny = 1, kMixed = 2;
 
 template <int MODE>
 struct Traversal {
-    float3 o, idir, ood;
-    fx_shear sh;            // per-ray constants of the watertight triangle test (fovpt_exact.h); the direction itself is not kept
+    float3 idir, ood;
+    float rs_ox, rs_oy, rs_oz;     // offsets of the ray-space map (fovpt_exact.h); its rows live behind RayRows.  Origin and
+                                   // direction themselves are not kept: the slab test needs idir and o * idir only.
     float tmin, tmax;
     float best_t, best_u, best_v;
     uint32_t best_gid, best_k;
@@ -128,15 +144,17 @@ struct Traversal {
 
     __device__ __forceinline__ bool is_any() const { return MODE == kMixed ? any : MODE == kAny; }
 
-    __device__ __forceinline__ void begin(float3 o_, float3 d_, float tmin_, float tmax_)
+    __device__ __forceinline__ void begin(float3 o_, float3 d_, float tmin_, float tmax_, const RayRows& rows)
     {
         // tmax finite: unused child slots sit at +inf.  The caller guarantees tmin >= 0 (fovpt_set_config enforces it, the
         // query kernels clamp): every entry distance is then >= 0 and its bit pattern orders like the float (node_step keys).
-        o = o_; tmin = tmin_; tmax = fminf(tmax_, 3.0e38f);
+        tmin = tmin_; tmax = fminf(tmax_, 3.0e38f);
         idir = make_float3(safe_rcp(d_.x), safe_rcp(d_.y), safe_rcp(d_.z));
-        ood = make_float3(o.x * idir.x, o.y * idir.y, o.z * idir.z);
-        const fx_vec3 D = {d_.x, d_.y, d_.z};
-        sh = fx_shear_init(D);
+        ood = make_float3(o_.x * idir.x, o_.y * idir.y, o_.z * idir.z);
+        const fx_vec3 O = {o_.x, o_.y, o_.z}, D = {d_.x, d_.y, d_.z};
+        const fx_rayspace rs = fx_rayspace_init(O, D);
+        rows.put(rs);
+        rs_ox = rs.ox; rs_oy = rs.oy; rs_oz = rs.oz;
         best_t = __int_as_float(0x7f800000); best_u = best_v = 0.f; best_gid = 0xffffffffu; best_k = 0;
         cur = 0; sp = 0;
     }
@@ -217,11 +235,9 @@ struct Traversal {
 
     // `nmax` = largest triangle count among the lanes of this warp that execute the step together
     // (keeps the loop trip count warp-uniform; each lane predicates on its own count)
-    __device__ __forceinline__ void leaf_step(const DeviceBvh& bvh, const RayStack& stack, uint32_t nmax)
+    __device__ __forceinline__ void leaf_step(const DeviceBvh& bvh, const RayStack& stack, const RayRows& rows, uint32_t nmax)
     {
         const uint32_t first = leaf_first(cur), count = leaf_count(cur);
-        const fx_vec3 O = {o.x, o.y, o.z};
-        const fx_basis rb = fx_shear_basis(sh);                // once per step, not per triangle
         bool occluded = false;
         for (uint32_t i = 0; i < nmax; ++i) {
             if (i < count) {
@@ -231,8 +247,16 @@ struct Traversal {
                 tr.v0.x = a.x; tr.v0.y = a.y; tr.v0.z = a.z;
                 tr.v1.x = b.x; tr.v1.y = b.y; tr.v1.z = b.z;
                 tr.v2.x = c.x; tr.v2.y = c.y; tr.v2.z = c.z;
+                // fx_ray_tri_wt of fovpt_exact.h, row by row: each row of the ray-space map is fetched when its coordinate is
+                // computed, so only three coefficients are live at a time (all nine at once spilled at 56 registers)
                 float t, u, v;
-                const int side = fx_ray_tri_wt(O, rb, tr, &t, &u, &v);
+                fx_vec3 rw = rows.row(0);
+                const float Ax = fx_rayspace_coord(tr.v0, rw, rs_ox), Bx = fx_rayspace_coord(tr.v1, rw, rs_ox), Cx = fx_rayspace_coord(tr.v2, rw, rs_ox);
+                rw = rows.row(1);
+                const float Ay = fx_rayspace_coord(tr.v0, rw, rs_oy), By = fx_rayspace_coord(tr.v1, rw, rs_oy), Cy = fx_rayspace_coord(tr.v2, rw, rs_oy);
+                rw = rows.row(2);
+                const float Az = fx_rayspace_coord(tr.v0, rw, rs_oz), Bz = fx_rayspace_coord(tr.v1, rw, rs_oz), Cz = fx_rayspace_coord(tr.v2, rw, rs_oz);
+                const int side = fx_ray_tri_2d(Ax, Ay, Az, Bx, By, Bz, Cx, Cy, Cz, FX_ADD(FX_ADD(rw.x, rw.y), rw.z), &t, &u, &v);
                 const bool in_range = t > tmin && t < tmax;
                 if (MODE != kClosest) occluded = occluded || (side == 1 && in_range);
                 if (MODE != kAny) {
@@ -248,11 +272,11 @@ struct Traversal {
     }
 
     // scalar driver (query kernels): one ray per thread, no warp cooperation
-    __device__ __forceinline__ void run(const DeviceBvh& bvh, const RayStack& stack)
+    __device__ __forceinline__ void run(const DeviceBvh& bvh, const RayStack& stack, const RayRows& rows)
     {
         while (!done()) {
             if (at_node()) node_step(bvh, stack);
-            else leaf_step(bvh, stack, leaf_count(cur));
+            else leaf_step(bvh, stack, rows, leaf_count(cur));
         }
     }
 };
@@ -264,8 +288,10 @@ __device__ __forceinline__ bool trace_closest(const DeviceBvh& bvh, float3 o, fl
     if (bvh.n_tris == 0) return false;
     FOVPT_TRAV(kClosest) T;
     int2 stack[kStackSize];
-    T.begin(o, d, tmin, tmax);
-    T.run(bvh, local_stack(stack));
+    float rows_local[9];
+    const RayRows rows{rows_local, 1};
+    T.begin(o, d, tmin, tmax, rows);
+    T.run(bvh, local_stack(stack), rows);
     if (!T.found()) return false;
     out.t = T.best_t; out.u = T.best_u; out.v = T.best_v; out.k = T.best_k; out.gid = T.best_gid;
     return true;
@@ -276,8 +302,10 @@ __device__ __forceinline__ bool trace_any_front(const DeviceBvh& bvh, float3 o, 
     if (bvh.n_tris == 0) return false;
     FOVPT_TRAV(kAny) T;
     int2 stack[kStackSize];
-    T.begin(o, d, tmin, tmax);
-    T.run(bvh, local_stack(stack));
+    float rows_local[9];
+    const RayRows rows{rows_local, 1};
+    T.begin(o, d, tmin, tmax, rows);
+    T.run(bvh, local_stack(stack), rows);
     return T.found();
 }
 

@@ -273,11 +273,20 @@ __global__ void k_ploc_init(uint32_t n, const uint32_t* __restrict__ sorted_ids,
     cid[i] = ~(int)t; clo[i] = box_lo[t]; chi[i] = box_hi[t];
 }
 
-// nn[i] = position of the cluster within [i-R, i+R] whose union with cluster i has the smallest area
-// (ties: smaller position), boxes of the block's window staged in shared memory
+// nn[i] = position of the cluster within [i-R, i+R] whose union with cluster i has the smallest area, boxes of the
+// block's window staged in shared memory.  Ties are broken SYMMETRICALLY: first the partner i ^ 1, then the nearer
+// position -- in a run of clusters with identical boxes (duplicated or coincident triangles) every cluster then finds a
+// mutual partner and the run halves per round; "smallest position wins" made only the pair (0, 1) mutual, one merge per
+// round and a left-deep chain the collapse cannot rebalance.  forced != 0: nn[i] = i ^ 1 regardless of area -- a
+// balanced tree over the Morton order, the fallback when the area-driven tree comes out too deep for the traversal stack.
 __global__ void __launch_bounds__(kPlocThreads) k_ploc_nearest(uint32_t n, const float4* __restrict__ clo, const float4* __restrict__ chi,
-                                                               uint32_t* __restrict__ nn)
+                                                               uint32_t* __restrict__ nn, int forced)
 {
+    if (forced) {
+        const uint32_t i = blockIdx.x * kPlocThreads + threadIdx.x;
+        if (i < n) nn[i] = (i ^ 1u) < n ? (i ^ 1u) : i;
+        return;
+    }
     __shared__ float4 slo[kPlocThreads + 2 * kPlocRadius], shi[kPlocThreads + 2 * kPlocRadius];
     const int base = (int)(blockIdx.x * kPlocThreads) - kPlocRadius;
     for (int k = threadIdx.x; k < kPlocThreads + 2 * kPlocRadius; k += kPlocThreads) {
@@ -288,12 +297,13 @@ __global__ void __launch_bounds__(kPlocThreads) k_ploc_nearest(uint32_t n, const
     const int i = (int)(blockIdx.x * kPlocThreads + threadIdx.x);
     if (i >= (int)n) return;
     const float4 lo = slo[threadIdx.x + kPlocRadius], hi = shi[threadIdx.x + kPlocRadius];
-    float best = 3.0e38f; int bestj = i;
+    float best = 3.0e38f; int bestj = i, bestp = 0x7fffffff;
     for (int d = -kPlocRadius; d <= kPlocRadius; ++d) {
         const int j = i + d;
         if (d == 0 || j < 0 || j >= (int)n) continue;
         const float a = union_area(lo, hi, slo[threadIdx.x + kPlocRadius + d], shi[threadIdx.x + kPlocRadius + d]);
-        if (a < best) { best = a; bestj = j; }
+        const int pref = j == (i ^ 1) ? 0 : 2 * (d < 0 ? -d : d) + (d > 0 ? 1 : 0);      // symmetric between i and i ^ 1
+        if (a < best || (a == best && pref < bestp)) { best = a; bestj = j; bestp = pref; }
     }
     nn[i] = (uint32_t)bestj;
 }
@@ -484,8 +494,18 @@ __global__ void k_gather_tris(uint32_t n, const uint32_t* __restrict__ sorted_id
 }
 
 // ------------------------------------------------------------------ host orchestration
-template <typename T>
-static cudaError_t dalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T) + 32); }
+// Every temporary of one build; freed when the build returns, on the error paths too.
+struct Temps {
+    std::vector<void*> ptrs;
+    ~Temps() { for (void* p : ptrs) cudaFree(p); }
+    template <typename T> cudaError_t alloc(T** p, size_t n)
+    {
+        cudaError_t e = cudaMalloc((void**)p, n * sizeof(T) + 32);
+        if (e == cudaSuccess) ptrs.push_back((void*)*p); else *p = nullptr;
+        return e;
+    }
+    void release(const void* p) { for (auto& q : ptrs) if (q == p) { q = ptrs.back(); ptrs.pop_back(); return; } }   // the caller keeps it
+};
 
 // exclusive scan of data[0..n) in place; *total_out (device, may be null) receives the sum.  tile_sums: scratch of >= n / SC_TILE + 2 words
 static void scan_u32(uint32_t* data, uint32_t n, uint32_t* total_out, uint32_t* tile_sums, cudaStream_t st, uint64_t* launches)
@@ -504,8 +524,9 @@ cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, const uint32_t*
     const size_t nstride = 4;                          // uint4 per node
     out->wide = wide;
     out->nodes = nullptr; out->tris = nullptr; out->tri_rec = nullptr; out->sorted_ids = nullptr;
-    out->n_nodes = 0; out->n_tris = ntri; out->max_depth = 0;
+    out->n_nodes = 0; out->n_tris = ntri; out->max_depth = 0; out->balanced_fallback = 0;
     if (ntri == 0) return cudaSuccess;
+    Temps tmp;
     const int T = 256;
     const uint32_t gb = (ntri + T - 1) / T;
     float4 *tri_rec = nullptr, *box_lo = nullptr, *box_hi = nullptr, *nlo = nullptr, *nhi = nullptr;
@@ -520,12 +541,12 @@ cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, const uint32_t*
     uint32_t* lvl_counts = nullptr;
     const uint32_t nblocks = (ntri + RS_TILE - 1) / RS_TILE;
     const uint32_t ninner = ntri > 1 ? ntri - 1 : 1;
-    CK(dalloc(&tri_rec, 3 * (size_t)ntri)); CK(dalloc(&box_lo, ntri)); CK(dalloc(&box_hi, ntri));
-    CK(dalloc(&bounds, 8)); CK(dalloc(&keys[0], ntri)); CK(dalloc(&keys[1], ntri));
-    CK(dalloc(&vals[0], ntri)); CK(dalloc(&vals[1], ntri)); CK(dalloc(&hist, 256 * (size_t)nblocks));
-    CK(dalloc(&scal, 8)); CK(dalloc(&sorted, ntri));
+    CK(tmp.alloc(&tri_rec, 3 * (size_t)ntri)); CK(tmp.alloc(&box_lo, ntri)); CK(tmp.alloc(&box_hi, ntri));
+    CK(tmp.alloc(&bounds, 8)); CK(tmp.alloc(&keys[0], ntri)); CK(tmp.alloc(&keys[1], ntri));
+    CK(tmp.alloc(&vals[0], ntri)); CK(tmp.alloc(&vals[1], ntri)); CK(tmp.alloc(&hist, 256 * (size_t)nblocks));
+    CK(tmp.alloc(&scal, 8)); CK(tmp.alloc(&sorted, ntri));
     uint32_t* tile_sums = nullptr;
-    CK(dalloc(&tile_sums, std::max<size_t>(ntri, 256 * (size_t)nblocks) / SC_TILE + 2));
+    CK(tmp.alloc(&tile_sums, std::max<size_t>(ntri, 256 * (size_t)nblocks) / SC_TILE + 2));
     CK(cudaMemsetAsync(scal, 0, 8 * sizeof(uint32_t), st));
 
     k_init_bounds<<<1, 32, 0, st>>>(bounds);
@@ -556,64 +577,72 @@ cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, const uint32_t*
     out->pad = pad;
 
     float4* tri_sorted = nullptr; uint4* nodes = nullptr;
-    CK(dalloc(&tri_sorted, 3 * (size_t)ntri));
+    CK(tmp.alloc(&tri_sorted, 3 * (size_t)ntri));
     if ((int)ntri <= leaf_max) {
-        CK(dalloc(&nodes, nstride));
+        CK(tmp.alloc(&nodes, nstride));
         k_emit_single4<<<1, 32, 0, st>>>((int)ntri, bounds, pad, nodes);
         CK(cudaMemcpyAsync(sorted, vals[cur], ntri * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
         *launches += 1;
         out->n_nodes = 1; out->max_depth = 1;
     } else {
-        // ---- PLOC: bottom-up binary tree over the Morton-ordered clusters
-        for (int k = 0; k < 2; ++k) { CK(dalloc(&cid[k], ntri)); CK(dalloc(&clo[k], ntri)); CK(dalloc(&chi[k], ntri)); }
-        CK(dalloc(&nn, ntri)); CK(dalloc(&alive, ntri)); CK(dalloc(&pos, ntri));
-        CK(dalloc(&left, ninner)); CK(dalloc(&right, ninner)); CK(dalloc(&nlo, ninner)); CK(dalloc(&nhi, ninner)); CK(dalloc(&cnt, ninner));
-        k_ploc_init<<<gb, T, 0, st>>>(ntri, vals[cur], box_lo, box_hi, cid[0], clo[0], chi[0]);
-        *launches += 1;
-        uint32_t n = ntri; int cb = 0; uint32_t rounds = 0;
-        while (n > 1) {
-            const uint32_t g = (n + kPlocThreads - 1) / kPlocThreads;
-            k_ploc_nearest<<<g, kPlocThreads, 0, st>>>(n, clo[cb], chi[cb], nn);
-            k_ploc_merge<<<g, kPlocThreads, 0, st>>>(n, nn, cid[cb], clo[cb], chi[cb], scal + 3, left, right, nlo, nhi, cnt, alive);
-            CK(cudaMemcpyAsync(pos, alive, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-            scan_u32(pos, n, scal + 4, tile_sums, st, launches);
-            k_ploc_compact<<<g, kPlocThreads, 0, st>>>(n, alive, pos, cid[cb], clo[cb], chi[cb], cid[1 - cb], clo[1 - cb], chi[1 - cb]);
-            uint32_t n_next = 0;
-            CK(cudaMemcpyAsync(&n_next, scal + 4, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            *launches += 3;
-            if (n_next == 0 || n_next >= n) return cudaErrorUnknown;      // every round merges at least the globally closest pair
-            n = n_next; cb = 1 - cb; ++rounds;
-        }
-        out->ploc_rounds = rounds;
-        // ---- 4-wide collapse, one launch per level of the wide tree, until a level comes up empty
+        for (int k = 0; k < 2; ++k) { CK(tmp.alloc(&cid[k], ntri)); CK(tmp.alloc(&clo[k], ntri)); CK(tmp.alloc(&chi[k], ntri)); }
+        CK(tmp.alloc(&nn, ntri)); CK(tmp.alloc(&alive, ntri)); CK(tmp.alloc(&pos, ntri));
+        CK(tmp.alloc(&left, ninner)); CK(tmp.alloc(&right, ninner)); CK(tmp.alloc(&nlo, ninner)); CK(tmp.alloc(&nhi, ninner)); CK(tmp.alloc(&cnt, ninner));
         const uint32_t cap = ninner;                     // a wide node consumes at least one binary node
         const uint32_t max_levels = kMaxWideDepth + 1;
-        CK(dalloc(&nodes, nstride * (size_t)cap));
-        CK(dalloc(&items[0], cap)); CK(dalloc(&items[1], cap));
-        CK(dalloc(&lvl_counts, (size_t)max_levels + 2));
-        CK(cudaMemsetAsync(lvl_counts, 0, ((size_t)max_levels + 2) * sizeof(uint32_t), st));
-        k_seed_collapse<<<1, 32, 0, st>>>(items[0], lvl_counts, scal + 2, cid[cb]);
-        const int cgrid = (int)std::min<uint32_t>((cap + 127) / 128, 148u * 8u);
-        for (uint32_t lvl = 0; lvl < max_levels; ++lvl) {
-            k_collapse4<<<cgrid, 128, 0, st>>>(items[lvl & 1], items[(lvl + 1) & 1], lvl_counts, (int)lvl, scal + 2, left, right, cnt,
-                                              box_lo, box_hi, nlo, nhi, leaf_max, pad, nodes, sorted);
+        CK(tmp.alloc(&nodes, nstride * (size_t)cap));
+        CK(tmp.alloc(&items[0], cap)); CK(tmp.alloc(&items[1], cap));
+        CK(tmp.alloc(&lvl_counts, (size_t)max_levels + 2));
+        // Attempt 0: the area-driven PLOC tree.  Attempt 1 (only if that tree is deeper than the traversal stack allows --
+        // adversarial input such as long runs of nested boxes): forced pairing of Morton neighbours, a balanced tree of
+        // depth ceil(log2 n) <= 29, which always fits.  OptiX accepts any input; so does this builder.
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            // ---- PLOC: bottom-up binary tree over the Morton-ordered clusters
+            CK(cudaMemsetAsync(scal, 0, 8 * sizeof(uint32_t), st));
+            k_ploc_init<<<gb, T, 0, st>>>(ntri, vals[cur], box_lo, box_hi, cid[0], clo[0], chi[0]);
             *launches += 1;
-        }
-        std::vector<uint32_t> hc((size_t)max_levels + 2);
-        uint32_t n4 = 0;
-        CK(cudaMemcpyAsync(hc.data(), lvl_counts, hc.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(&n4, scal + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        uint32_t depth4 = 0;
-        while (depth4 < hc.size() && hc[depth4] > 0) ++depth4;
-        out->n_nodes = n4; out->max_depth = depth4;      // depth4 > kMaxWideDepth: tree cut off, the caller refuses it
-        if (n4 < cap) {                                  // shrink to fit
-            uint4* exact = nullptr;
-            CK(dalloc(&exact, nstride * (size_t)n4));
-            CK(cudaMemcpyAsync(exact, nodes, nstride * (size_t)n4 * sizeof(uint4), cudaMemcpyDeviceToDevice, st));
+            uint32_t n = ntri; int cb = 0; uint32_t rounds = 0;
+            while (n > 1) {
+                const uint32_t g = (n + kPlocThreads - 1) / kPlocThreads;
+                k_ploc_nearest<<<g, kPlocThreads, 0, st>>>(n, clo[cb], chi[cb], nn, attempt);
+                k_ploc_merge<<<g, kPlocThreads, 0, st>>>(n, nn, cid[cb], clo[cb], chi[cb], scal + 3, left, right, nlo, nhi, cnt, alive);
+                CK(cudaMemcpyAsync(pos, alive, n * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+                scan_u32(pos, n, scal + 4, tile_sums, st, launches);
+                k_ploc_compact<<<g, kPlocThreads, 0, st>>>(n, alive, pos, cid[cb], clo[cb], chi[cb], cid[1 - cb], clo[1 - cb], chi[1 - cb]);
+                uint32_t n_next = 0;
+                CK(cudaMemcpyAsync(&n_next, scal + 4, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                *launches += 3;
+                if (n_next == 0 || n_next >= n) return cudaErrorUnknown;      // every round merges at least the globally closest pair
+                n = n_next; cb = 1 - cb; ++rounds;
+            }
+            out->ploc_rounds = rounds;
+            // ---- 4-wide collapse, one launch per level of the wide tree, until a level comes up empty
+            CK(cudaMemsetAsync(lvl_counts, 0, ((size_t)max_levels + 2) * sizeof(uint32_t), st));
+            k_seed_collapse<<<1, 32, 0, st>>>(items[0], lvl_counts, scal + 2, cid[cb]);
+            const int cgrid = (int)std::min<uint32_t>((cap + 127) / 128, 148u * 8u);
+            for (uint32_t lvl = 0; lvl < max_levels; ++lvl) {
+                k_collapse4<<<cgrid, 128, 0, st>>>(items[lvl & 1], items[(lvl + 1) & 1], lvl_counts, (int)lvl, scal + 2, left, right, cnt,
+                                                  box_lo, box_hi, nlo, nhi, leaf_max, pad, nodes, sorted);
+                *launches += 1;
+            }
+            std::vector<uint32_t> hc((size_t)max_levels + 2);
+            uint32_t n4 = 0;
+            CK(cudaMemcpyAsync(hc.data(), lvl_counts, hc.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(&n4, scal + 2, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
-            cudaFree(nodes); nodes = exact;
+            uint32_t depth4 = 0;
+            while (depth4 < hc.size() && hc[depth4] > 0) ++depth4;
+            out->n_nodes = n4; out->max_depth = depth4;      // depth4 > kMaxWideDepth: the tree was cut off at the last level
+            if (depth4 <= kMaxWideDepth) break;
+            out->balanced_fallback = 1;
+        }
+        if (out->n_nodes < cap) {                            // shrink to fit
+            uint4* exact = nullptr;
+            CK(tmp.alloc(&exact, nstride * (size_t)out->n_nodes));
+            CK(cudaMemcpyAsync(exact, nodes, nstride * (size_t)out->n_nodes * sizeof(uint4), cudaMemcpyDeviceToDevice, st));
+            CK(cudaStreamSynchronize(st));
+            nodes = exact;
         }
     }
     k_gather_tris<<<gb, T, 0, st>>>(ntri, sorted, tri_rec, tri_sorted);
@@ -621,10 +650,7 @@ cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, const uint32_t*
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
     out->nodes = nodes; out->tris = tri_sorted; out->tri_rec = tri_rec; out->sorted_ids = sorted;
-    cudaFree(box_lo); cudaFree(box_hi); cudaFree(bounds); cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]);
-    cudaFree(hist); cudaFree(scal); cudaFree(tile_sums); cudaFree(left); cudaFree(right); cudaFree(nlo); cudaFree(nhi); cudaFree(cnt);
-    cudaFree(nn); cudaFree(alive); cudaFree(pos); cudaFree(items[0]); cudaFree(items[1]); cudaFree(lvl_counts);
-    for (int k = 0; k < 2; ++k) { cudaFree(cid[k]); cudaFree(clo[k]); cudaFree(chi[k]); }
+    tmp.release(nodes); tmp.release(tri_sorted); tmp.release(tri_rec); tmp.release(sorted);
     return cudaSuccess;
 }
 

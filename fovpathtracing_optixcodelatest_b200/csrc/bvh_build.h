@@ -14,7 +14,8 @@ struct BuiltBvh {
     const uint32_t* sorted_ids = nullptr;  // leaf slot -> global triangle id
     uint32_t        n_nodes = 0, n_tris = 0, max_depth = 0;   // max_depth: levels of the 4-wide tree
     uint32_t        ploc_rounds = 0;
-    int             wide = 4;              // 4: 64-byte nodes, 8: 96-byte compressed wide nodes (bvh.cuh)
+    int             balanced_fallback = 0; // 1: the area-driven tree was too deep for the traversal stack, a balanced Morton tree was built instead
+    int             wide = 4;              // branching factor (64-byte nodes, bvh.cuh)
     float           pad = 0.f;
     float           bounds[6] = {0, 0, 0, 0, 0, 0};
 };

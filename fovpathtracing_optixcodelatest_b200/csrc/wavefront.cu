@@ -213,7 +213,7 @@ constexpr int kFetchMin = FOVPT_FETCH_MIN;          // refill as soon as this ma
 // until every lane is done).
 template <bool THIN>
 __device__ __forceinline__ void trace_loop(const SceneDev& S, const PathState& ps, const Queues& q, int shadow_slot, float tmin, float tmax,
-                                           const RayStack& stack, uint32_t n_any, uint32_t n, uint32_t cap_in, DevStats* stats)
+                                           const RayStack& stack, const RayRows& rows, uint32_t n_any, uint32_t n, uint32_t cap_in, DevStats* stats)
 {
     constexpr unsigned FULL = 0xffffffffu;
     const uint32_t cap = THIN ? cap_in : 32u;
@@ -245,7 +245,7 @@ __device__ __forceinline__ void trace_loop(const SceneDev& S, const PathState& p
                     const bool is_any = mine < n_any;
                     pid = is_any ? mine : mine - n_any;                // slot in the shadow / radiance buffer
                     const float4 o = is_any ? q.shadow.o[pid] : q.cur.o[pid], d = is_any ? q.shadow.d[pid] : q.cur.d[pid];
-                    T.begin(make_float3(o.x, o.y, o.z), make_float3(d.x, d.y, d.z), tmin, tmax);
+                    T.begin(make_float3(o.x, o.y, o.z), make_float3(d.x, d.y, d.z), tmin, tmax, rows);
                     T.any = is_any;
                 }
                 if (base + (uint32_t)want >= n) { exhausted = true; keep = 0; }
@@ -271,7 +271,7 @@ __device__ __forceinline__ void trace_loop(const SceneDev& S, const PathState& p
 #ifdef FOVPT_TRACE_STATS
                 st_leaf_exec++; st_leaf_lanes += __popc(ml); st_leaf_nmax += nmax; st_leaf_tris += __reduce_add_sync(FULL, leaf ? T.leaf_work() : 0u);
 #endif
-                if (leaf) T.leaf_step(S.bvh, stack, nmax);
+                if (leaf) T.leaf_step(S.bvh, stack, rows, nmax);
                 stepped = leaf;
             }
             if (stepped && T.done()) {
@@ -325,9 +325,11 @@ __global__ void __launch_bounds__(128, FOVPT_TRACE_BLOCKS) k_trace(SceneDev S, P
 #else
     const RayStack stack = local_stack(stack_local);
 #endif
+    __shared__ float rows_shared[9 * 128];
+    const RayRows rows{rows_shared + threadIdx.x, 128};
     // the full-width case gets its own copy of the loop with cap / lanes / fetch_min folded into constants
-    if (cap >= 32u) trace_loop<false>(S, ps, q, shadow_slot, tmin, tmax, stack, n_any, n, 32u, stats);
-    else trace_loop<true>(S, ps, q, shadow_slot, tmin, tmax, stack, n_any, n, cap, stats);
+    if (cap >= 32u) trace_loop<false>(S, ps, q, shadow_slot, tmin, tmax, stack, rows, n_any, n, 32u, stats);
+    else trace_loop<true>(S, ps, q, shadow_slot, tmin, tmax, stack, rows, n_any, n, cap, stats);
 }
 
 // ------------------------------------------------------------------ k_shade  (closest-hit / miss program)
@@ -653,20 +655,22 @@ __global__ void k_trace_query(SceneDev S, const float* __restrict__ rays, size_t
         } else {                                       // modes 2 / 3: closest / any with visit counters in tuv
             float nodes = 0.f, leaves = 0.f, tris = 0.f;
             int2 stack_local[kStackSize];
+            float rows_local[9];
             const RayStack stack = local_stack(stack_local);
+            const RayRows rows{rows_local, 1};
             if (S.bvh.n_tris == 0) { tri[i] = mode == 2 ? -1 : 0; }
             else if (mode == 2) {
-                FOVPT_TRAV(kClosest) T; T.begin(o, d, fmaxf(r[3], 0.f), r[7]);
+                FOVPT_TRAV(kClosest) T; T.begin(o, d, fmaxf(r[3], 0.f), r[7], rows);
                 while (!T.done()) {
                     if (T.at_node()) { nodes += 1.f; T.node_step(S.bvh, stack); }
-                    else { leaves += 1.f; tris += (float)T.leaf_work(); T.leaf_step(S.bvh, stack, T.leaf_work()); }
+                    else { leaves += 1.f; tris += (float)T.leaf_work(); T.leaf_step(S.bvh, stack, rows, T.leaf_work()); }
                 }
                 tri[i] = T.found() ? (int32_t)T.best_gid : -1;
             } else {
-                FOVPT_TRAV(kAny) T; T.begin(o, d, fmaxf(r[3], 0.f), r[7]);
+                FOVPT_TRAV(kAny) T; T.begin(o, d, fmaxf(r[3], 0.f), r[7], rows);
                 while (!T.done()) {
                     if (T.at_node()) { nodes += 1.f; T.node_step(S.bvh, stack); }
-                    else { leaves += 1.f; tris += (float)T.leaf_work(); T.leaf_step(S.bvh, stack, T.leaf_work()); }
+                    else { leaves += 1.f; tris += (float)T.leaf_work(); T.leaf_step(S.bvh, stack, rows, T.leaf_work()); }
                 }
                 tri[i] = T.found() ? 1 : 0;
             }
@@ -701,7 +705,7 @@ __global__ void k_texture_probe(cudaTextureObject_t tex, const uint32_t* __restr
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         const float2 t = uv[i];
         hw[i] = tex2D<float4>(tex, t.x, t.y);
-        if (mode < 0) { const float3 c = texture_bilinear(texels, w, h, t.x, t.y); sw[i] = make_float4(c.x, c.y, c.z, 0.f); continue; }   // the product's fetch
+        if (mode < 0) { float o4[4]; fx_tex_bilinear_rgba8(texels, w, h, t.x, t.y, o4); sw[i] = make_float4(o4[0], o4[1], o4[2], o4[3]); continue; }   // the product's fetch (shade.cuh texture_bilinear)
         int x0, x1, y0, y1; float a, b;
         tex_axis(t.x, w, mode, &x0, &x1, &a); tex_axis(t.y, h, mode, &y0, &y1, &b);
         const uint32_t p00 = texels[(size_t)y0 * w + x0], p10 = texels[(size_t)y0 * w + x1], p01 = texels[(size_t)y1 * w + x0], p11 = texels[(size_t)y1 * w + x1];

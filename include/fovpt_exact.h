@@ -175,52 +175,50 @@ FX_HD fx_tri fx_make_tri(fx_vec3 a, fx_vec3 b, fx_vec3 c)
  * property OptiX's built-in triangle test has and Moeller-Trumbore has not (round 1 used the latter: of rays aimed at
  * the shared edges of a closed mesh about 20 % slipped between the two triangles).
  *
- * Per ray: the dominant direction axis kz and the shear constants that map the ray onto the +z axis of a "ray space".
- * Per vertex: its ray-space coordinates, a deterministic function of (vertex, ray) ONLY -- so two triangles that share
- * an edge see bit-identical end points.  Per edge: the 2-D edge function  p - q  with two separately rounded products,
- * which is exactly antisymmetric in its end points: the triangle on the other side of the edge computes exactly the
- * negated value.  A ray therefore never falls between two triangles that share an edge (or a vertex fan), and a value
- * of exactly zero (the ray meets the edge) is accepted by both, the closest-hit tie-break picks one.  Differences from
- * the paper: no double-precision re-evaluation of zero edge functions (over-acceptance on the edge itself is harmless
- * here), no kx/ky swap (the facing rule carries the sign of d[kz] instead), and the shear is applied as a sparse dot
- * product so that SIMT code needs no per-vertex component selects. */
+ * Per ray: an affine map into a "ray space" whose +z axis is the ray (shear along the dominant direction axis kz, then
+ * the origin moved to 0).  Per vertex: its ray-space coordinates, a deterministic function of (vertex, ray) ONLY -- so two
+ * triangles that share an edge see bit-identical end points.  Per edge: the 2-D edge function  p - q  with two separately
+ * rounded products, which is exactly antisymmetric in its end points: the triangle on the other side of the edge computes
+ * exactly the negated value.  A ray therefore never falls between two triangles that share an edge (or a vertex fan), and
+ * a value of exactly zero (the ray meets the edge) is accepted by both; the closest-hit tie-break picks one.
+ * Differences from the paper, none of which touches that argument: no double-precision re-evaluation of zero edge
+ * functions (over-acceptance on the edge itself is harmless here); no kx/ky swap (the facing rule carries the sign of
+ * d[kz] instead); the shear rows are applied as three fused multiply-adds per coordinate with the ray origin folded into
+ * the constant term, so SIMT code needs neither per-vertex component selects nor the nine vertex-minus-origin subtractions. */
 #define FX_FRONT_SIGN 1
-typedef struct { float sx, sy, sz; int kz; } fx_shear;           /* per ray */
-typedef struct { fx_vec3 ex, ey, ez; float face; } fx_basis;     /* per ray: rows of the ray-space transform */
-
-FX_HD fx_shear fx_shear_init(fx_vec3 d)
-{
-    const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
-    fx_shear s;
-    s.kz = (ax >= ay) ? (ax >= az ? 0 : 2) : (ay >= az ? 1 : 2);
-    const float dz = s.kz == 0 ? d.x : (s.kz == 1 ? d.y : d.z);
-    const float dx = s.kz == 0 ? d.y : (s.kz == 1 ? d.z : d.x);   /* kx = kz + 1 (mod 3) */
-    const float dy = s.kz == 0 ? d.z : (s.kz == 1 ? d.x : d.y);   /* ky = kz + 2 (mod 3) */
-    s.sx = FX_DIV(dx, dz); s.sy = FX_DIV(dy, dz); s.sz = FX_DIV(1.0f, dz);
-    return s;
-}
-
-/* x' = v[kx] - sx*v[kz], y' = v[ky] - sy*v[kz], z' = sz*v[kz], written as dot products with sparse rows */
-FX_HD fx_basis fx_shear_basis(fx_shear s)
-{
-    fx_basis b;
-    const float nx = -s.sx, ny = -s.sy;
-    b.ex.x = s.kz == 0 ? nx : (s.kz == 2 ? 1.0f : 0.0f);
-    b.ex.y = s.kz == 1 ? nx : (s.kz == 0 ? 1.0f : 0.0f);
-    b.ex.z = s.kz == 2 ? nx : (s.kz == 1 ? 1.0f : 0.0f);
-    b.ey.x = s.kz == 0 ? ny : (s.kz == 1 ? 1.0f : 0.0f);
-    b.ey.y = s.kz == 1 ? ny : (s.kz == 2 ? 1.0f : 0.0f);
-    b.ey.z = s.kz == 2 ? ny : (s.kz == 0 ? 1.0f : 0.0f);
-    b.ez.x = s.kz == 0 ? s.sz : 0.0f;
-    b.ez.y = s.kz == 1 ? s.sz : 0.0f;
-    b.ez.z = s.kz == 2 ? s.sz : 0.0f;
-    b.face = s.sz;            /* sign of d[kz]: orients the ray-space winding */
-    return b;
-}
+typedef struct { fx_vec3 ex, ey, ez; float ox, oy, oz; } fx_rayspace;     /* x' = ex.v - ox,  y' = ey.v - oy,  z' = ez.v - oz */
 
 FX_HD float fx_dot3_fma(fx_vec3 a, fx_vec3 b)
 {
     return FX_FMA(a.z, b.z, FX_FMA(a.y, b.y, FX_MUL(a.x, b.x)));
+}
+
+FX_HD fx_rayspace fx_rayspace_init(fx_vec3 o, fx_vec3 d)
+{
+    const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    const int kz = (ax >= ay) ? (ax >= az ? 0 : 2) : (ay >= az ? 1 : 2);
+    const float dz = kz == 0 ? d.x : (kz == 1 ? d.y : d.z);
+    const float dx = kz == 0 ? d.y : (kz == 1 ? d.z : d.x);       /* kx = kz + 1 (mod 3) */
+    const float dy = kz == 0 ? d.z : (kz == 1 ? d.x : d.y);       /* ky = kz + 2 (mod 3) */
+    const float sz = FX_DIV(1.0f, dz), nx = -FX_DIV(dx, dz), ny = -FX_DIV(dy, dz);
+    fx_rayspace r;
+    /* x' = v[kx] - sx*v[kz],  y' = v[ky] - sy*v[kz],  z' = sz*v[kz]  as sparse rows */
+    r.ex.x = kz == 0 ? nx : (kz == 2 ? 1.0f : 0.0f);
+    r.ex.y = kz == 1 ? nx : (kz == 0 ? 1.0f : 0.0f);
+    r.ex.z = kz == 2 ? nx : (kz == 1 ? 1.0f : 0.0f);
+    r.ey.x = kz == 0 ? ny : (kz == 1 ? 1.0f : 0.0f);
+    r.ey.y = kz == 1 ? ny : (kz == 2 ? 1.0f : 0.0f);
+    r.ey.z = kz == 2 ? ny : (kz == 0 ? 1.0f : 0.0f);
+    r.ez.x = kz == 0 ? sz : 0.0f;
+    r.ez.y = kz == 1 ? sz : 0.0f;
+    r.ez.z = kz == 2 ? sz : 0.0f;
+    r.ox = fx_dot3_fma(o, r.ex); r.oy = fx_dot3_fma(o, r.ey); r.oz = fx_dot3_fma(o, r.ez);
+    return r;
+}
+
+FX_HD float fx_rayspace_coord(fx_vec3 v, fx_vec3 row, float c)
+{
+    return FX_FMA(v.z, row.z, FX_FMA(v.y, row.y, FX_FMA(v.x, row.x, -c)));
 }
 
 /* The test, without early returns (SIMT-friendly; the host uses the same code so that both sides produce the same
@@ -230,15 +228,10 @@ FX_HD float fx_dot3_fma(fx_vec3 a, fx_vec3 b)
  *   returns -1: hit on the back face.
  * (u,v) are the barycentric weights of vertex 1 and vertex 2 (optixGetTriangleBarycentrics convention, used at
  * deviceProgram.cu:656-661).  The caller applies the open interval tmin < t < tmax. */
-FX_HD int fx_ray_tri_wt(fx_vec3 o, const fx_basis rb, const fx_tri tr, float* t_out, float* u_out, float* v_out)
+/* second half of the test: the vertices are already in ray space (face = 1 / d[kz], only its sign is used) */
+FX_HD int fx_ray_tri_2d(float Ax, float Ay, float Az, float Bx, float By, float Bz, float Cx, float Cy, float Cz, float face,
+                        float* t_out, float* u_out, float* v_out)
 {
-    fx_vec3 A, B, C;
-    A.x = FX_SUB(tr.v0.x, o.x); A.y = FX_SUB(tr.v0.y, o.y); A.z = FX_SUB(tr.v0.z, o.z);
-    B.x = FX_SUB(tr.v1.x, o.x); B.y = FX_SUB(tr.v1.y, o.y); B.z = FX_SUB(tr.v1.z, o.z);
-    C.x = FX_SUB(tr.v2.x, o.x); C.y = FX_SUB(tr.v2.y, o.y); C.z = FX_SUB(tr.v2.z, o.z);
-    const float Ax = fx_dot3_fma(A, rb.ex), Ay = fx_dot3_fma(A, rb.ey), Az = fx_dot3_fma(A, rb.ez);
-    const float Bx = fx_dot3_fma(B, rb.ex), By = fx_dot3_fma(B, rb.ey), Bz = fx_dot3_fma(B, rb.ez);
-    const float Cx = fx_dot3_fma(C, rb.ex), Cy = fx_dot3_fma(C, rb.ey), Cz = fx_dot3_fma(C, rb.ez);
     const float U = FX_SUB(FX_MUL(Cx, By), FX_MUL(Cy, Bx));      /* edge v1 -> v2: weight of v0 */
     const float V = FX_SUB(FX_MUL(Ax, Cy), FX_MUL(Ay, Cx));      /* edge v2 -> v0: weight of v1 */
     const float W = FX_SUB(FX_MUL(Bx, Ay), FX_MUL(By, Ax));      /* edge v0 -> v1: weight of v2 */
@@ -249,13 +242,23 @@ FX_HD int fx_ray_tri_wt(fx_vec3 o, const fx_basis rb, const fx_tri tr, float* t_
     const int neg = (U < 0.0f) | (V < 0.0f) | (W < 0.0f), pos = (U > 0.0f) | (V > 0.0f) | (W > 0.0f);
     const int ok = !(neg & pos) & (det != 0.0f) & (t == t);
     *t_out = t; *u_out = FX_MUL(V, inv); *v_out = FX_MUL(W, inv);
-    return ok ? (((det > 0.0f) == (rb.face > 0.0f)) ? FX_FRONT_SIGN : -FX_FRONT_SIGN) : 0;
+    return ok ? (((det > 0.0f) == (face > 0.0f)) ? FX_FRONT_SIGN : -FX_FRONT_SIGN) : 0;
+}
+
+FX_HD float fx_rayspace_face(const fx_rayspace rs) { return FX_ADD(FX_ADD(rs.ez.x, rs.ez.y), rs.ez.z); }   /* = 1 / d[kz]: the other two are zero */
+
+FX_HD int fx_ray_tri_wt(const fx_rayspace rs, const fx_tri tr, float* t_out, float* u_out, float* v_out)
+{
+    const float Ax = fx_rayspace_coord(tr.v0, rs.ex, rs.ox), Ay = fx_rayspace_coord(tr.v0, rs.ey, rs.oy), Az = fx_rayspace_coord(tr.v0, rs.ez, rs.oz);
+    const float Bx = fx_rayspace_coord(tr.v1, rs.ex, rs.ox), By = fx_rayspace_coord(tr.v1, rs.ey, rs.oy), Bz = fx_rayspace_coord(tr.v1, rs.ez, rs.oz);
+    const float Cx = fx_rayspace_coord(tr.v2, rs.ex, rs.ox), Cy = fx_rayspace_coord(tr.v2, rs.ey, rs.oy), Cz = fx_rayspace_coord(tr.v2, rs.ez, rs.oz);
+    return fx_ray_tri_2d(Ax, Ay, Az, Bx, By, Bz, Cx, Cy, Cz, fx_rayspace_face(rs), t_out, u_out, v_out);
 }
 
 /* one-off convenience (tests, tools): builds the per-ray constants each call */
 FX_HD int fx_ray_tri(fx_vec3 o, fx_vec3 d, const fx_tri tr, float* t_out, float* u_out, float* v_out)
 {
-    return fx_ray_tri_wt(o, fx_shear_basis(fx_shear_init(d)), tr, t_out, u_out, v_out);
+    return fx_ray_tri_wt(fx_rayspace_init(o, d), tr, t_out, u_out, v_out);
 }
 
 /* ------------------------------------------------------------------ RGBA8 texture fetch

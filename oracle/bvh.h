@@ -205,14 +205,14 @@ struct Scene {
         return t0 <= t1 * 1.0000012f + 0.0f;
     }
 
-    inline void leaf_closest(uint32_t first, int count, const fx_vec3& o, const fx_basis& d, float tmin, float tmax,
+    inline void leaf_closest(uint32_t first, int count, const fx_rayspace& d, float tmin, float tmax,
                              float& best_t, uint32_t& best_id, float& bu, float& bv, uint64_t& ntri) const
     {
         for (int i = 0; i < count; ++i) {
             uint32_t id = order[first + i];
             float t, u, v;
             ++ntri;
-            if (fx_ray_tri_wt(o, d, tris[id], &t, &u, &v) == 0) continue;
+            if (fx_ray_tri_wt(d, tris[id], &t, &u, &v) == 0) continue;
             if (!(t > tmin && t < tmax)) continue;
             if (fx_hit_better(t, id, best_t, best_id)) { best_t = t; best_id = id; bu = u; bv = v; }
         }
@@ -220,12 +220,12 @@ struct Scene {
 
     bool closest(const fx_vec3& o, const fx_vec3& dir, float tmin, float tmax, Hit* hit, Counters* ctr = nullptr) const
     {
-        const fx_basis d = fx_shear_basis(fx_shear_init(dir));      // per-ray constants of the watertight triangle test
+        const fx_rayspace d = fx_rayspace_init(o, dir);                // per-ray constants of the watertight triangle test
         float best_t = INFINITY, bu = 0, bv = 0; uint32_t best_id = 0xffffffffu;
         uint64_t nnode = 0, ntri = 0;
         if (!tris.empty()) {
             if (single_leaf) {
-                leaf_closest(0, (int)order.size(), o, d, tmin, tmax, best_t, best_id, bu, bv, ntri);
+                leaf_closest(0, (int)order.size(), d, tmin, tmax, best_t, best_id, bu, bv, ntri);
             } else {
                 RayPrep r = {{o.x, o.y, o.z}, {1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z}};
                 int stack[128]; int sp = 0; stack[sp++] = 0;
@@ -241,7 +241,7 @@ struct Scene {
                         int s = k == 0 ? first : 1 - first;
                         if (!h[s]) continue;
                         if (nd.child[s] < 0) {
-                            leaf_closest((uint32_t)~nd.child[s], nd.count[s], o, d, tmin, tmax, best_t, best_id, bu, bv, ntri);
+                            leaf_closest((uint32_t)~nd.child[s], nd.count[s], d, tmin, tmax, best_t, best_id, bu, bv, ntri);
                         }
                     }
                     // push far inner child first so the near one is popped first
@@ -262,13 +262,13 @@ struct Scene {
     // popped nodes are re-tested against the shrunken interval implicitly: the slab test above
     // was done with the limit at push time; a stale entry only costs work, never correctness.
 
-    inline bool leaf_any(uint32_t first, int count, const fx_vec3& o, const fx_basis& d, float tmin, float tmax, uint64_t& ntri) const
+    inline bool leaf_any(uint32_t first, int count, const fx_rayspace& d, float tmin, float tmax, uint64_t& ntri) const
     {
         for (int i = 0; i < count; ++i) {
             uint32_t id = order[first + i];
             float t, u, v;
             ++ntri;
-            if (fx_ray_tri_wt(o, d, tris[id], &t, &u, &v) != 1) continue;     // front faces only
+            if (fx_ray_tri_wt(d, tris[id], &t, &u, &v) != 1) continue;     // front faces only
             if (t > tmin && t < tmax) return true;
         }
         return false;
@@ -276,11 +276,11 @@ struct Scene {
 
     bool any_front(const fx_vec3& o, const fx_vec3& dir, float tmin, float tmax, Counters* ctr = nullptr) const
     {
-        const fx_basis d = fx_shear_basis(fx_shear_init(dir));
+        const fx_rayspace d = fx_rayspace_init(o, dir);
         uint64_t nnode = 0, ntri = 0; bool occ = false;
         if (!tris.empty()) {
             if (single_leaf) {
-                occ = leaf_any(0, (int)order.size(), o, d, tmin, tmax, ntri);
+                occ = leaf_any(0, (int)order.size(), d, tmin, tmax, ntri);
             } else {
                 RayPrep r = {{o.x, o.y, o.z}, {1.0f / dir.x, 1.0f / dir.y, 1.0f / dir.z}};
                 int stack[128]; int sp = 0; stack[sp++] = 0;
@@ -290,7 +290,7 @@ struct Scene {
                     for (int s = 0; s < 2 && !occ; ++s) {
                         float tn;
                         if (!slab(nd.lo[s], nd.hi[s], r, tmin, tmax, &tn)) continue;
-                        if (nd.child[s] < 0) occ = leaf_any((uint32_t)~nd.child[s], nd.count[s], o, d, tmin, tmax, ntri);
+                        if (nd.child[s] < 0) occ = leaf_any((uint32_t)~nd.child[s], nd.count[s], d, tmin, tmax, ntri);
                         else stack[sp++] = nd.child[s];
                     }
                 }

@@ -206,6 +206,32 @@ def test_degenerate_rays_and_geometry(gpu, port):
     ctx.close(); o.close()
 
 
+def test_builder_accepts_duplicated_and_nested_geometry(gpu, port):
+    """input OptiX accepts must not be refused: thousands of coincident / duplicated triangles (equal-cost clusters: the PLOC
+    tie-break must pair them up instead of chaining them) and a long run of nested triangles around one point (an area-driven
+    tree degenerates; the builder falls back to a balanced Morton tree if the wide tree gets deeper than the traversal stack)"""
+    m = Material.diffuse((.5, .5, .5))
+    sc = scenes.Scene()
+    tri = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0]], np.float32)
+    sc.add(np.tile(tri, (3000, 1)), np.arange(9000, dtype=np.uint32).reshape(3000, 3), m)            # 3000 exact duplicates
+    sc.add(np.zeros((600, 3), np.float32) + np.float32([5, 5, 5]), np.arange(600, dtype=np.uint32).reshape(200, 3), m)   # 200 collapsed to a point
+    k = (1.0 + 1.03 ** np.arange(400))[:, None, None].astype(np.float32)
+    nested = (np.array([[-1, -1, 0], [1, -1, 0], [0, 1, 0]], np.float32)[None] * k + np.float32([20, 0, 0])).reshape(-1, 3)
+    nested[:, 2] += np.repeat(np.arange(400, dtype=np.float32) * 0.01, 3)
+    sc.add(nested, np.arange(1200, dtype=np.uint32).reshape(400, 3), m)
+    o = port.Oracle("port"); o.add_scene(sc); o.commit()
+    ctx = gpu.native.Context(0); ctx.upload_scene(sc)                                                # must not raise
+    rng = np.random.default_rng(4)
+    org = rng.uniform(-3, 25, (20000, 3)); org[:, 2] = -50.0
+    d = np.tile(np.float64([0, 0, 1]), (20000, 1)) + rng.normal(size=(20000, 3)) * 0.02; d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([org, np.full((20000, 1), 0.01), d, np.full((20000, 1), 1e16)], 1).astype(np.float32)
+    for mode in (0, 1):
+        ot, otuv = o.trace(rays, mode); gt, gtuv = ctx.trace(rays, mode)
+        assert (ot == gt).all() and (bits(otuv) == bits(gtuv)).all(), mode
+    assert (ot >= 0).mean() > 0.01
+    ctx.close(); o.close()
+
+
 def test_bvh_is_valid(gpu):
     """on-device builder (Morton sort -> PLOC clustering -> collapse into quantised wide nodes, csrc/bvh.cuh layouts):
     every triangle sits in exactly one leaf, every stored child box contains all geometry below it and is no looser

@@ -200,7 +200,7 @@ FX_HD fx_rayspace fx_rayspace_init(fx_vec3 o, fx_vec3 d)
     const float dz = kz == 0 ? d.x : (kz == 1 ? d.y : d.z);
     const float dx = kz == 0 ? d.y : (kz == 1 ? d.z : d.x);       /* kx = kz + 1 (mod 3) */
     const float dy = kz == 0 ? d.z : (kz == 1 ? d.x : d.y);       /* ky = kz + 2 (mod 3) */
-    const float sz = FX_DIV(1.0f, dz), nx = -FX_DIV(dx, dz), ny = -FX_DIV(dy, dz);
+    const float sz = FX_RCP(dz), nx = -FX_MUL(dx, sz), ny = -FX_MUL(dy, sz);
     fx_rayspace r;
     /* x' = v[kx] - sx*v[kz],  y' = v[ky] - sy*v[kz],  z' = sz*v[kz]  as sparse rows */
     r.ex.x = kz == 0 ? nx : (kz == 2 ? 1.0f : 0.0f);

@@ -256,6 +256,7 @@ def native_arm(args):
             dist.all_reduce(okt, op=dist.ReduceOp.MIN)
             if int(okt[0]) == 1:
                 lp.frame.frame_buffer = shared_ptr
+                r.ctx.peer_frame_accum(True)           # every rank also mirrors the float4 accumulation value of its pixels into rank 0's memory
             else:
                 # CUDA IPC / peer access unavailable between these processes: every rank falls back to the NCCL reduce,
                 # and the result line says so (config.gather)
@@ -263,6 +264,8 @@ def native_arm(args):
                     print(f"[bench] rank {rank}: peer frame unavailable ({why}); using --gather nccl", file=sys.stderr)
                 r.ctx.peer_frame_close()
                 gather = "nccl"
+        if gather == "nccl":
+            accum_sum = torch.zeros((h, w, 4), dtype=torch.float32, device="cuda")       # reduce target: the job's accumulation buffer on rank 0
         if gather == "nccl" and rank == 0:
             # NCCL path: rank 0 renders its tiles into its own buffer; frame_t receives the sum over ranks
             frame_own = torch.zeros((h, w), dtype=torch.int32, device="cuda")
@@ -297,6 +300,8 @@ def native_arm(args):
             if rank == 0:
                 frame_t.copy_(frame_own)
             dist.reduce(frame_t, dst=0, op=dist.ReduceOp.SUM)
+            accum_sum.copy_(accum_t)                   # ranks hold disjoint pixels (zero elsewhere): the sum is the whole float image
+            dist.reduce(accum_sum, dst=0, op=dist.ReduceOp.SUM)
             if rank == 0 and consume:
                 consume()
         elif consume:
@@ -328,6 +333,47 @@ def native_arm(args):
         r.ctx.set_tile_owner(tile, owner, rank)
     elif args.emulate_world > 1:
         r.ctx.set_tile_owner(tile, owner, 0)
+    # ---- N > 1: before anything is timed, the partitioned + gathered result of one step is compared PER PIXEL with the same
+    # step rendered by rank 0 alone (RGBA8 frame and float4 accumulation buffer, bit for bit)
+    parity = None
+    if world > 1:
+        ref_frame = ref_accum = None
+        if rank == 0:
+            shared_fb = lp.frame.frame_buffer
+            lp.frame.frame_buffer = frame_t.data_ptr()          # rank 0 alone, into its private buffers
+            r.ctx.set_tile_owner(tile, None, 0)
+            accum_t.zero_(); frame_t.zero_(); lp.frame.subframe_index = 0; step_no[0] = 0
+            if wl.view_at is not None:
+                cam_k, gaze_k = wl.view_at(0); r.setCamera(cam_k); lp.frame.c_x, lp.frame.c_y = gaze_k
+            r.ctx.render_frames(lp, S); torch.cuda.synchronize()
+            ref_frame = frame_t.cpu().numpy().view(np.uint32).copy(); ref_accum = accum_t.cpu().numpy().copy()
+            lp.frame.frame_buffer = shared_fb
+            r.ctx.set_tile_owner(tile, owner, rank)
+        accum_t.zero_(); frame_t.zero_(); lp.frame.subframe_index = 0; step_no[0] = 0
+        if frame_own is not None:
+            frame_own.zero_()
+        barrier()
+        got = {}
+
+        def grab():
+            torch.cuda.current_stream().synchronize()
+            if gather == "peer":
+                got["frame"] = r.ctx.download(w, h); got["accum"] = r.ctx.download_accum(w, h)
+            else:
+                got["frame"] = frame_t.cpu().numpy().view(np.uint32).copy(); got["accum"] = accum_sum.cpu().numpy().copy()
+        if wl.view_at is not None:
+            cam_k, gaze_k = wl.view_at(0); r.setCamera(cam_k); lp.frame.c_x, lp.frame.c_y = gaze_k; step_no[0] = 1
+        r.ctx.render_frames(lp, S)
+        gather_frame(grab)
+        barrier()
+        if rank == 0:
+            dpx = int((got["frame"] != ref_frame).sum())
+            dac = int((got["accum"].view(np.uint32) != ref_accum.view(np.uint32)).any(axis=2).sum())
+            parity = {"checked": f"one step ({S} subframe(s)) rendered by {world} ranks and gathered vs the same step rendered by rank 0 alone",
+                      "frame_pixels_differing": dpx, "accum_pixels_differing_bitwise": dac, "pixels": w * h, "identical": dpx == 0 and dac == 0}
+            if not parity["identical"]:
+                print(f"[bench] WARNING: multi-GPU result differs from the 1-rank render: {parity}", file=sys.stderr)
+        accum_t.zero_(); frame_t.zero_(); lp.frame.subframe_index = 0; step_no[0] = 0
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
@@ -427,11 +473,13 @@ def native_arm(args):
                     "d2h_bytes_per_step": w * h * 4, "ms_per_step": e2e_ms / args.steps, "frame_checksum": checksum},
             "clocks": clk, "wall_s_timed_region": t_wall, "step_ms": step_ms, "per_rank": per_rank,
         }
+        if parity is not None:
+            line["multi_gpu_parity"] = parity
         if world > 1:
             line["config"]["parallelism"] = (f"{world} ranks, static interleaved {tile}-px screen tiles (gaze-independent)" if wl.view_at is not None
                                              else f"{world} ranks, screen tiles of {tile} px weighted by foveal sample density")
-            line["config"]["gather"] = ("peer stores into rank 0's frame over NVLink (CUDA IPC), fused into k_resolve_px; device-side arrival/release flags"
-                                        if gather == "peer" else "one NCCL reduce(SUM) of zero-filled RGBA8 frames per step")
+            line["config"]["gather"] = ("peer stores of the RGBA8 pixel and the float4 accumulation value into rank 0's memory over NVLink (CUDA IPC), fused into k_resolve_px; device-side arrival/release flags"
+                                        if gather == "peer" else "NCCL reduce(SUM) of the zero-filled RGBA8 frame and of the float4 accumulation buffer per step")
         ab = algorithmic_bytes(wl.name)
         if args.kernel_times and ext_ms > 0:
             # k_trace serves both ray kinds in one launch (stats field last_extend_ms carries its time)

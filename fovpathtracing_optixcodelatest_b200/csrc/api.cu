@@ -1,6 +1,7 @@
 // api.cu -- the C ABI of libfovpt (include/fovpt.h): context, scene ingest, probe, frame buffers and
 // the frame scheduler that strings the wavefront kernels together.  Each entry point names, in
 // fovpt.h, the reference host function it stands in for (PT_sv5_/SimplePathtracer.cpp).
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -522,6 +523,10 @@ int fovpt_scene_commit(fovpt_ctx* c, uint64_t* traversable_out)
 {
     if (!c) return 1;
     cudaSetDevice(c->device);
+    const bool trace = getenv("FOVPT_BUILD_TRACE") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_last = now();
+    auto phase = [&](const char* name) { if (trace) { const double t = now(); fprintf(stderr, "[fovpt commit] %-27s %9.3f ms\n", name, t - t_last); t_last = t; } };
     free_scene(c);
     size_t nv = 0, nt = 0;
     for (auto& m : c->meshes) { nv += m.vtx.size() / 3; nt += m.idx.size() / 3; }
@@ -550,6 +555,7 @@ int fovpt_scene_commit(fovpt_ctx* c, uint64_t* traversable_out)
         tex_info.push_back(make_int4((int)texels.size(), t.w, t.h, 0));
         texels.insert(texels.end(), t.px.begin(), t.px.end());
     }
+    phase("flatten meshes (host)");
     CU(dmalloc(&c->d_vtx, vtx.size())); CU(dmalloc(&c->d_idx, idx.size())); CU(dmalloc(&c->d_tri_mesh, tri_mesh.size()));
     CU(dmalloc(&c->d_tc, nv)); CU(dmalloc(&c->d_mat, mats.size())); CU(dmalloc(&c->d_mesh_tex, mesh_tex.size()));
     CU(dmalloc(&c->d_tex_info, tex_info.size())); CU(dmalloc(&c->d_texels, texels.size()));
@@ -562,6 +568,7 @@ int fovpt_scene_commit(fovpt_ctx* c, uint64_t* traversable_out)
     CU(cudaMemcpy(c->d_tex_info, tex_info.data(), tex_info.size() * sizeof(int4), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(c->d_texels, texels.data(), texels.size() * 4, cudaMemcpyHostToDevice));
 
+    phase("allocate + upload");
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, c->stream);
     int leaf_max = 2;        // measured on C3: 2 -> 4.49 ms, 3 -> 4.52 ms, 4 -> 4.56 ms of k_trace per frame
@@ -572,6 +579,7 @@ int fovpt_scene_commit(fovpt_ctx* c, uint64_t* traversable_out)
     cudaEventSynchronize(e1);
     cudaEventElapsedTime(&c->build_ms, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
+    phase("build_bvh");
     static_assert(3 * kMaxWideDepth + 1 <= (uint32_t)kStackSize, "traversal stack must hold 3 deferred children per level");
     if (c->bvh.max_depth > kMaxWideDepth) return fail(c, "BVH deeper than the traversal stack allows (3 deferred children per level)");
 

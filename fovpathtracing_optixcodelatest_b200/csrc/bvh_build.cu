@@ -26,6 +26,8 @@
 // independent of the tree (tie-break in fx_hit_better), so tree quality is purely a speed matter.
 #include <algorithm>
 #include <cfloat>
+#include <chrono>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -526,6 +528,17 @@ cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, const uint32_t*
     out->nodes = nullptr; out->tris = nullptr; out->tri_rec = nullptr; out->sorted_ids = nullptr;
     out->n_nodes = 0; out->n_tris = ntri; out->max_depth = 0; out->balanced_fallback = 0;
     if (ntri == 0) return cudaSuccess;
+    // FOVPT_BUILD_TRACE=1: host wall time per phase on stderr (phases end with a stream synchronise only when tracing)
+    const bool trace = getenv("FOVPT_BUILD_TRACE") != nullptr;
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t_last = now();
+    auto phase = [&](const char* name) {
+        if (!trace) return;
+        cudaStreamSynchronize(st);
+        const double t = now();
+        fprintf(stderr, "[fovpt build] %-28s %9.3f ms\n", name, t - t_last);
+        t_last = now();
+    };
     Temps tmp;
     const int T = 256;
     const uint32_t gb = (ntri + T - 1) / T;
@@ -548,11 +561,13 @@ cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, const uint32_t*
     uint32_t* tile_sums = nullptr;
     CK(tmp.alloc(&tile_sums, std::max<size_t>(ntri, 256 * (size_t)nblocks) / SC_TILE + 2));
     CK(cudaMemsetAsync(scal, 0, 8 * sizeof(uint32_t), st));
+    phase("allocate (sort stage)");
 
     k_init_bounds<<<1, 32, 0, st>>>(bounds);
     k_tri_setup<<<gb, T, 0, st>>>(d_vtx, d_idx, d_tri_mesh, ntri, tri_rec, box_lo, box_hi, bounds);
     k_morton<<<gb, T, 0, st>>>(box_lo, box_hi, ntri, bounds, keys[0], vals[0]);
     *launches += 3;
+    phase("triangle setup + morton");
     int cur = 0;
     for (int pass = 0; pass < 8; ++pass) {
         const int shift = pass * 8;
@@ -562,6 +577,7 @@ cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, const uint32_t*
         cur = 1 - cur;
         *launches += 2;
     }
+    phase("radix sort");
     // scene pad needs the bounds on the host
     int hb[6];
     CK(cudaMemcpyAsync(hb, bounds, sizeof(hb), cudaMemcpyDeviceToHost, st));
@@ -593,6 +609,7 @@ cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, const uint32_t*
         CK(tmp.alloc(&nodes, nstride * (size_t)cap));
         CK(tmp.alloc(&items[0], cap)); CK(tmp.alloc(&items[1], cap));
         CK(tmp.alloc(&lvl_counts, (size_t)max_levels + 2));
+        phase("allocate (tree stage)");
         // Attempt 0: the area-driven PLOC tree.  Attempt 1 (only if that tree is deeper than the traversal stack allows --
         // adversarial input such as long runs of nested boxes): forced pairing of Morton neighbours, a balanced tree of
         // depth ceil(log2 n) <= 29, which always fits.  OptiX accepts any input; so does this builder.
@@ -617,6 +634,7 @@ cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, const uint32_t*
                 n = n_next; cb = 1 - cb; ++rounds;
             }
             out->ploc_rounds = rounds;
+            phase("PLOC rounds");
             // ---- 4-wide collapse, one launch per level of the wide tree, until a level comes up empty
             CK(cudaMemsetAsync(lvl_counts, 0, ((size_t)max_levels + 2) * sizeof(uint32_t), st));
             k_seed_collapse<<<1, 32, 0, st>>>(items[0], lvl_counts, scal + 2, cid[cb]);
@@ -634,6 +652,7 @@ cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, const uint32_t*
             uint32_t depth4 = 0;
             while (depth4 < hc.size() && hc[depth4] > 0) ++depth4;
             out->n_nodes = n4; out->max_depth = depth4;      // depth4 > kMaxWideDepth: the tree was cut off at the last level
+            phase("collapse");
             if (depth4 <= kMaxWideDepth) break;
             out->balanced_fallback = 1;
         }
@@ -645,10 +664,12 @@ cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, const uint32_t*
             nodes = exact;
         }
     }
+    phase("shrink to fit");
     k_gather_tris<<<gb, T, 0, st>>>(ntri, sorted, tri_rec, tri_sorted);
     *launches += 1;
     CK(cudaStreamSynchronize(st));
     CK(cudaGetLastError());
+    phase("gather triangles");
     out->nodes = nodes; out->tris = tri_sorted; out->tri_rec = tri_rec; out->sorted_ids = sorted;
     tmp.release(nodes); tmp.release(tri_sorted); tmp.release(tri_rec); tmp.release(sorted);
     return cudaSuccess;

@@ -319,6 +319,8 @@ def native_arm(args):
         r.ctx.set_tile_owner(tile, None, 0)
     r.ctx.reset_stats(); lp.frame.subframe_index = 0
     if rank == 0 or world == 1:
+        job_fb = lp.frame.frame_buffer
+        lp.frame.frame_buffer = frame_t.data_ptr()      # a counting pass must not leave pixels in the job's shared frame
         if wl.view_at is not None and world > 1:       # moving gaze: the count changes with the gaze point -> the K views of the timed region
             for k in range(args.steps):
                 cam_k, gaze_k = wl.view_at(k)
@@ -327,6 +329,7 @@ def native_arm(args):
             torch.cuda.synchronize()
         else:
             r.ctx.render_frame(lp); torch.cuda.synchronize()
+        lp.frame.frame_buffer = job_fb
     frame_samples = float(r.ctx.stats()["samples"])    # (moving gaze at N>1: the total of the K timed frames)
     if world > 1:
         fs = torch.tensor([frame_samples], dtype=torch.float64, device="cuda"); dist.broadcast(fs, src=0); frame_samples = float(fs[0])

@@ -59,6 +59,16 @@ def algorithmic_bytes(workload_name):
     return None
 
 
+def issue_profile(workload_name):
+    """ncu-measured constants of k_trace per workload (profiles/issue_slots_r02.json: warp instructions per ray, lanes per warp
+    instruction, DRAM / L2 bytes per ray) -- what turns the live rays/s of this run into an issue-slot fraction"""
+    p = os.path.join(ROOT, "profiles", "issue_slots_r02.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get(workload_name)
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -492,15 +502,35 @@ def native_arm(args):
                 n_trace_launches = int(st["trace_launches"]) if world == 1 else args.steps * (wl.max_depth + 2)
                 alg_bytes = (rad / world) * b_closest + (shw / world) * b_any              # per GPU, whole timed region
                 achieved = alg_bytes / (ext_ms * 1e-3) / 1e9
+                ip = issue_profile(wl.name)
+                rays_in_kernel = ((rad + shw) / world) / (ext_ms * 1e-3)                   # per GPU
                 line["roofline"] = {"bound": "hbm", "kernel": "k_trace", "achieved": achieved, "peak": hbm, "unit": "GB/s",
-                                    "frac": achieved / hbm, "traffic": ab.get("measured_dram_bytes_per_launch"),
+                                    "frac": achieved / hbm,
+                                    # measured DRAM bytes per launch (ncu --set full, dram__bytes_read + write) exist for the 1-GPU launch shape only
+                                    "traffic": (ip or {}).get("measured_dram_bytes_per_launch") if world == 1 else None,
                                     "peak_source": peak_src, "bytes_per_ray": {"closest": b_closest, "any": b_any},
                                     "launches": n_trace_launches, "algorithmic_bytes_per_launch": alg_bytes / n_trace_launches,
                                     "avg_launch_ms": ext_ms / n_trace_launches,
-                                    "rays_per_s_in_kernel": ((rad + shw) / world) / (ext_ms * 1e-3),
+                                    "rays_per_s_in_kernel": rays_in_kernel,
                                     "note": "algorithmic bytes = oracle canonical-BVH node visits*64 + triangle tests*48 + 48 per ray "
-                                            "(DESIGN.md section 5); the BVH is L2-resident, so DRAM traffic (`traffic`, ncu) is far below "
-                                            "this by construction and L1 wavefronts / issue slots are what binds the kernel (profiles/)"}
+                                            "(DESIGN.md section 5).  Measured DRAM traffic is 59 B/ray on C3 (tree L2-resident) and 147 B/ray on C5 "
+                                            "(10 M triangles, tree > L2; ncu, profiles/ncu_r02f_*): L1/L2 absorb > 90 % of the algorithmic bytes on every "
+                                            "workload, so HBM is not what binds k_trace -- issue slots are, see roofline_issue"}
+                if ip and clk and clk.get("sm_mhz"):
+                    # issue-slot roofline: one warp instruction per SM sub-partition and clock.  warp_inst_per_ray is an ncu constant of this
+                    # build (smsp__inst_executed.sum of the k_trace launches of one step / rays in them); everything else is live.
+                    n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+                    peak_issue = 4.0 * n_sm * clk["sm_mhz"] * 1e6
+                    ach_issue = rays_in_kernel * ip["warp_inst_per_ray"]
+                    line["roofline_issue"] = {"bound": "issue-slots", "kernel": "k_trace", "achieved": ach_issue / 1e9, "peak": peak_issue / 1e9,
+                                              "unit": "G warp-instructions/s", "frac": ach_issue / peak_issue,
+                                              "warp_inst_per_ray": ip["warp_inst_per_ray"], "lanes_per_warp_inst": ip["lanes_per_warp_inst"],
+                                              "useful_lane_frac": ach_issue / peak_issue * ip["lanes_per_warp_inst"] / 32.0,
+                                              "sm_mhz_under_load": clk["sm_mhz"], "ncu_issue_active_pct": ip["issue_active_pct_weighted"],
+                                              "l2_bytes_per_ray": ip["l2_bytes_per_ray"], "l2_GBps": rays_in_kernel * ip["l2_bytes_per_ray"] / 1e9,
+                                              "dram_bytes_per_ray": ip["measured_dram_bytes_per_ray"], "dram_GBps": rays_in_kernel * ip["measured_dram_bytes_per_ray"] / 1e9,
+                                              "note": "peak = 4 sub-partitions x SMs x SM clock sampled during the timed region; warp_inst_per_ray, "
+                                                      "lanes, L2 / DRAM bytes per ray from profiles/issue_slots_r02.json (ncu --set full of one step, N = 1 launch shapes)"}
         if world == 1 and not args.no_cpu_baseline:
             dt1, _, _, _ = run_oracle_frames(wl, 1)                       # sizes the sample: about 12 s of host work
             nfr = int(min(16, max(1, round(12.0 / max(dt1, 1e-3)))))

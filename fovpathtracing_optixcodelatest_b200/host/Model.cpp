@@ -1,11 +1,11 @@
 // Model.cpp -- OBJ / MTL ingest behind the reference's loadOBJ / addBox interface (PT_sv5_/Model.h:45-47).
 //
 // The reference parses with the vendored tinyobjloader and decodes textures with stb_image; neither is
-// reproduced here.  This is a small self-contained reader for the subset those calls exercised:
+// vendored here.  This is a small self-contained reader for the subset those calls exercised:
 //   OBJ : v, vn, vt, f (v, v/vt, v//vn, v/vt/vn; negative indices; polygons), o, g, usemtl, mtllib
 //   MTL : newmtl, Kd, Ke, map_Kd
-//   textures : binary PPM (P6) and uncompressed 24/32-bit BMP -- other formats are reported and skipped
-//              (diffuseTextureID = -1), exactly what the reference does when stb_image cannot decode a file
+//   textures : PNG, TGA, JPEG, BMP, PPM through host/ImageDecode.cpp (own decoders, texel-identical to the
+//              reference's); undecodable files are reported and skipped (diffuseTextureID = -1) as in the reference
 // Resulting Model, as the reference produces it (Model.cpp:138-217):
 //   * a new shape starts at every `o` / `g`; one TriangleMesh per (shape, material id), shapes in file
 //     order, material ids ascending inside a shape; meshes without faces are dropped;
@@ -16,6 +16,7 @@
 //   * faces with more than three vertices are split as a fan (tinyobjloader ear-clips: same triangles for
 //     convex faces); faces without a usemtl get a default Material instead of the reference's materials[-1] read.
 #include "Model.h"
+#include "ImageDecode.h"
 
 #include <algorithm>
 #include <cstdio>
@@ -112,64 +113,6 @@ Corner parse_corner(const std::string& tok, int nv, int nvt, int nvn)
     return c;
 }
 
-bool read_ppm(const std::string& path, int& w, int& h, std::vector<uint32_t>& px)
-{
-    FILE* f = std::fopen(path.c_str(), "rb");
-    if (!f) return false;
-    char magic[3] = {0, 0, 0};
-    int maxv = 0;
-    auto next_int = [&](int& out) {
-        int c = std::fgetc(f);
-        while (c == '#' || std::isspace(c)) { if (c == '#') while (c != '\n' && c != EOF) c = std::fgetc(f); else c = std::fgetc(f); }
-        if (c == EOF) return false;
-        std::ungetc(c, f);
-        return std::fscanf(f, "%d", &out) == 1;
-    };
-    bool ok = std::fread(magic, 1, 2, f) == 2 && magic[0] == 'P' && magic[1] == '6' && next_int(w) && next_int(h) && next_int(maxv) && maxv == 255 && w > 0 && h > 0;
-    if (ok) {
-        std::fgetc(f);                                   // the single whitespace after maxval
-        std::vector<unsigned char> rgb((size_t)w * h * 3);
-        ok = std::fread(rgb.data(), 1, rgb.size(), f) == rgb.size();
-        if (ok) {
-            px.resize((size_t)w * h);
-            for (size_t i = 0; i < px.size(); ++i) px[i] = rgb[3 * i] | (rgb[3 * i + 1] << 8) | (rgb[3 * i + 2] << 16) | (255u << 24);
-        }
-    }
-    std::fclose(f);
-    return ok;
-}
-
-bool read_bmp(const std::string& path, int& w, int& h, std::vector<uint32_t>& px)
-{
-    FILE* f = std::fopen(path.c_str(), "rb");
-    if (!f) return false;
-    unsigned char hd[54];
-    bool ok = std::fread(hd, 1, 54, f) == 54 && hd[0] == 'B' && hd[1] == 'M';
-    if (ok) {
-        auto u32 = [&](int o) { return (uint32_t)hd[o] | ((uint32_t)hd[o + 1] << 8) | ((uint32_t)hd[o + 2] << 16) | ((uint32_t)hd[o + 3] << 24); };
-        const uint32_t off = u32(10); w = (int)u32(18); int hh = (int)u32(22);
-        const int bpp = hd[28] | (hd[29] << 8); const uint32_t comp = u32(30);
-        const bool top_down = hh < 0; h = top_down ? -hh : hh;
-        ok = (bpp == 24 || bpp == 32) && comp == 0 && w > 0 && h > 0;
-        if (ok) {
-            const size_t stride = ((size_t)w * (bpp / 8) + 3) & ~(size_t)3;
-            std::vector<unsigned char> row(stride);
-            px.resize((size_t)w * h);
-            std::fseek(f, (long)off, SEEK_SET);
-            for (int y = 0; y < h && ok; ++y) {
-                ok = std::fread(row.data(), 1, stride, f) == stride;
-                const int dst_y = top_down ? y : h - 1 - y;               // store top row first, like stb_image
-                for (int x = 0; x < w; ++x) {
-                    const unsigned char* p = &row[(size_t)x * (bpp / 8)];
-                    px[(size_t)dst_y * w + x] = p[2] | (p[1] << 8) | (p[0] << 16) | ((bpp == 32 ? p[3] : 255u) << 24);
-                }
-            }
-        }
-    }
-    std::fclose(f);
-    return ok;
-}
-
 // returns the texture id in model->textures, or -1 (reference loadTexture, Model.cpp:87-136)
 int load_texture(Model* model, std::map<std::string, int>& known, const std::string& name, const std::string& model_dir)
 {
@@ -181,7 +124,8 @@ int load_texture(Model* model, std::map<std::string, int>& known, const std::str
     file = model_dir + file;
     int w = 0, h = 0; std::vector<uint32_t> px;
     int id = -1;
-    if (read_ppm(file, w, h, px) || read_bmp(file, w, h, px)) {
+    std::string why;
+    if (fovpt_image::decode_file(file, w, h, px, &why)) {
         Texture* t = new Texture;
         t->resolution = make_int2(w, h);
         t->pixel = new uint32_t[(size_t)w * h];
@@ -190,7 +134,7 @@ int load_texture(Model* model, std::map<std::string, int>& known, const std::str
         id = (int)model->textures.size();
         model->textures.push_back(t);
     } else {
-        std::cout << "Could not load texture from " << file << "!" << std::endl;
+        std::cout << "Could not load texture from " << file << "! (" << why << ")" << std::endl;
     }
     known[name] = id;
     return id;

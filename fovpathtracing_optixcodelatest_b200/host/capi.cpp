@@ -5,6 +5,7 @@
 #include <stdexcept>
 #include <string>
 
+#include "ImageDecode.h"
 #include "SimplePathtracer.h"
 
 namespace { thread_local std::string g_err; }
@@ -66,6 +67,15 @@ int fovpth_texture_get(const Model* m, int i, int* w, int* h, uint32_t* out)
     const Texture* t = m->textures[i];
     *w = t->resolution.x; *h = t->resolution.y;
     if (out) std::memcpy(out, t->pixel, (size_t)t->resolution.x * t->resolution.y * 4);
+    return 0;
+}
+
+// decode one image file with the texture decoders; *w,*h always, pixels when `out` has room for them
+int fovpth_decode_image(const char* path, int* w, int* h, uint32_t* out, size_t capacity)
+{
+    std::vector<uint32_t> px; std::string why;
+    if (!fovpt_image::decode_file(path, *w, *h, px, &why)) { g_err = why; return -1; }
+    if (out && capacity >= px.size()) std::memcpy(out, px.data(), px.size() * 4);
     return 0;
 }
 

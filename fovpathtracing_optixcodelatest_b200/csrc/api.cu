@@ -65,6 +65,8 @@ struct fovpt_ctx {
     PathState ps{};
     Queues q{};
     size_t li_cap = 0, needed_cap = 0; float4* li_backplate = nullptr; float4* li_color = nullptr; uint8_t* needed = nullptr;
+    size_t li_feat_cap = 0; float4 *li_normal = nullptr, *li_albedo = nullptr;      // fovpt_config.features only
+    float4 *fb_color = nullptr, *fb_normal = nullptr, *fb_albedo = nullptr;         // fovpt_feature_buffers
     size_t px_cap = 0; uint32_t* owner_map = nullptr;
     std::vector<unsigned char> owner_key;      // what the cached owner map was computed for
     DevStats* d_stats = nullptr;
@@ -130,7 +132,7 @@ void free_scene(fovpt_ctx* c)
 
 void free_paths(fovpt_ctx* c)
 {
-    cudaFree(c->ps.direct); cudaFree(c->ps.indirect); cudaFree(c->ps.alpha);
+    cudaFree(c->ps.direct); cudaFree(c->ps.indirect); cudaFree(c->ps.alpha); cudaFree(c->ps.feat_n); cudaFree(c->ps.feat_a);
     for (RayBuf* b : {&c->q.cur, &c->q.next}) { cudaFree(b->o); cudaFree(b->d); cudaFree(b->thr); cudaFree(b->rng); cudaFree(b->meta); *b = RayBuf{}; }
     cudaFree(c->q.shadow.o); cudaFree(c->q.shadow.d); cudaFree(c->q.shadow.pend); cudaFree(c->q.shadow.pid); c->q.shadow = ShadowBuf{};
     cudaFree(c->q.hit); c->q.hit = nullptr;
@@ -139,9 +141,12 @@ void free_paths(fovpt_ctx* c)
 
 int ensure_paths(fovpt_ctx* c, size_t n)
 {
-    if (n <= c->path_cap) return 0;
+    const bool feat = c->cfg.features != 0;
+    if (n <= c->path_cap && (!feat || c->ps.feat_n)) return 0;
+    n = std::max(n, c->path_cap);
     free_paths(c);
     CU(dmalloc(&c->ps.direct, n)); CU(dmalloc(&c->ps.indirect, n)); CU(dmalloc(&c->ps.alpha, n));
+    if (feat) { CU(dmalloc(&c->ps.feat_n, n)); CU(dmalloc(&c->ps.feat_a, n)); }
     for (RayBuf* b : {&c->q.cur, &c->q.next}) {
         CU(dmalloc(&b->o, n)); CU(dmalloc(&b->d, n)); CU(dmalloc(&b->thr, n)); CU(dmalloc(&b->rng, n)); CU(dmalloc(&b->meta, n));
     }
@@ -159,6 +164,12 @@ int ensure_li(fovpt_ctx* c, size_t n, size_t n_needed)
         c->li_backplate = nullptr; c->li_color = nullptr; c->li_cap = 0;
         CU(dmalloc(&c->li_backplate, n)); CU(dmalloc(&c->li_color, n));
         c->li_cap = n;
+    }
+    if (c->cfg.features && n > c->li_feat_cap) {
+        cudaFree(c->li_normal); cudaFree(c->li_albedo);
+        c->li_normal = nullptr; c->li_albedo = nullptr; c->li_feat_cap = 0;
+        CU(dmalloc(&c->li_normal, n)); CU(dmalloc(&c->li_albedo, n));
+        c->li_feat_cap = n;
     }
     if (n_needed > c->needed_cap) {
         cudaFree(c->needed); c->needed = nullptr; c->needed_cap = 0;
@@ -204,6 +215,7 @@ void fill_frame(fovpt_ctx* c, const LaunchParamsBlob& lp, const std::vector<Pass
         F->guide.gy = c->p_gy; F->guide.gx = c->p_gx;
     }
     F->accum = lp.frame.accum_buffer; F->frame = lp.frame.frame_buffer;
+    if (c->cfg.features) { F->feat_color = lp.frame.color_buffer; F->feat_normal = lp.frame.normal_buffer; F->feat_albedo = lp.frame.albedo_buffer; }
     F->npass = (int)passes.size();
     size_t li = 0;
     for (size_t p = 0; p < passes.size(); ++p) {
@@ -322,24 +334,27 @@ int run_frame(fovpt_ctx* c, const LaunchParamsBlob& lp, const std::vector<PassHo
     if (max_paths >= 0xff000000ull) return fail(c, "path batch exceeds 32-bit ids");
     if (ensure_paths(c, max_paths)) return 1;
 
+    const bool feat = c->cfg.features != 0;
+    PathState ps = c->ps;
+    if (!feat) { ps.feat_n = nullptr; ps.feat_a = nullptr; }
     const int iters = c->cfg.max_depth + 1 + (c->scene.any_catcher ? 4 : 0);
     for (auto& g : groups) {
         mark(c, K_RAYGEN);
         CU(cudaMemsetAsync(c->q.counts, 0, 8 * sizeof(uint32_t), c->stream));
-        launch_raygen(c->L, F, g.gen, c->needed, c->ps, c->q, c->li_backplate, c->d_stats); c->launches++;
+        launch_raygen(c->L, F, g.gen, c->needed, ps, c->q, c->li_backplate, c->d_stats); c->launches++;
         // iteration i: k_trace extends the radiance rays of bounce i and resolves the shadow rays that
         // k_shade(i-1) emitted (counter slot alternates 2 / 5), k_shade(i) consumes the hits.
         for (int it = 0; it <= iters; ++it) {
             const int slot_prev = (it & 1) ? 2 : 5, slot_new = (it & 1) ? 5 : 2;
             mark(c, K_EXTEND);
-            launch_trace(c->L, c->scene, c->ps, c->q, slot_prev, c->cfg.tmin, c->cfg.tmax, c->d_stats); c->launches++; c->trace_launches++;
+            launch_trace(c->L, c->scene, ps, c->q, slot_prev, c->cfg.tmin, c->cfg.tmax, c->d_stats); c->launches++; c->trace_launches++;
             if (it == iters) break;                      // the last launch only drains the final shadow rays
             mark(c, K_SHADE);
-            launch_shade(c->L, F, c->scene, c->ps, c->q, slot_new, c->cfg.fast_math != 0); c->launches++;
+            launch_shade(c->L, F, c->scene, ps, c->q, slot_new, c->cfg.fast_math != 0); c->launches++;
             std::swap(c->q.cur, c->q.next);                // the device-side counters are swapped by k_shade's last CTA
         }
         mark(c, K_RESOLVE);
-        launch_resolve_li(c->L, F, g.res, c->needed, c->ps, c->li_backplate, c->li_color); c->launches++;
+        launch_resolve_li(c->L, F, g.res, c->needed, c->ps, c->li_backplate, c->li_color, feat ? c->li_normal : nullptr, feat ? c->li_albedo : nullptr); c->launches++;
     }
     // a contributor to a shared frame stores its pixels into the owner's memory: not before the owner released the last frame
     float4* mirror = nullptr;
@@ -348,7 +363,7 @@ int run_frame(fovpt_ctx* c, const LaunchParamsBlob& lp, const std::vector<PassHo
             launch_peer_wait(c->L, c->peer.flags + kPeerRelease, 1, -1, c->peer.seq, c->peer.d_err, c->peer.timeout_clocks);
         if (c->peer.mirror_accum) mirror = c->peer.accum;
     }
-    launch_resolve_px(c->L, F, c->owner_map, c->li_color, c->needed, mirror, c->cfg.fast_math != 0); c->launches++;
+    launch_resolve_px(c->L, F, c->owner_map, c->li_color, c->needed, mirror, feat ? c->li_normal : nullptr, feat ? c->li_albedo : nullptr, c->cfg.fast_math != 0); c->launches++;
     cudaEventRecord(c->ev_frame1, c->stream);
     nvtx_pop();
     c->frame_timed = true;
@@ -410,7 +425,7 @@ void fovpt_default_config(fovpt_config* k)
     memset(k, 0, sizeof(*k));
     k->max_depth = 4; k->tmin = 0.01f; k->tmax = 1e16f; k->exposure = 16.0f; k->accumulate = 0; k->foveated = 1;
     k->inner_radius = 74; k->outer_radius = 241; k->spp_periphery = 8; k->spp_mid = 16; k->spp_fovea = 32; k->spp_uniform = 4;
-    k->seed_all_passes_with_subframe = 0; k->skip_wasted_trace = 1; k->fast_math = 0; k->filter = 0;
+    k->seed_all_passes_with_subframe = 0; k->skip_wasted_trace = 1; k->fast_math = 0; k->filter = 0; k->features = 0;
 }
 
 int fovpt_create(fovpt_ctx** out, int device, void* stream)
@@ -453,6 +468,7 @@ int fovpt_destroy(fovpt_ctx* c)
     free_scene(c); free_paths(c);
     cudaFree(c->p_data); cudaFree(c->p_pdfX); cudaFree(c->p_cdfX); cudaFree(c->p_pdfY); cudaFree(c->p_cdfY); cudaFree(c->p_gy); cudaFree(c->p_gx);
     cudaFree(c->fb_accum); cudaFree(c->fb_frame); cudaFree(c->li_backplate); cudaFree(c->li_color); cudaFree(c->needed);
+    cudaFree(c->li_normal); cudaFree(c->li_albedo); cudaFree(c->fb_color); cudaFree(c->fb_normal); cudaFree(c->fb_albedo);
     cudaFree(c->owner_map); cudaFree(c->q.counts); cudaFree(c->d_stats); cudaFree(c->d_tile_owner);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     for (auto& m : c->marks) cudaEventDestroy(m.ev);
@@ -472,6 +488,7 @@ int fovpt_set_config(fovpt_ctx* c, const fovpt_config* k)
     if (k->foveated && (k->inner_radius < 0 || k->outer_radius < k->inner_radius)) return fail(c, "bad radii");
     if (k->spp_periphery <= 0 || k->spp_mid <= 0 || k->spp_fovea <= 0 || k->spp_uniform <= 0) return fail(c, "spp must be positive");
     if (k->filter < 0 || k->filter > 1) return fail(c, "filter must be 0 (box) or 1 (bilinear)");
+    if (k->features < 0 || k->features > 1) return fail(c, "features must be 0 or 1");
     if (!(k->tmin >= 0.f) || !(k->tmax > k->tmin)) return fail(c, "need 0 <= tmin < tmax");
     c->cfg = *k;
     return 0;
@@ -630,8 +647,8 @@ int fovpt_resize(fovpt_ctx* c, int w, int h, void** accum_out, void** frame_out)
     if (w <= 0 || h <= 0) return fail(c, "bad frame size");
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    cudaFree(c->fb_accum); cudaFree(c->fb_frame);
-    c->fb_accum = nullptr; c->fb_frame = nullptr;
+    cudaFree(c->fb_accum); cudaFree(c->fb_frame); cudaFree(c->fb_color); cudaFree(c->fb_normal); cudaFree(c->fb_albedo);
+    c->fb_accum = nullptr; c->fb_frame = nullptr; c->fb_color = c->fb_normal = c->fb_albedo = nullptr;
     const size_t n = (size_t)w * h;
     CU(dmalloc(&c->fb_accum, n)); CU(dmalloc(&c->fb_frame, n));
     CU(cudaMemset(c->fb_accum, 0, n * 16)); CU(cudaMemset(c->fb_frame, 0, n * 4));
@@ -639,6 +656,34 @@ int fovpt_resize(fovpt_ctx* c, int w, int h, void** accum_out, void** frame_out)
     c->last_frame_ptr = c->fb_frame; c->last_accum_ptr = c->fb_accum; c->last_npix = n;
     if (accum_out) *accum_out = c->fb_accum;
     if (frame_out) *frame_out = c->fb_frame;
+    return 0;
+}
+
+int fovpt_feature_buffers(fovpt_ctx* c, void** color_out, void** normal_out, void** albedo_out)
+{
+    if (!c) return 1;
+    if (c->fb_w <= 0 || c->fb_h <= 0) return fail(c, "call fovpt_resize first");
+    cudaSetDevice(c->device);
+    const size_t n = (size_t)c->fb_w * c->fb_h;
+    if (!c->fb_color) {
+        CU(dmalloc(&c->fb_color, n)); CU(dmalloc(&c->fb_normal, n)); CU(dmalloc(&c->fb_albedo, n));
+        CU(cudaMemset(c->fb_color, 0, n * 16)); CU(cudaMemset(c->fb_normal, 0, n * 16)); CU(cudaMemset(c->fb_albedo, 0, n * 16));
+    }
+    if (color_out) *color_out = c->fb_color;
+    if (normal_out) *normal_out = c->fb_normal;
+    if (albedo_out) *albedo_out = c->fb_albedo;
+    return 0;
+}
+
+int fovpt_download_features(fovpt_ctx* c, float* color_rgba, float* normal_rgba, float* albedo_rgba, size_t npix)
+{
+    if (!c) return 1;
+    if (!c->fb_color || npix > (size_t)c->fb_w * c->fb_h) return fail(c, "no feature buffers of that size (fovpt_feature_buffers)");
+    cudaSetDevice(c->device);
+    if (color_rgba) CU(cudaMemcpyAsync(color_rgba, c->fb_color, npix * 16, cudaMemcpyDeviceToHost, c->stream));
+    if (normal_rgba) CU(cudaMemcpyAsync(normal_rgba, c->fb_normal, npix * 16, cudaMemcpyDeviceToHost, c->stream));
+    if (albedo_rgba) CU(cudaMemcpyAsync(albedo_rgba, c->fb_albedo, npix * 16, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
     return 0;
 }
 

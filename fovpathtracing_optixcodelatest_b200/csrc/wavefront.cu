@@ -155,6 +155,7 @@ __global__ void k_raygen(FrameDev F, ChunkTable T, const uint8_t* __restrict__ n
             ps.direct[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
             ps.indirect[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
             ps.alpha[pid] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ps.feat_n) { ps.feat_n[pid] = make_float4(0.f, 0.f, 0.f, 1.f); ps.feat_a[pid] = make_float4(0.f, 0.f, 0.f, 0.f); }   // a miss adds zeros (:271-272)
             if (k == P.spp - 1) {                                                           // backplate of the LAST sample (:495)
                 const float4 bp = probe_eval(F.probe, probe_dir_to_uv(dir));
                 li_backplate[(size_t)layer * F.li_total + P.li_base + li] = bp;
@@ -380,6 +381,9 @@ __device__ __forceinline__ void shade_path(const FrameDev& F, const SceneDev& S,
     const bool secondary = (st & kFlagSecondary) != 0;
     const bool catcher = (mflags & kMaterialShadowCatcher) != 0;
     if (catcher && secondary) {                              // pass-through, --depth then ++depth (:646-651, :529)
+        // a pass-through at depth 1 drops prd.depth to 0 with prd.normal / prd.albedo still holding the first hit, which the
+        // raygen loop then adds once more (:509-512)
+        if (ps.feat_n && depth == 1u) ps.feat_n[pid].w += 1.f;
         out.o = make_float4(P.x, P.y, P.z, 0.f); out.d = rd4; out.thr = th4; out.rng = r2; out.meta = meta;
         out.push_next = true;
         return;
@@ -396,6 +400,10 @@ __device__ __forceinline__ void shade_path(const FrameDev& F, const SceneDev& S,
         const float u = h4.y, v = h4.z, w0 = 1.f - u - v;
         const int4 ti = __ldg(&S.tex_info[mt.x]);
         albedo = texture_bilinear(S.texels + ti.x, ti.y, ti.z, w0 * t0.x + u * t1.x + v * t2.x, w0 * t0.y + u * t1.y + v * t2.y);
+    }
+    if (ps.feat_n && !secondary) {                           // prd.normal / prd.albedo of the first hit (:653-665)
+        ps.feat_n[pid] = make_float4(N.x, N.y, N.z, 1.f);
+        ps.feat_a[pid] = make_float4(albedo.x, albedo.y, albedo.z, 0.f);
     }
     float3 T = f3(th4.x, th4.y, th4.z);
     float ray_eta = th4.w;
@@ -516,7 +524,8 @@ __global__ void __launch_bounds__(128, FOVPT_SHADE_BLOCKS) k_shade(FrameDev F, S
 // per (layer, launch index): sum its spp samples in order, apply the backplate/alpha composite (:536-560).  One launch for
 // all passes and layers; work item i of chunk c = (layer - s0) * rows * lw + (ly - row0) * lw + lx.
 __global__ void k_resolve_li(FrameDev F, ChunkTable T, const uint8_t* __restrict__ needed, PathState ps,
-                             const float4* __restrict__ li_backplate, float4* __restrict__ li_color)
+                             const float4* __restrict__ li_backplate, float4* __restrict__ li_color,
+                             float4* __restrict__ li_normal, float4* __restrict__ li_albedo)
 {
     const uint32_t total = T.total;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -542,6 +551,16 @@ __global__ void k_resolve_li(FrameDev F, ChunkTable T, const uint8_t* __restrict
         const float3 color = (f3(bp.x, bp.y, bp.z) * sppf) * (f3(1.f) - alpha) + result;
         const float3 acc = color * inv;
         li_color[at] = make_float4(acc.x, acc.y, acc.z, 1.0f);
+        if (li_normal) {                                     // :509-512, :541-542: sums in sample order, then / spp
+            float3 nsum = f3(0.f), asum = f3(0.f);
+            for (unsigned k = 0; k < P.spp; ++k) {
+                const float4 n4 = ps.feat_n[pid0 + k], a4 = ps.feat_a[pid0 + k];
+                for (int j = (int)n4.w; j > 0; --j) { nsum = nsum + f3(n4.x, n4.y, n4.z); asum = asum + f3(a4.x, a4.y, a4.z); }
+            }
+            nsum = nsum * inv; asum = asum * inv;
+            li_normal[at] = make_float4(nsum.x, nsum.y, nsum.z, 1.0f);
+            li_albedo[at] = make_float4(asum.x, asum.y, asum.z, 1.0f);
+        }
     }
 }
 
@@ -578,7 +597,8 @@ __device__ __forceinline__ float3 filtered_color(const FrameDev& F, const PassDe
 // buffer: the result is bit-identical to rendering them one by one; only the final state is tonemapped.
 template <bool FAST>
 __global__ void k_resolve_px(FrameDev F, const uint32_t* __restrict__ owner_map, const float4* __restrict__ li_color,
-                             const uint8_t* __restrict__ needed, float4* __restrict__ accum_mirror)
+                             const uint8_t* __restrict__ needed, float4* __restrict__ accum_mirror,
+                             const float4* __restrict__ li_normal, const float4* __restrict__ li_albedo)
 {
     const size_t npix = (size_t)F.w * F.h;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
@@ -603,6 +623,12 @@ __global__ void k_resolve_px(FrameDev F, const uint32_t* __restrict__ owner_map,
         F.accum[i] = out;
         if (accum_mirror) accum_mirror[i] = out;                 // multi-GPU: the owner rank's shared accumulation buffer (peer memory)
         F.frame[i] = tonemap_rgba8<FAST>(acc, F.exposure);
+        if (F.feat_color) F.feat_color[i] = out;                 // :612-614: what the last frame of the batch leaves behind
+        if (li_normal) {
+            const size_t at = (size_t)(F.nsub - 1) * F.li_total + P.li_base + (own & 0x0fffffffu);
+            if (F.feat_normal) F.feat_normal[i] = li_normal[at];
+            if (F.feat_albedo) F.feat_albedo[i] = li_albedo[at];
+        }
     }
 }
 
@@ -781,15 +807,15 @@ void launch_peer_wait(const LaunchCfg& L, const uint32_t* flags, int count, int 
     k_peer_wait<<<1, 64, 0, L.stream>>>(flags, count, skip, seq, err, timeout_clocks);
 }
 void launch_resolve_li(const LaunchCfg& L, const FrameDev& F, const ChunkTable& T, const uint8_t* needed, const PathState& ps,
-                       const float4* li_backplate, float4* li_color)
+                       const float4* li_backplate, float4* li_color, float4* li_normal, float4* li_albedo)
 {
-    k_resolve_li<<<L.grid_light, 256, 0, L.stream>>>(F, T, needed, ps, li_backplate, li_color);
+    k_resolve_li<<<L.grid_light, 256, 0, L.stream>>>(F, T, needed, ps, li_backplate, li_color, li_normal, li_albedo);
 }
 void launch_resolve_px(const LaunchCfg& L, const FrameDev& F, const uint32_t* owner_map, const float4* li_color, const uint8_t* needed,
-                       float4* accum_mirror, bool fast)
+                       float4* accum_mirror, const float4* li_normal, const float4* li_albedo, bool fast)
 {
-    if (fast) k_resolve_px<true><<<L.grid_light, 256, 0, L.stream>>>(F, owner_map, li_color, needed, accum_mirror);
-    else k_resolve_px<false><<<L.grid_light, 256, 0, L.stream>>>(F, owner_map, li_color, needed, accum_mirror);
+    if (fast) k_resolve_px<true><<<L.grid_light, 256, 0, L.stream>>>(F, owner_map, li_color, needed, accum_mirror, li_normal, li_albedo);
+    else k_resolve_px<false><<<L.grid_light, 256, 0, L.stream>>>(F, owner_map, li_color, needed, accum_mirror, li_normal, li_albedo);
 }
 void launch_probe_guides(const LaunchCfg& L, const ProbeBlob& p, uint16_t* gy, uint16_t* gx)
 {

@@ -33,6 +33,10 @@ struct PathState {
     float4* direct;             // directLight.xyz
     float4* indirect;           // indirectLight.xyz
     float4* alpha;              // alpha.xyz
+    // denoiser features (fovpt_config.features; null when off): what prd.normal / prd.albedo held after the FIRST trace
+    // of the path (deviceProgram.cu:509-512, :653-665); feat_n.w counts how many times the raygen loop adds them
+    float4* feat_n;             // normal.xyz, multiplicity
+    float4* feat_a;             // albedo.xyz
 };
 
 // The wavefront itself is DENSE: the state of the rays of one bounce lives in queue order, so every kernel reads and
@@ -80,6 +84,7 @@ struct FrameDev {
     ProbeGuide guide;           // null unless the probe's CDFs are the ones fovpt_probe_upload built guides for
     float4*   accum;
     uint32_t* frame;
+    float4   *feat_color, *feat_normal, *feat_albedo;      // LaunchParams.frame.{color,normal,albedo}_buffer when fovpt_config.features, else null
     int       npass;
     PassDev   pass[kMaxPasses];
     // a batch of nsub accumulated subframes traced as ONE wavefront (fovpt_render_frames): per-launch-index buffers hold

@@ -24,11 +24,12 @@ void launch_shade(const LaunchCfg&, const FrameDev&, const SceneDev&, const Path
 // peer-frame flags (api.cu fovpt_peer_frame_*): raise *flag to seq / wait until flags[0..count) (except `skip`) reached seq
 void launch_peer_signal(const LaunchCfg&, uint32_t* flag, uint32_t seq);
 void launch_peer_wait(const LaunchCfg&, const uint32_t* flags, int count, int skip, uint32_t seq, uint32_t* err, long long timeout_clocks);
+// li_normal / li_albedo: per-(layer, launch index) denoiser features, or null (fovpt_config.features off)
 void launch_resolve_li(const LaunchCfg&, const FrameDev&, const ChunkTable&, const uint8_t* needed, const PathState&,
-                       const float4* li_backplate, float4* li_color);
+                       const float4* li_backplate, float4* li_color, float4* li_normal, float4* li_albedo);
 // accum_mirror: second destination of the accumulation value (the owner rank's shared buffer of a multi-GPU job) or null
 void launch_resolve_px(const LaunchCfg&, const FrameDev&, const uint32_t* owner_map, const float4* li_color, const uint8_t* needed,
-                       float4* accum_mirror, bool fast);
+                       float4* accum_mirror, const float4* li_normal, const float4* li_albedo, bool fast);
 void launch_probe_guides(const LaunchCfg&, const ProbeBlob&, uint16_t* gy, uint16_t* gx);
 void launch_primary_hits(const LaunchCfg&, const FrameDev&, const SceneDev&, int32_t* tri, float* tuv, float* dir);
 void launch_trace_query(const LaunchCfg&, const SceneDev&, const float* rays, size_t n, int mode, int32_t* tri, float* tuv);

@@ -85,7 +85,16 @@ void SampleRenderer::resize(const int2& newSize)
     launchParams.frame.accum_buffer = (float4*)accum;
     launchParams.frame.frame_buffer = (uchar4*)frame;
     ownFrameBuffer = (uchar4*)frame;
-    launchParams.frame.color_buffer = launchParams.frame.normal_buffer = launchParams.frame.albedo_buffer = nullptr;   // dead on device
+    // the reference allocates its three denoiser buffers here (:245-260) and never writes them (deviceProgram.cu:612-614 are
+    // commented out); here they exist only when fovpt_config.features asks for those stores
+    launchParams.frame.color_buffer = launchParams.frame.normal_buffer = launchParams.frame.albedo_buffer = nullptr;
+    fovpt_config k;
+    check(fovpt_get_config(ctx, &k));
+    if (k.features) {
+        void *col = nullptr, *nrm = nullptr, *alb = nullptr;
+        check(fovpt_feature_buffers(ctx, &col, &nrm, &alb));
+        launchParams.frame.color_buffer = (float4*)col; launchParams.frame.normal_buffer = (float4*)nrm; launchParams.frame.albedo_buffer = (float4*)alb;
+    }
     launchParams.viewportSize = newSize;
 }
 

@@ -121,10 +121,11 @@ int fovpth_set_probe(SampleRenderer* r, int w, int h, const float* rgba, int bui
 void* fovpth_launch_params(SampleRenderer* r) { return &r->launchParams; }      // the public member, as main.cpp uses it
 int fovpth_render(SampleRenderer* r) { GUARD(r->render()); }
 int fovpth_render_subframes(SampleRenderer* r, int n) { GUARD(r->renderSubframes(n)); }
-int fovpth_render_to_output_buffer(SampleRenderer* r, uint32_t* host_out)
+// type: sutil::CUDAOutputBufferType (0 CUDA_DEVICE, 1 GL_INTEROP -- throws in this headless build, 2 ZERO_COPY, 3 CUDA_P2P)
+int fovpth_render_to_output_buffer(SampleRenderer* r, int type, uint32_t* host_out)
 {
     GUARD({
-        sutil::CUDAOutputBuffer<uint32_t> target(sutil::CUDAOutputBufferType::CUDA_DEVICE, r->launchParams.frame.size.x, r->launchParams.frame.size.y);
+        sutil::CUDAOutputBuffer<uint32_t> target((sutil::CUDAOutputBufferType)type, r->launchParams.frame.size.x, r->launchParams.frame.size.y);
         target.setStream(r->stream);
         r->render(target);
         std::memcpy(host_out, target.getHostPointer(), (size_t)target.width() * target.height() * 4);

@@ -21,7 +21,7 @@ class Config(C.Structure):
         ("accumulate", C.c_int32), ("foveated", C.c_int32), ("inner_radius", C.c_int32), ("outer_radius", C.c_int32),
         ("spp_periphery", C.c_int32), ("spp_mid", C.c_int32), ("spp_fovea", C.c_int32), ("spp_uniform", C.c_int32),
         ("seed_all_passes_with_subframe", C.c_int32), ("skip_wasted_trace", C.c_int32), ("fast_math", C.c_int32),
-        ("filter", C.c_int32),
+        ("filter", C.c_int32), ("features", C.c_int32),
     ]
 
 
@@ -47,6 +47,7 @@ EXPORTS = [
     "fovpt_peer_frame_create", "fovpt_peer_frame_open", "fovpt_peer_frame_signal", "fovpt_peer_frame_wait",
     "fovpt_peer_frame_release", "fovpt_peer_frame_close", "fovpt_set_kernel_timing",
     "fovpt_render_frames", "fovpt_peer_frame_accum", "fovpt_forget_frame", "fovpt_texture_check",
+    "fovpt_feature_buffers", "fovpt_download_features",
 ]
 
 _lib = None
@@ -80,6 +81,8 @@ def load_library():
     L.fovpt_render_frame.argtypes = [vp, vp]
     L.fovpt_render_frames.argtypes = [vp, vp, i32]
     L.fovpt_forget_frame.argtypes = [vp]
+    L.fovpt_feature_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.fovpt_download_features.argtypes = [vp, vp, vp, vp, C.c_size_t]
     L.fovpt_texture_check.argtypes = [vp, i32, vp, C.c_size_t, i32, vp, vp]
     L.fovpt_peer_frame_accum.argtypes = [vp, i32, C.POINTER(vp)]
     L.fovpt_sync.argtypes = [vp]
@@ -225,6 +228,17 @@ class Context:
         out = np.empty((h, w, 4), np.float32)
         self._chk(self.L.fovpt_download_accum(self.h, _p(out), w * h))
         return out
+
+    def feature_buffers(self):
+        """device pointers (color, normal, albedo) of the denoiser buffers at the size of the last resize"""
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._chk(self.L.fovpt_feature_buffers(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def download_features(self, w, h):
+        out = [np.empty((h, w, 4), np.float32) for _ in range(3)]
+        self._chk(self.L.fovpt_download_features(self.h, _p(out[0]), _p(out[1]), _p(out[2]), w * h))
+        return dict(color=out[0], normal=out[1], albedo=out[2])
 
     def trace(self, rays, mode):
         r = np.ascontiguousarray(rays, dtype=np.float32).reshape(-1, 8)

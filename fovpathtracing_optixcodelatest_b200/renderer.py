@@ -71,6 +71,15 @@ class SampleRenderer:
         lp.frame.size_x, lp.frame.size_y = w, h
         lp.frame.accum_buffer, lp.frame.frame_buffer = accum, frame
         lp.viewport_x, lp.viewport_y = w, h
+        self._feature_buffers()
+
+    # the denoiser buffers resize() allocates in the reference (SimplePathtracer.cpp:245-260); here only when they are written
+    def _feature_buffers(self):
+        lp = self.launchParams
+        if self.config.features and lp.frame.size_x:
+            lp.frame.color_buffer, lp.frame.normal_buffer, lp.frame.albedo_buffer = self.ctx.feature_buffers()
+        else:
+            lp.frame.color_buffer = lp.frame.normal_buffer = lp.frame.albedo_buffer = 0
 
     # -- SampleRenderer::setCamera, SimplePathtracer.cpp:282-289 (aspect from frame.size)
     def setCamera(self, camera: CameraSpec):
@@ -91,6 +100,7 @@ class SampleRenderer:
     def setConfig(self, config: native.Config):
         self.config = config
         self.ctx.set_config(config)
+        self._feature_buffers()
 
     # -- SampleRenderer::render, SimplePathtracer.cpp:77-214 (three passes, one submission, then sync)
     def render(self):
@@ -123,6 +133,11 @@ class SampleRenderer:
     def downloadAccum(self):
         lp = self.launchParams
         return self.ctx.download_accum(lp.frame.size_x, lp.frame.size_y)
+
+    def downloadFeatures(self):
+        """dict(color, normal, albedo) of (h, w, 4) float32: LaunchParams.frame.{color,normal,albedo}_buffer (config.features = 1)"""
+        lp = self.launchParams
+        return self.ctx.download_features(lp.frame.size_x, lp.frame.size_y)
 
     def stats(self):
         return self.ctx.stats()

@@ -47,6 +47,11 @@ typedef struct fovpt_config {
                                * 1 = bilinear interpolation between neighbouring launch indices of the    *
                                * same ring -- fills the reference's empty Filter.h (Filter.h:3-7); no      *
                                * reference semantics exist for it (SURVEY 8a R-FILTER, 8f-3)               */
+    int32_t features;         /* denoiser feature buffers.  0 = sv5 as shipped (the three stores are commented     *
+                               * out, deviceProgram.cu:612-614); 1 = execute them: frame.normal_buffer /            *
+                               * albedo_buffer receive the mean first-hit normal / albedo of the pixel's launch      *
+                               * index (:509-512, :541-542, :653-665), frame.color_buffer the accumulated colour     *
+                               * (LaunchParams.h:55-57); null pointers are skipped                                   */
 } fovpt_config;
 
 typedef struct fovpt_stats {
@@ -92,6 +97,13 @@ int fovpt_probe_upload(fovpt_ctx*, int w, int h, const float* rgba, const float*
  *    (accumulation is dropped, as in the reference); returns the device pointers to put in
  *    LaunchParams.frame.{accum_buffer,frame_buffer}. */
 int fovpt_resize(fovpt_ctx*, int w, int h, void** accum_out, void** frame_out);
+
+/* -- the denoiser buffers SampleRenderer::resize also allocates (SimplePathtracer.cpp:245-260): color / normal / albedo,
+ *    float4 per pixel at the size of the last fovpt_resize (which frees them); returns the device pointers to put in
+ *    LaunchParams.frame.{color_buffer,normal_buffer,albedo_buffer}.  Written only with fovpt_config.features = 1. */
+int fovpt_feature_buffers(fovpt_ctx*, void** color_out, void** normal_out, void** albedo_out);
+/* blocking D2H of the three feature buffers (any destination may be NULL) */
+int fovpt_download_features(fovpt_ctx*, float* color_rgba, float* normal_rgba, float* albedo_rgba, size_t npix);
 
 /* -- one optixLaunch (SimplePathtracer.cpp:148-157,178-187,200-209): uploads the 248-byte params and
  *    runs raygen for launch indices [0,lw)x[0,lh).  Asynchronous on the context's stream. */

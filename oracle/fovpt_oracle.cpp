@@ -414,6 +414,10 @@ struct orc_ctx {
     std::string err;
     std::vector<float> prev_accum;          // snapshot of the accumulation buffer at frame start (extension mode)
     bool prev_accum_active = false;
+    // orc_opts.filter: what the passes of one frame leave behind for the reconstruction pass of orc_render
+    std::vector<f4> li_color;               // per launch index of the pass in flight: colour before accumulation
+    std::vector<std::atomic<uint32_t>> owner;   // per pixel: (pass << 28 | launch index) of the surviving write, kNoOwner = none
+    int pass_in_flight = -1;
 };
 
 namespace {
@@ -423,6 +427,7 @@ struct PRD {                                                       // RadiancePR
     float bsdfPdf; f3 pathThroughput; float rayEta;
     int depth; bool done, secondary;
     Random rand;
+    f3 normal, albedo;                                               // denoiser features of the last shaded hit (:69-70)
 };
 
 struct Frame {                                                     // one launch in flight
@@ -475,6 +480,7 @@ void closest_hit(const Frame& F, PRD& prd, const obvh::Hit& hit, f3 ray_org, f3 
     if ((mat.flags & kShadowCatcher) != 0 && prd.secondary) {       // :646-651
         prd.origin = P; prd.direction = ray_dir; --prd.depth; return;
     }
+    prd.normal = N;                                                  // :653
     f3 albedo = mat.color;
     if (mesh.texture_id >= 0 && mesh.texture_id < (int)F.c->textures.size() && !mesh.tc.empty()) {   // :655-665
         const float u = hit.u, v = hit.v;
@@ -486,6 +492,7 @@ void closest_hit(const Frame& F, PRD& prd, const obvh::Hit& hit, f3 ray_org, f3 
         ocommon::tex_bilinear(F.c->textures[(size_t)mesh.texture_id], tc.x, tc.y, px);
         albedo = mk3(px[0], px[1], px[2]);
     }
+    prd.albedo = albedo;                                             // :654, :665
     float outEta;
     if (prd.rayEta == 1.0f) outEta = mat.ior(); else outEta = 1.0f;  // :673-683 (absorption is tracked but never applied)
 
@@ -530,6 +537,7 @@ bool raygen(const Frame& F, unsigned lx, unsigned ly, unsigned lw)
     fx_vec3 U = {p.camera.U.x, p.camera.U.y, p.camera.U.z}, V = {p.camera.V.x, p.camera.V.y, p.camera.V.z},
             Wv = {p.camera.W.x, p.camera.W.y, p.camera.W.z};
     f3 result = mk3(0.f), alpha = mk3(0.f), backplate = mk3(0.f);
+    f3 normal = mk3(0.f), albedo = mk3(0.f);                          // :443-444
     int i = spp;
     bool first = true;
     do {
@@ -539,6 +547,7 @@ bool raygen(const Frame& F, unsigned lx, unsigned ly, unsigned lw)
         prd.rand = Random(seed);                                       // :464, BEFORE the jitter advances seed
         prd.rayEta = 1.0f; prd.pathThroughput = mk3(1.f); prd.bsdfPdf = 1.0f;
         prd.done = false; prd.secondary = false; prd.depth = 0;
+        prd.normal = mk3(0.f); prd.albedo = mk3(0.f);                  // :471-472
         float jx, jy;                                                  // :479 (argument evaluation order)
         if (o.jitter_yx) { jy = fx_rnd(&seed); jx = fx_rnd(&seed); } else { jx = fx_rnd(&seed); jy = fx_rnd(&seed); }
         fx_vec3 d = fx_camera_dir(px, py, jx, jy, w, h, U, V, Wv);     // :483-491
@@ -557,7 +566,10 @@ bool raygen(const Frame& F, unsigned lx, unsigned ly, unsigned lw)
                 if (o.primary_dir) { float* q = o.primary_dir + 3 * li; q[0] = d.x; q[1] = d.y; q[2] = d.z; }
             }
             if (ok) closest_hit(F, prd, hit, ray_origin, ray_direction);
-            else prd.done = true;                                      // __miss__radiance :253-282
+            else { prd.done = true; prd.normal = mk3(0.f); prd.albedo = mk3(0.f); }      // __miss__radiance :253-282
+            // :509-512.  A secondary ray that passes through a shadow catcher decrements depth (:650) and leaves prd.normal
+            // untouched, so a pass-through at depth 1 adds the first hit's features once more: kept as written.
+            if (prd.depth == 0) { normal += prd.normal; albedo += prd.albedo; }
             if (prd.done || prd.depth >= o.max_depth) break;           // :515
             if (prd.depth == 0) direct += prd.radiance; else indirect += prd.radiance;
             ++prd.depth;
@@ -566,7 +578,13 @@ bool raygen(const Frame& F, unsigned lx, unsigned ly, unsigned lw)
         result += direct + indirect;                                   // :536-537
         alpha += prd.alpha;
     } while (--i);
-    alpha /= (float)spp;                                               // :543
+    normal /= (float)spp;                                              // :541-543
+    albedo /= (float)spp;
+    alpha /= (float)spp;
+    if (!F.c->li_color.empty()) {                                      // orc_opts.filter: keep the launch index's colour, unaccumulated
+        const f3 c0 = ((backplate * (float)spp) * (1.0f - alpha) + result) / (float)spp;
+        F.c->li_color[li] = {c0.x, c0.y, c0.z, 1.0f};
+    }
 
     for (int a = 0; a < p.frame.fillSize; ++a) {                       // :546-616
         for (int b = 0; b < p.frame.fillSize; ++b) {
@@ -585,6 +603,17 @@ bool raygen(const Frame& F, unsigned lx, unsigned ly, unsigned lw)
             }
             p.frame.accum_buffer[image_index] = {accum_color.x, accum_color.y, accum_color.z, 1.0f};
             p.frame.frame_buffer[image_index] = tonemap(accum_color, o.exposure);
+            if (o.features) {                                          // :612-614 (commented out in sv5)
+                if (p.frame.normal_buffer) p.frame.normal_buffer[image_index] = {normal.x, normal.y, normal.z, 1.0f};
+                if (p.frame.color_buffer) p.frame.color_buffer[image_index] = {accum_color.x, accum_color.y, accum_color.z, 1.0f};
+                if (p.frame.albedo_buffer) p.frame.albedo_buffer[image_index] = {albedo.x, albedo.y, albedo.z, 1.0f};
+            }
+            if (!F.c->owner.empty()) {                                 // surviving write = last pass, row-major last launch index
+                const uint32_t me = ((uint32_t)F.c->pass_in_flight << 28) | (uint32_t)li;
+                std::atomic<uint32_t>& w8 = F.c->owner[image_index];
+                uint32_t cur = w8.load(std::memory_order_relaxed);
+                while ((cur == 0xffffffffu || cur < me) && !w8.compare_exchange_weak(cur, me, std::memory_order_relaxed)) {}
+            }
         }
     }
     return true;
@@ -736,7 +765,18 @@ int orc_render(orc_ctx* c, void* lp248, const orc_fov_cfg* cfg, const orc_opts* 
     }
     orc_opts local = *o;
     local.primary_tri = nullptr; local.primary_tuv = nullptr; local.primary_dir = nullptr;
+    const bool filter = o->filter != 0;
+    const int w = lp->frame.size_x, h = lp->frame.size_y;
+    std::vector<std::vector<f4>> li_colors;
+    std::vector<f4> before;                                            // the accumulation buffer as the previous frame left it
+    if (filter) {
+        before.assign(lp->frame.accum_buffer, lp->frame.accum_buffer + (size_t)w * h);
+        c->owner = std::vector<std::atomic<uint32_t>>((size_t)w * h);
+        for (auto& a : c->owner) a.store(0xffffffffu, std::memory_order_relaxed);
+    }
+    std::vector<unsigned> pass_sub;
     for (auto& p : passes) {
+        if (filter) { c->pass_in_flight = (int)li_colors.size(); c->li_color.assign((size_t)p.lw * p.lh, f4{0.f, 0.f, 0.f, 0.f}); }
         lp->frame.factor_x = lp->frame.factor_y = p.factor; lp->frame.factor_z = 1;
         lp->frame.fillSize = p.fill;
         lp->frame.r_inner = p.r_inner; lp->frame.r_outer = p.r_outer;
@@ -745,7 +785,54 @@ int orc_render(orc_ctx* c, void* lp248, const orc_fov_cfg* cfg, const orc_opts* 
         lp->frame.redraw = o->seed_all_passes_with_subframe ? 0u : p.redraw;
         if (p.zero_subframe && !o->seed_all_passes_with_subframe) lp->frame.subframe_index = 0;
         else lp->frame.subframe_index = saved;
+        pass_sub.push_back(lp->frame.subframe_index);
         if (orc_launch(c, lp, p.lw, p.lh, &local)) return -1;
+        if (filter) li_colors.push_back(std::move(c->li_color));
+    }
+    if (filter) {
+        // Reconstruction pass ("reconstruction filter"): every pixel takes the colour of the launch index
+        // whose write survived; in a sub-sampled ring (fillSize > 1) it is blended with the three neighbouring launch indices of
+        // the SAME pass on the side of the block the pixel lies on, weights = distance from the block centre in block units.
+        // A neighbour takes part only if it is inside the launch and itself owns at least one pixel of the frame.
+        c->li_color.clear(); c->pass_in_flight = -1;
+        std::vector<std::vector<uint8_t>> owns(passes.size());
+        for (size_t p = 0; p < passes.size(); ++p) owns[p].assign((size_t)passes[p].lw * passes[p].lh, 0);
+        for (size_t i = 0; i < (size_t)w * h; ++i) { const uint32_t ow = c->owner[i].load(); if (ow != 0xffffffffu) owns[ow >> 28][ow & 0x0fffffffu] = 1; }
+        for (int Y = 0; Y < h; ++Y) for (int X = 0; X < w; ++X) {
+            const size_t i = (size_t)Y * w + X;
+            const uint32_t ow = c->owner[i].load();
+            if (ow == 0xffffffffu) { lp->frame.accum_buffer[i] = before[i]; continue; }      // nobody wrote it: untouched
+            const size_t pi = ow >> 28; const uint32_t li = ow & 0x0fffffffu;
+            const auto& P = passes[pi];
+            const std::vector<f4>& col = li_colors[pi];
+            const f3 own = mk3(col[li].x, col[li].y, col[li].z);
+            f3 cur = own;
+            if (P.fill > 1) {
+                const int lx = (int)(li % P.lw), ly = (int)(li / P.lw);
+                const float half = 0.5f * (float)(P.fill - 1);
+                const float dx = ((float)X - ((float)(lx * (int)P.factor + (int)P.off_x) + half)) / (float)P.factor;
+                const float dy = ((float)Y - ((float)(ly * (int)P.factor + (int)P.off_y) + half)) / (float)P.factor;
+                const int sx = dx < 0.f ? -1 : 1, sy = dy < 0.f ? -1 : 1;
+                const float wx = fminf(fabsf(dx), 1.f), wy = fminf(fabsf(dy), 1.f);
+                auto fetch = [&](int ax, int ay) {
+                    if (ax < 0 || ay < 0 || ax >= (int)P.lw || ay >= (int)P.lh) return own;
+                    const size_t j = (size_t)ay * P.lw + (size_t)ax;
+                    if (!owns[pi][j]) return own;
+                    return mk3(col[j].x, col[j].y, col[j].z);
+                };
+                const f3 c10 = fetch(lx + sx, ly), c01 = fetch(lx, ly + sy), c11 = fetch(lx + sx, ly + sy);
+                cur = lerp3(lerp3(own, c10, wx), lerp3(c01, c11, wx), wy);
+            }
+            const bool redraw = o->seed_all_passes_with_subframe ? false : P.redraw != 0;
+            if (o->accumulate && pass_sub[pi] > 0 && !redraw) {
+                cur = mk3(clampf(cur.x, 0.f, 10.f), clampf(cur.y, 0.f, 10.f), clampf(cur.z, 0.f, 10.f));
+                cur = lerp3(mk3(before[i].x, before[i].y, before[i].z), cur, 1.0f / (float)(pass_sub[pi] + 1));
+            }
+            lp->frame.accum_buffer[i] = {cur.x, cur.y, cur.z, 1.0f};
+            lp->frame.frame_buffer[i] = tonemap(cur, o->exposure);
+            if (o->features && lp->frame.color_buffer) lp->frame.color_buffer[i] = {cur.x, cur.y, cur.z, 1.0f};
+        }
+        c->owner.clear();
     }
     lp->frame.subframe_index = saved + 1;
     c->prev_accum_active = false;

@@ -21,12 +21,13 @@ class Opts(C.Structure):
         ("threads", C.c_int32), ("accumulate", C.c_int32), ("exposure", C.c_float),
         ("seed_all_passes_with_subframe", C.c_int32),
         ("primary_tri", C.c_void_p), ("primary_tuv", C.c_void_p), ("primary_dir", C.c_void_p),
+        ("features", C.c_int32), ("filter", C.c_int32),
     ]
 
     @classmethod
     def sv5(cls, **kw):
         o = cls(max_depth=4, tmin=0.01, tmax=1e16, jitter_yx=0, threads=0, accumulate=0, exposure=16.0,
-                seed_all_passes_with_subframe=0)
+                seed_all_passes_with_subframe=0, features=0, filter=0)
         for k, v in kw.items():
             setattr(o, k, v)
         return o

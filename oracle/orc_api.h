@@ -36,6 +36,13 @@ typedef struct orc_opts {
     int32_t* primary_tri;   /* global triangle id of sample 0's primary hit, -1 miss, -2 ring-culled */
     float*   primary_tuv;   /* 3 floats: t,u,v                                                       */
     float*   primary_dir;   /* 3 floats: the sample-0 camera direction                               */
+    /* port only (the reference ships with both disabled / empty; oracle/_ref ignores these fields) */
+    int32_t  features;      /* 1: write frame.normal_buffer / color_buffer / albedo_buffer as the commented-out  *
+                             * statements deviceProgram.cu:612-614 would (first-hit normal and albedo, :509-512,  *
+                             * :541-542, :653-665); 0: sv5 as shipped                                             */
+    int32_t  filter;        /* orc_render only.  1: bilinear reconstruction of the sub-sampled rings instead of   *
+                             * the fillSize^2 box splat (the reference's Filter.h is an empty class; definition    *
+                             * in DESIGN.md section 3); 0: box splat                                               */
 } orc_opts;
 
 typedef struct orc_fov_cfg {     /* three-pass parameters, SimplePathtracer.cpp:20-21,137-209 */

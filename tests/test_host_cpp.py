@@ -49,7 +49,7 @@ def H():
     L.fovpth_set_probe.argtypes = [vp, C.c_int, C.c_int, vp, C.c_int]
     L.fovpth_launch_params.argtypes = [vp]
     L.fovpth_render.argtypes = [vp]
-    L.fovpth_render_to_output_buffer.argtypes = [vp, vp]
+    L.fovpth_render_to_output_buffer.argtypes = [vp, C.c_int, vp]
     L.fovpth_download_pixels.argtypes = [vp, vp]
     L.fovpth_download_accum.argtypes = [vp, vp]
     return L
@@ -238,10 +238,57 @@ def test_cpp_samplerenderer_matches_oracle_and_python_binding(H, port):
     pr.render()
     assert (pr.downloadPixels() == px).all() and (bits(pr.downloadAccum()) == bits(acc)).all()
     pr.close()
-    # (3) render(CUDAOutputBuffer&): same frame into an external display buffer
-    lp.frame.subframe_index = 0
-    out = np.zeros((h, w), np.uint32)
-    assert H.fovpth_render_to_output_buffer(r, p(out)) == 0, H.fovpth_last_error()
+    # (3) render(CUDAOutputBuffer&): same frame into an external display buffer, every flavour of sutil/CUDAOutputBuffer.h:43-49
     written = acc[..., 3] == 1.0          # the few pixels no pass writes (ring-boundary holes) keep the target's old content, as in the reference
-    assert (out[written] == px[written]).all() and written.mean() > 0.999
+    for kind in (0, 2, 3):                # CUDA_DEVICE, ZERO_COPY (kernels store into mapped host memory), CUDA_P2P
+        lp.frame.subframe_index = 0
+        out = np.zeros((h, w), np.uint32)
+        assert H.fovpth_render_to_output_buffer(r, kind, p(out)) == 0, H.fovpth_last_error()
+        assert (out[written] == px[written]).all() and written.mean() > 0.999, kind
+    assert H.fovpth_render_to_output_buffer(r, 1, p(out)) != 0 and b"GL interop" in H.fovpth_last_error()   # no GL context here
+    # after a borrowed target the renderer falls back to its own frame buffer
+    lp.frame.subframe_index = 0
+    assert H.fovpth_render(r) == 0
+    px2 = np.zeros((h, w), np.uint32); H.fovpth_download_pixels(r, p(px2))
+    assert (px2 == px).all()
     H.fovpth_renderer_free(r); H.fovpth_model_free(m)
+
+
+@pytest.mark.gpu
+def test_fovpt_demo_renders_writes_and_rereads_a_ppm(H, tmp_path):
+    """host/main.cpp (the headless stand-in for the reference's main.cpp:297-481: loadOBJ -> SampleRenderer -> resize ->
+    setCamera -> setProbe -> per frame gaze + render() -> downloadPixels -> image file) run as a program: the PPM it writes,
+    re-read through the texture decoder, is the frame the python binding renders with the same settings"""
+    import subprocess
+    from fovpathtracing_optixcodelatest_b200 import native
+    from fovpathtracing_optixcodelatest_b200.renderer import ProbeData, SampleRenderer
+    demo = os.path.join(ROOT, "fovpathtracing_optixcodelatest_b200", "host", "fovpt_demo")
+    assert os.path.exists(demo), "fovpt_demo missing: run __graft_entry__.build()"
+    w, h, frames, gx, gy = 320, 180, 3, 200, 70
+    out = tmp_path / "demo.ppm"
+    run = subprocess.run([demo, os.path.join(ROOT, "assets", "cornell.obj"), str(w), str(h), str(frames), str(gx), str(gy), str(out)],
+                         capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stderr
+    assert "Msamples/s" in run.stdout
+    ww, hh = C.c_int(), C.c_int(); px = np.zeros((h, w), np.uint32)
+    assert H.fovpth_decode_image(str(out).encode(), C.byref(ww), C.byref(hh), p(px), px.size) == 0, H.fovpth_last_error()
+    assert (ww.value, hh.value) == (w, h)
+    # the same frame through the python binding (main.cpp's camera: bounding box centre, 1.4 extents back along +z)
+    sc = scenes.cornell_box()
+    v = np.concatenate([m.vtx for m in sc.meshes]); lo, hi = v.min(0), v.max(0)
+    centre = (0.5 * (lo + hi)).astype(np.float32); extent = np.float32((hi - lo).max())
+    cam = scenes.CameraSpec(eye=(centre[0], centre[1], np.float32(centre[2] + np.float32(1.4) * extent)), lookat=tuple(centre), up=(0.0, 1.0, 0.0), fovy=45.0)
+    cfg = native.default_config()
+    cfg.tmin = np.float32(1e-4) * extent; cfg.accumulate = 1; cfg.seed_all_passes_with_subframe = 1; cfg.exposure = 1.0
+    r = SampleRenderer(sc, 0, cfg); r.resize((w, h)); r.setCamera(cam)
+    r.setProbe(ProbeData(scenes.constant_probe(64, 32, 2.5)).BuildCDF())
+    for _ in range(frames):
+        r.launchParams.frame.c_x, r.launchParams.frame.c_y = gx, gy
+        r.render()
+    want = r.downloadPixels()[::-1] | np.uint32(0xff000000)                # the file stores the top row first, without alpha
+    acc = r.downloadAccum()[::-1]
+    r.close()
+    written = acc[..., 3] == 1.0
+    same = (px[written] == want[written]).mean()
+    assert same > 0.999, same
+    assert len(np.unique(px)) > 50                                          # an image, not a constant

@@ -186,3 +186,36 @@ def test_ray_triangle_test_is_watertight(P, mesh):
     occ, _ = P2.trace(rays, 1)
     P2.close()
     assert (occ == 1).all(), f"{(occ == 0).sum()} shadow rays leaked"
+
+
+def test_oracle_filter_and_features_properties(port):
+    """the oracle's reconstruction filter and denoiser features (orc_opts.filter / features; port only -- the reference ships an
+    empty Filter.h and commented-out feature stores): filter 0 through the same code path is the box splat bit for bit, filter 1
+    leaves the fovea alone and keeps a constant image constant; normals are unit length, albedo is the material colour"""
+    from fovpathtracing_optixcodelatest_b200 import scenes
+    w, h, ri, ro = 160, 90, 12, 40
+    sc, cam = scenes.cornell_box(), scenes.CORNELL_CAMERA
+    out = {}
+    for f in (0, 1):
+        o = port.Oracle("port"); o.add_scene(sc); o.commit(); o.set_probe(scenes.sky_probe(32, 16, 1))
+        U, V, W = o.camera_uvw(cam.eye, cam.lookat, cam.up, cam.fovy, w / h)
+        lp, accum, frame = o.make_params(w, h, cam.eye, U, V, W)
+        nb, ab = np.zeros((h, w, 4), np.float32), np.zeros((h, w, 4), np.float32)
+        lp.frame.normal_buffer, lp.frame.albedo_buffer = nb.ctypes.data, ab.ctypes.data
+        o.render(lp, port.FovCfg.sv5(inner_radius=ri, outer_radius=ro), port.Opts.sv5(filter=f, features=1, threads=1))
+        out[f] = (accum.copy(), nb, ab); o.close()
+    o = port.Oracle("port"); o.add_scene(sc); o.commit(); o.set_probe(scenes.sky_probe(32, 16, 1))
+    lp, accum, frame = o.make_params(w, h, cam.eye, U, V, W)
+    o.render(lp, port.FovCfg.sv5(inner_radius=ri, outer_radius=ro), port.Opts.sv5(threads=1)); o.close()
+    assert (accum.view(np.uint32) == out[0][0].view(np.uint32)).all()
+    y, x = np.mgrid[0:h, 0:w]; rr = np.hypot(x - w // 2, y - h // 2)
+    assert (out[0][0][rr < ri - 2] == out[1][0][rr < ri - 2]).all()
+    assert (out[0][0][rr > ro + 8] != out[1][0][rr > ro + 8]).any()
+    nb, ab = out[0][1], out[0][2]
+    hit = np.linalg.norm(nb[..., :3], axis=2) > 0
+    fov = hit & (rr < ri - 2)                                      # fovea: 32 samples of the same wall -> mean of equal unit vectors
+    ln = np.linalg.norm(nb[..., :3], axis=2)
+    assert fov.any() and (ln[hit] <= 1.0 + 1e-5).all() and (ln[fov] > 0.5).all()
+    colours = {tuple(np.float32(m.material.color.tolist())) for m in sc.meshes}
+    centre = ab[h // 2, w // 2, :3]
+    assert min(np.abs(np.array(c) - centre).max() for c in colours) < 1e-6

@@ -349,6 +349,7 @@ int run_frame(fovpt_ctx* c, const LaunchParamsBlob& lp, const std::vector<PassHo
             mark(c, K_EXTEND);
             launch_trace(c->L, c->scene, ps, c->q, slot_prev, c->cfg.tmin, c->cfg.tmax, c->d_stats); c->launches++; c->trace_launches++;
             if (it == iters) break;                      // the last launch only drains the final shadow rays
+            if (feat && it == 0) { launch_features(c->L, c->scene, ps, c->q, c->cfg.fast_math != 0); c->launches++; }
             mark(c, K_SHADE);
             launch_shade(c->L, F, c->scene, ps, c->q, slot_new, c->cfg.fast_math != 0); c->launches++;
             std::swap(c->q.cur, c->q.next);                // the device-side counters are swapped by k_shade's last CTA

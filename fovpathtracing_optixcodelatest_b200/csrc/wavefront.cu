@@ -401,10 +401,6 @@ __device__ __forceinline__ void shade_path(const FrameDev& F, const SceneDev& S,
         const int4 ti = __ldg(&S.tex_info[mt.x]);
         albedo = texture_bilinear(S.texels + ti.x, ti.y, ti.z, w0 * t0.x + u * t1.x + v * t2.x, w0 * t0.y + u * t1.y + v * t2.y);
     }
-    if (ps.feat_n && !secondary) {                           // prd.normal / prd.albedo of the first hit (:653-665)
-        ps.feat_n[pid] = make_float4(N.x, N.y, N.z, 1.f);
-        ps.feat_a[pid] = make_float4(albedo.x, albedo.y, albedo.z, 0.f);
-    }
     float3 T = f3(th4.x, th4.y, th4.z);
     float ray_eta = th4.w;
     float out_eta = 1.0f;                                    // :673-683
@@ -466,6 +462,41 @@ __device__ __forceinline__ void shade_path(const FrameDev& F, const SceneDev& S,
         out.thr = make_float4(T.x, T.y, T.z, ray_eta);
         out.rng = make_uint2(rng.s1, rng.s2);
         out.push_next = true;
+    }
+}
+
+// Denoiser features of the primary hits (fovpt_config.features): what __closesthit__radiance leaves in prd.normal /
+// prd.albedo after the FIRST trace of a path (deviceProgram.cu:632-634, :653-665).  Runs between the first k_trace and the
+// first k_shade, one thread per primary ray; a kernel of its own so that k_shade carries no extra registers for a
+// feature that is off by default.  Misses keep the zeros k_raygen wrote (:271-272).
+template <bool FAST>
+__global__ void k_features(SceneDev S, PathState ps, Queues q)
+{
+    const uint32_t n = q.counts[0];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 h4 = q.hit[i];
+        const uint32_t slot = (uint32_t)__float_as_int(h4.w);
+        if (slot == kNoHit) continue;
+        const uint32_t pid = q.cur.meta[i].x;
+        const float4 rd4 = q.cur.d[i];
+        const float4* tp = S.bvh.tris + 3 * (size_t)slot;
+        const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
+        const float3 v0 = f3(ta.x, ta.y, ta.z);
+        const float3 n0 = unit3<FAST>(cross3(f3(tb.x, tb.y, tb.z) - v0, f3(tc.x, tc.y, tc.z) - v0));
+        const float3 N = n0 * copysignf(1.0f, dot3(f3(-rd4.x, -rd4.y, -rd4.z), n0));
+        const uint32_t gid = (uint32_t)__float_as_int(ta.w), mesh = (uint32_t)__float_as_int(tb.w);
+        const float* M = reinterpret_cast<const float*>(S.materials + mesh);
+        float3 albedo = f3(__ldg(M + 3), __ldg(M + 4), __ldg(M + 5));                 // color @12,16,20
+        const int2 mt = __ldg(&S.mesh_tex[mesh]);
+        if (mt.x >= 0 && mt.y) {
+            const uint32_t* vi = S.tri_vidx + 3 * (size_t)gid;
+            const float2 t0 = __ldg(&S.texcoords[vi[0]]), t1 = __ldg(&S.texcoords[vi[1]]), t2 = __ldg(&S.texcoords[vi[2]]);
+            const float u = h4.y, v = h4.z, w0 = 1.f - u - v;
+            const int4 ti = __ldg(&S.tex_info[mt.x]);
+            albedo = texture_bilinear(S.texels + ti.x, ti.y, ti.z, w0 * t0.x + u * t1.x + v * t2.x, w0 * t0.y + u * t1.y + v * t2.y);
+        }
+        ps.feat_n[pid] = make_float4(N.x, N.y, N.z, 1.f);
+        ps.feat_a[pid] = make_float4(albedo.x, albedo.y, albedo.z, 0.f);
     }
 }
 
@@ -800,6 +831,11 @@ void launch_shade(const LaunchCfg& L, const FrameDev& F, const SceneDev& S, cons
 {
     if (fast) k_shade<true><<<L.grid_shade, 128, 0, L.stream>>>(F, S, ps, q, shadow_slot);
     else k_shade<false><<<L.grid_shade, 128, 0, L.stream>>>(F, S, ps, q, shadow_slot);
+}
+void launch_features(const LaunchCfg& L, const SceneDev& S, const PathState& ps, const Queues& q, bool fast)
+{
+    if (fast) k_features<true><<<L.grid_light, 256, 0, L.stream>>>(S, ps, q);
+    else k_features<false><<<L.grid_light, 256, 0, L.stream>>>(S, ps, q);
 }
 void launch_peer_signal(const LaunchCfg& L, uint32_t* flag, uint32_t seq) { k_peer_signal<<<1, 32, 0, L.stream>>>(flag, seq); }
 void launch_peer_wait(const LaunchCfg& L, const uint32_t* flags, int count, int skip, uint32_t seq, uint32_t* err, long long timeout_clocks)

@@ -21,6 +21,8 @@ void launch_raygen(const LaunchCfg&, const FrameDev&, const ChunkTable&, const u
 // shadow_slot: index into Queues::counts (2 or 5, alternating per iteration) of the shadow-ray counter in use
 void launch_trace(const LaunchCfg&, const SceneDev&, const PathState&, const Queues&, int shadow_slot, float tmin, float tmax, DevStats*);
 void launch_shade(const LaunchCfg&, const FrameDev&, const SceneDev&, const PathState&, const Queues&, int shadow_slot, bool fast);
+// primary-hit normal / albedo into PathState::feat_n / feat_a; between the first launch_trace and the first launch_shade
+void launch_features(const LaunchCfg&, const SceneDev&, const PathState&, const Queues&, bool fast);
 // peer-frame flags (api.cu fovpt_peer_frame_*): raise *flag to seq / wait until flags[0..count) (except `skip`) reached seq
 void launch_peer_signal(const LaunchCfg&, uint32_t* flag, uint32_t seq);
 void launch_peer_wait(const LaunchCfg&, const uint32_t* flags, int count, int skip, uint32_t seq, uint32_t* err, long long timeout_clocks);

@@ -6,6 +6,7 @@
 #include <string>
 
 #include "ImageDecode.h"
+#include "MultiGpu.h"
 #include "SimplePathtracer.h"
 
 namespace { thread_local std::string g_err; }
@@ -77,6 +78,21 @@ int fovpth_decode_image(const char* path, int* w, int* h, uint32_t* out, size_t 
     if (!fovpt_image::decode_file(path, *w, *h, px, &why)) { g_err = why; return -1; }
     if (out && capacity >= px.size()) std::memcpy(out, px.data(), px.size() * 4);
     return 0;
+}
+
+// ---- multi-GPU tile partition (MultiGpu.h); owner: tiles_y*tiles_x bytes, loads: n_ranks doubles; returns tiles_x | tiles_y << 16
+int fovpth_partition(int w, int h, unsigned gx, unsigned gy, const fovpt_config* cfg, int n_ranks, int tile, int interleave, uint8_t* owner, double* loads)
+{
+    try {
+        const fovpt_multigpu::TilePartition p = interleave ? fovpt_multigpu::interleaved(w, h, n_ranks, tile)
+                                                           : fovpt_multigpu::partition(w, h, make_uint2(gx, gy), *cfg, n_ranks, tile);
+        if (owner) std::memcpy(owner, p.owner.data(), p.owner.size());
+        if (loads) {
+            const std::vector<double> l = interleave ? fovpt_multigpu::loads_of(p, w, h, make_uint2(gx, gy), *cfg, n_ranks) : p.loads;
+            std::memcpy(loads, l.data(), l.size() * sizeof(double));
+        }
+        return p.tiles_x | (p.tiles_y << 16);
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
 }
 
 // ---- ProbeData / Camera

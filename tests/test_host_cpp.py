@@ -40,6 +40,7 @@ def H():
     L.fovpth_texture_count.argtypes = [vp]
     L.fovpth_texture_get.argtypes = [vp, C.c_int, vp, vp, vp]
     L.fovpth_decode_image.argtypes = [C.c_char_p, vp, vp, vp, C.c_size_t]
+    L.fovpth_partition.argtypes = [C.c_int, C.c_int, C.c_uint, C.c_uint, vp, C.c_int, C.c_int, C.c_int, vp, vp]
     L.fovpth_build_cdf.argtypes = [C.c_int, C.c_int] + [vp] * 5
     L.fovpth_camera_uvw.argtypes = [vp, vp, vp, C.c_float, C.c_float, vp]
     L.fovpth_renderer_new.argtypes = [vp, C.c_int, vp]
@@ -156,6 +157,32 @@ def test_texture_decoders_match_reference_loader(H):
     w, h = C.c_int(), C.c_int()
     assert H.fovpth_decode_image(os.path.join(GOLDEN, "textures", "broken.png").encode(), C.byref(w), C.byref(h), None, 0) != 0
     assert b"PNG" in H.fovpth_last_error() or b"truncated" in H.fovpth_last_error()
+
+
+def test_cpp_tile_partition_is_the_python_partition(H):
+    """host/MultiGpu.cpp (what a C++ application links) against partition.py (what bench.py uses): byte-identical owner tables
+    and equal per-rank loads, for the density-weighted and the interleaved assignment, several frame sizes / gaze points / ranks"""
+    from fovpathtracing_optixcodelatest_b200 import native, partition
+    cases = [(1920, 1080, (960, 540), 74, 241, 32), (2160, 2160, (1680, 480), 148, 482, 32), (1000, 333, (3, 330), 20, 90, 16), (64, 48, (32, 24), 4, 12, 32)]
+    for (w, h, gaze, ri, ro, tile) in cases:
+        for n in (1, 2, 3, 4, 8):
+            cfg = native.Config(); cfg.foveated = 1; cfg.inner_radius, cfg.outer_radius = ri, ro
+            cfg.spp_periphery, cfg.spp_mid, cfg.spp_fovea, cfg.spp_uniform = 8, 16, 32, 4
+            want, wloads = partition.partition(w, h, gaze, ri, ro, n, tile=tile)
+            own = np.zeros(want.shape, np.uint8); loads = np.zeros(max(1, n), np.float64)
+            rc = H.fovpth_partition(w, h, gaze[0], gaze[1], C.byref(cfg), n, tile, 0, p(own), p(loads))
+            assert rc == (want.shape[1] | (want.shape[0] << 16)), H.fovpth_last_error()
+            assert (own == want).all() and (loads == wloads).all(), (w, h, n)
+            want = partition.interleaved(w, h, n, 16)
+            own = np.zeros(want.shape, np.uint8)
+            assert H.fovpth_partition(w, h, gaze[0], gaze[1], C.byref(cfg), n, 16, 1, p(own), p(loads)) == (want.shape[1] | (want.shape[0] << 16))
+            assert (own == want).all()
+            assert np.allclose(loads, partition.loads_of(want, w, h, gaze, ri, ro, n, 16))
+    cfg = native.Config(); cfg.foveated = 0; cfg.spp_uniform = 4; cfg.spp_periphery = cfg.spp_mid = cfg.spp_fovea = 1
+    want, _ = partition.partition(640, 360, (0, 0), 0, 0, 4, foveated=False)
+    own = np.zeros(want.shape, np.uint8)
+    assert H.fovpth_partition(640, 360, 0, 0, C.byref(cfg), 4, 32, 0, p(own), None) > 0 and (own == want).all()
+    assert H.fovpth_partition(640, 360, 0, 0, C.byref(cfg), 300, 32, 0, p(own), None) == -1       # one byte per tile: <= 256 ranks
 
 
 def test_addbox_matches_reference(H, ref):
@@ -292,3 +319,21 @@ def test_fovpt_demo_renders_writes_and_rereads_a_ppm(H, tmp_path):
     same = (px[written] == want[written]).mean()
     assert same > 0.999, same
     assert len(np.unique(px)) > 50                                          # an image, not a constant
+
+
+@pytest.mark.gpu
+def test_fovpt_multi_cpp_processes_write_the_single_gpu_frame(tmp_path):
+    """host/multi_main.cpp: a C++ multi-GPU job -- one process per rank, tile partition from host/MultiGpu.cpp, the frame
+    gathered over peer memory into rank 0 (SharedFrame) -- writes byte for byte the PPM the single-process fovpt_demo writes.
+    With one GPU in the box the three ranks share it (the peer path is CUDA IPC either way)."""
+    import subprocess
+    host = os.path.join(ROOT, "fovpathtracing_optixcodelatest_b200", "host")
+    obj = os.path.join(ROOT, "assets", "cornell.obj")
+    args = ["320", "180", "3", "200", "70"]
+    one = tmp_path / "one.ppm"; many = tmp_path / "many.ppm"
+    a = subprocess.run([os.path.join(host, "fovpt_demo"), obj] + args + [str(one)], capture_output=True, text=True, timeout=300)
+    assert a.returncode == 0, a.stderr
+    b = subprocess.run([os.path.join(host, "fovpt_multi"), obj] + args + ["3", str(many)], capture_output=True, text=True, timeout=300)
+    assert b.returncode == 0, b.stderr + b.stdout
+    assert "rank 0 of 3" in b.stdout
+    assert one.read_bytes() == many.read_bytes()

@@ -19,10 +19,14 @@ using namespace fovpt;
 
 namespace {
 
-struct HostMesh {
-    std::vector<float> vtx; std::vector<uint32_t> idx; std::vector<float> tc;
-    MaterialBlob mat; int texture_id;
+// One mesh of the scene being assembled.  Geometry does not stay on the host: fovpt_scene_add_mesh copies it straight from the
+// caller's arrays into device arenas (vertices, mesh-local indices, texcoords), the record keeps where it went.
+struct MeshRec {
+    size_t vbase, tbase, nv, nt;       // first vertex / triangle in the arenas, counts
+    MaterialBlob mat; int texture_id; bool has_tc;
 };
+// Device array that grows by doubling (old contents moved device-to-device); `cap` / `used` in elements.
+template <typename T> struct Arena { T* p = nullptr; size_t cap = 0, used = 0; };
 struct HostTex { int w, h; std::vector<uint32_t> px; };
 
 struct Mark { cudaEvent_t ev; int kind; };      // start of a timed interval on the context stream; it ends at the next mark
@@ -41,13 +45,14 @@ struct fovpt_ctx {
     int n_sm = 148;
     LaunchCfg L;
 
-    // scene (host staging until commit)
-    std::vector<HostMesh> meshes;
+    // scene being assembled: mesh records + device arenas (filled by fovpt_scene_add_mesh), textures staged on the host
+    std::vector<MeshRec> meshes;
+    Arena<float> a_vtx; Arena<uint32_t> a_idx; Arena<float2> a_tc;     // 3 floats / 3 mesh-local indices / 1 texcoord per element group
     std::vector<HostTex> textures;
     // scene (device)
     BuiltBvh bvh;
     SceneDev scene{};
-    float* d_vtx = nullptr; uint32_t* d_idx = nullptr; uint32_t* d_tri_mesh = nullptr; float2* d_tc = nullptr;
+    uint32_t* d_idx = nullptr; uint32_t* d_tri_mesh = nullptr; uint2* d_mesh_table = nullptr;     // derived at commit: global indices, mesh per triangle
     MaterialBlob* d_mat = nullptr; int2* d_mesh_tex = nullptr; int4* d_tex_info = nullptr; uint32_t* d_texels = nullptr;
     bool committed = false;
 
@@ -123,11 +128,34 @@ void mark(fovpt_ctx* c, int kind)
 void free_scene(fovpt_ctx* c)
 {
     free_bvh(&c->bvh);
-    cudaFree(c->d_vtx); cudaFree(c->d_idx); cudaFree(c->d_tri_mesh); cudaFree(c->d_tc); cudaFree(c->d_mat);
+    cudaFree(c->d_idx); cudaFree(c->d_tri_mesh); cudaFree(c->d_mesh_table); cudaFree(c->d_mat);
     cudaFree(c->d_mesh_tex); cudaFree(c->d_tex_info); cudaFree(c->d_texels);
-    c->d_vtx = nullptr; c->d_idx = nullptr; c->d_tri_mesh = nullptr; c->d_tc = nullptr; c->d_mat = nullptr;
+    c->d_idx = nullptr; c->d_tri_mesh = nullptr; c->d_mesh_table = nullptr; c->d_mat = nullptr;
     c->d_mesh_tex = nullptr; c->d_tex_info = nullptr; c->d_texels = nullptr;
     c->committed = false;
+}
+
+// what fovpt_scene_add_mesh uploaded (the committed scene keeps using the arenas; only scene_begin / destroy drop them)
+void free_arenas(fovpt_ctx* c)
+{
+    cudaFree(c->a_vtx.p); cudaFree(c->a_idx.p); cudaFree(c->a_tc.p);
+    c->a_vtx = Arena<float>{}; c->a_idx = Arena<uint32_t>{}; c->a_tc = Arena<float2>{};
+    c->meshes.clear();
+}
+
+template <typename T> cudaError_t arena_reserve(Arena<T>& a, size_t need, cudaStream_t st)
+{
+    if (need <= a.cap) return cudaSuccess;
+    const size_t cap = std::max(need, a.cap * 2);
+    T* p = nullptr;
+    cudaError_t e = cudaMalloc((void**)&p, cap * sizeof(T) + 32);
+    if (e != cudaSuccess) return e;
+    if (a.used) e = cudaMemcpyAsync(p, a.p, a.used * sizeof(T), cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { cudaFree(p); return e; }
+    cudaFree(a.p);
+    a.p = p; a.cap = cap;
+    return cudaSuccess;
 }
 
 void free_paths(fovpt_ctx* c)
@@ -466,7 +494,7 @@ int fovpt_destroy(fovpt_ctx* c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     fovpt_peer_frame_close(c);
-    free_scene(c); free_paths(c);
+    free_scene(c); free_arenas(c); free_paths(c);
     cudaFree(c->p_data); cudaFree(c->p_pdfX); cudaFree(c->p_cdfX); cudaFree(c->p_pdfY); cudaFree(c->p_cdfY); cudaFree(c->p_gy); cudaFree(c->p_gx);
     cudaFree(c->fb_accum); cudaFree(c->fb_frame); cudaFree(c->li_backplate); cudaFree(c->li_color); cudaFree(c->needed);
     cudaFree(c->li_normal); cudaFree(c->li_albedo); cudaFree(c->fb_color); cudaFree(c->fb_normal); cudaFree(c->fb_albedo);
@@ -507,8 +535,8 @@ int fovpt_scene_begin(fovpt_ctx* c)
     if (!c) return 1;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    c->meshes.clear(); c->textures.clear();
-    free_scene(c);
+    c->textures.clear();
+    free_scene(c); free_arenas(c);
     return 0;
 }
 
@@ -524,16 +552,30 @@ int fovpt_scene_add_mesh(fovpt_ctx* c, const float* vtx, size_t nvtx, const uint
                          const float* tc, const void* material104, int texture_id)
 {
     if (!c || !vtx || !idx || !material104) { fail(c, "null mesh argument"); return -1; }
-    for (size_t i = 0; i < 3 * ntri; ++i)
-        if (idx[i] >= nvtx) { fail(c, "mesh index out of range (see SURVEY A.9: one usemtl per shape)"); return -1; }
-    for (size_t i = 0; i < 3 * nvtx; ++i)
-        if (!std::isfinite(vtx[i])) { fail(c, "non-finite vertex"); return -1; }
-    HostMesh m;
-    m.vtx.assign(vtx, vtx + 3 * nvtx); m.idx.assign(idx, idx + 3 * ntri);
-    if (tc) m.tc.assign(tc, tc + 2 * nvtx);
+    // validation as two branch-free reductions (they vectorise; an early-exit loop over 30 M indices does not)
+    uint32_t max_idx = 0;
+    for (size_t i = 0; i < 3 * ntri; ++i) max_idx = std::max(max_idx, idx[i]);
+    if (ntri && max_idx >= nvtx) { fail(c, "mesh index out of range (see SURVEY A.9: one usemtl per shape)"); return -1; }
+    uint32_t not_finite = 0;
+    for (size_t i = 0; i < 3 * nvtx; ++i) { uint32_t b; memcpy(&b, vtx + i, 4); not_finite |= (uint32_t)((b & 0x7f800000u) == 0x7f800000u); }
+    if (not_finite) { fail(c, "non-finite vertex"); return -1; }
+    if (c->a_vtx.used / 3 + nvtx >= (1ull << 32) || c->a_idx.used / 3 + ntri >= (1u << 29)) { fail(c, "too many vertices / triangles"); return -1; }
+    // Straight from the caller's arrays into the device arenas: no host-side copy of the geometry exists.  (cudaMemcpy from
+    // pageable memory returns when the source has been consumed, so the caller may free its arrays right away.)
+    cudaSetDevice(c->device);
+    cudaError_t e = arena_reserve(c->a_vtx, c->a_vtx.used + 3 * nvtx, c->stream);
+    if (e == cudaSuccess) e = arena_reserve(c->a_idx, c->a_idx.used + 3 * ntri, c->stream);
+    if (e == cudaSuccess) e = arena_reserve(c->a_tc, c->a_tc.used + nvtx, c->stream);
+    MeshRec m;
+    m.vbase = c->a_vtx.used / 3; m.tbase = c->a_idx.used / 3; m.nv = nvtx; m.nt = ntri; m.texture_id = texture_id; m.has_tc = tc != nullptr;
     memcpy(&m.mat, material104, sizeof(MaterialBlob));
-    m.texture_id = texture_id;
-    c->meshes.push_back(std::move(m));
+    if (e == cudaSuccess && nvtx) e = cudaMemcpy(c->a_vtx.p + c->a_vtx.used, vtx, 3 * nvtx * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && ntri) e = cudaMemcpy(c->a_idx.p + c->a_idx.used, idx, 3 * ntri * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && nvtx) e = tc ? cudaMemcpy(c->a_tc.p + c->a_tc.used, tc, nvtx * sizeof(float2), cudaMemcpyHostToDevice)
+                                         : cudaMemset(c->a_tc.p + c->a_tc.used, 0, nvtx * sizeof(float2));
+    if (e != cudaSuccess) { cuda_fail(c, e, "fovpt_scene_add_mesh upload"); return -1; }
+    c->a_vtx.used += 3 * nvtx; c->a_idx.used += 3 * ntri; c->a_tc.used += nvtx;
+    c->meshes.push_back(m);
     return (int)c->meshes.size() - 1;
 }
 
@@ -545,53 +587,42 @@ int fovpt_scene_commit(fovpt_ctx* c, uint64_t* traversable_out)
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     double t_last = now();
     auto phase = [&](const char* name) { if (trace) { const double t = now(); fprintf(stderr, "[fovpt commit] %-27s %9.3f ms\n", name, t - t_last); t_last = t; } };
-    free_scene(c);
-    size_t nv = 0, nt = 0;
-    for (auto& m : c->meshes) { nv += m.vtx.size() / 3; nt += m.idx.size() / 3; }
-    if (nt >= (1u << 29)) return fail(c, "too many triangles");
-    std::vector<float> vtx; vtx.reserve(3 * nv);
-    std::vector<uint32_t> idx; idx.reserve(3 * nt);
-    std::vector<uint32_t> tri_mesh; tri_mesh.reserve(nt);
-    std::vector<float> tc(2 * nv, 0.f);
-    std::vector<MaterialBlob> mats; std::vector<int2> mesh_tex;
+    free_scene(c);                                   // derived data only: the arenas filled by fovpt_scene_add_mesh stay
+    const size_t nv = c->a_vtx.used / 3, nt = c->a_idx.used / 3;
+    // per-mesh tables (small, host): where each mesh starts, its material and texture
+    std::vector<uint2> table; std::vector<MaterialBlob> mats; std::vector<int2> mesh_tex;
     int any_catcher = 0;
-    size_t vbase = 0;
-    for (size_t mi = 0; mi < c->meshes.size(); ++mi) {
-        HostMesh& m = c->meshes[mi];
-        vtx.insert(vtx.end(), m.vtx.begin(), m.vtx.end());
-        for (uint32_t i : m.idx) idx.push_back(i + (uint32_t)vbase);
-        tri_mesh.insert(tri_mesh.end(), m.idx.size() / 3, (uint32_t)mi);
-        if (!m.tc.empty()) memcpy(&tc[2 * vbase], m.tc.data(), m.tc.size() * 4);
+    for (const MeshRec& m : c->meshes) {
+        table.push_back(make_uint2((uint32_t)m.tbase, (uint32_t)m.vbase));
         mats.push_back(m.mat);
         const bool has_tex = m.texture_id >= 0 && m.texture_id < (int)c->textures.size();
-        mesh_tex.push_back(make_int2(has_tex ? m.texture_id : -1, m.tc.empty() ? 0 : 1));
+        mesh_tex.push_back(make_int2(has_tex ? m.texture_id : -1, m.has_tc ? 1 : 0));
         if (m.mat.flags & kMaterialShadowCatcher) any_catcher = 1;
-        vbase += m.vtx.size() / 3;
     }
     std::vector<int4> tex_info; std::vector<uint32_t> texels;
     for (auto& t : c->textures) {
         tex_info.push_back(make_int4((int)texels.size(), t.w, t.h, 0));
         texels.insert(texels.end(), t.px.begin(), t.px.end());
     }
-    phase("flatten meshes (host)");
-    CU(dmalloc(&c->d_vtx, vtx.size())); CU(dmalloc(&c->d_idx, idx.size())); CU(dmalloc(&c->d_tri_mesh, tri_mesh.size()));
-    CU(dmalloc(&c->d_tc, nv)); CU(dmalloc(&c->d_mat, mats.size())); CU(dmalloc(&c->d_mesh_tex, mesh_tex.size()));
+    phase("mesh tables (host)");
+    CU(dmalloc(&c->d_idx, 3 * nt)); CU(dmalloc(&c->d_tri_mesh, nt)); CU(dmalloc(&c->d_mesh_table, table.size()));
+    CU(dmalloc(&c->d_mat, mats.size())); CU(dmalloc(&c->d_mesh_tex, mesh_tex.size()));
     CU(dmalloc(&c->d_tex_info, tex_info.size())); CU(dmalloc(&c->d_texels, texels.size()));
-    CU(cudaMemcpy(c->d_vtx, vtx.data(), vtx.size() * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(c->d_idx, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(c->d_tri_mesh, tri_mesh.data(), tri_mesh.size() * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(c->d_tc, tc.data(), tc.size() * 4, cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(c->d_mat, mats.data(), mats.size() * sizeof(MaterialBlob), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(c->d_mesh_tex, mesh_tex.data(), mesh_tex.size() * sizeof(int2), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(c->d_tex_info, tex_info.data(), tex_info.size() * sizeof(int4), cudaMemcpyHostToDevice));
-    CU(cudaMemcpy(c->d_texels, texels.data(), texels.size() * 4, cudaMemcpyHostToDevice));
-
-    phase("allocate + upload");
+    CU(cudaMemcpyAsync(c->d_mesh_table, table.data(), table.size() * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_mat, mats.data(), mats.size() * sizeof(MaterialBlob), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_mesh_tex, mesh_tex.data(), mesh_tex.size() * sizeof(int2), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_tex_info, tex_info.data(), tex_info.size() * sizeof(int4), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->d_texels, texels.data(), texels.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    // mesh-local indices -> indices into the vertex soup, and the mesh id of every triangle, on the device
+    if (nt) { launch_rebase_indices(c->stream, c->a_idx.p, c->d_mesh_table, (uint32_t)table.size(), (uint32_t)nt, c->d_idx, c->d_tri_mesh); c->launches++; }
+    CU(cudaStreamSynchronize(c->stream));            // the host vectors above go out of scope
+    (void)nv;
+    phase("tables + index rebase");
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     cudaEventRecord(e0, c->stream);
     int leaf_max = 2;        // measured on C3: 2 -> 4.49 ms, 3 -> 4.52 ms, 4 -> 4.56 ms of k_trace per frame
     if (const char* e = getenv("FOVPT_LEAF_MAX")) { const int v = atoi(e); if (v >= 1 && v <= 4) leaf_max = v; }   // tuning knob
-    cudaError_t be = build_bvh(c->d_vtx, c->d_idx, c->d_tri_mesh, (uint32_t)nt, leaf_max, kBvhWide, c->stream, &c->bvh, &c->launches);
+    cudaError_t be = build_bvh(c->a_vtx.p, c->d_idx, c->d_tri_mesh, (uint32_t)nt, leaf_max, kBvhWide, c->stream, &c->bvh, &c->launches);
     cudaEventRecord(e1, c->stream);
     if (be != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return cuda_fail(c, be, "build_bvh"); }
     cudaEventSynchronize(e1);
@@ -603,7 +634,7 @@ int fovpt_scene_commit(fovpt_ctx* c, uint64_t* traversable_out)
 
     c->scene.bvh.nodes = c->bvh.nodes; c->scene.bvh.tris = c->bvh.tris;
     c->scene.bvh.n_nodes = c->bvh.n_nodes; c->scene.bvh.n_tris = c->bvh.n_tris;
-    c->scene.tri_mesh = c->d_tri_mesh; c->scene.tri_vidx = c->d_idx; c->scene.texcoords = c->d_tc;
+    c->scene.tri_mesh = c->d_tri_mesh; c->scene.tri_vidx = c->d_idx; c->scene.texcoords = c->a_tc.p;
     c->scene.materials = c->d_mat; c->scene.mesh_tex = c->d_mesh_tex; c->scene.tex_info = c->d_tex_info; c->scene.texels = c->d_texels;
     c->scene.any_catcher = any_catcher;
     c->committed = true;

@@ -49,6 +49,9 @@ struct HitRec { float t, u, v; uint32_t k; uint32_t gid; };   // k = sorted tria
 #ifndef FOVPT_SMEM_STACK
 #define FOVPT_SMEM_STACK 8
 #endif
+#ifndef FOVPT_RCP_APPROX
+#define FOVPT_RCP_APPROX 1
+#endif
 struct RayStack {
     int2* local;          // kStackSize entries
     int2* shared;         // this thread's column: entry e at shared[e * stride]
@@ -94,7 +97,17 @@ __device__ __forceinline__ float safe_rcp(float d)
     // direction component 0 -> a huge finite reciprocal keeps 0*inf NaNs out of the slab test
     const float kTiny = 1e-30f;
     float ad = fabsf(d) < kTiny ? copysignf(kTiny, d) : d;
+#if FOVPT_RCP_APPROX
+    // MUFU.RCP alone (1 ulp) instead of the correctly rounded reciprocal (MUFU + Newton step + range fix-up, ~14 instructions,
+    // three per ray).  idir only feeds the SLAB test, whose boxes are padded by 2^-16 of the scene extent (bvh_build.cu): an
+    // error of 2^-23 relative moves an entry point by < 2^-20 of the extent, so the test stays conservative and hits -- decided
+    // by the exact triangle test, which does not use idir -- are unchanged.
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(ad));
+    return r;
+#else
     return __frcp_rn(ad);          // correctly rounded, like 1.0f / ad, without the division's slow path
+#endif
 }
 
 // slab test of child slot J of a quantised node: near / far byte planes were already selected by the

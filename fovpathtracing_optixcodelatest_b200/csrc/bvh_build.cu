@@ -495,13 +495,39 @@ __global__ void k_gather_tris(uint32_t n, const uint32_t* __restrict__ sorted_id
     tri_sorted[3 * (size_t)i + 2] = tri_rec[3 * (size_t)id + 2];
 }
 
+// ------------------------------------------------------------------ scene assembly
+__global__ void k_rebase_indices(const uint32_t* __restrict__ idx_local, const uint2* __restrict__ mesh_table, uint32_t n_meshes, uint32_t ntri,
+                                 uint32_t* __restrict__ idx_global, uint32_t* __restrict__ tri_mesh)
+{
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < ntri; t += gridDim.x * blockDim.x) {
+        uint32_t lo = 0, hi = n_meshes;                   // last mesh whose first triangle is <= t (empty meshes share a start: take the last)
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (mesh_table[mid].x <= t) lo = mid; else hi = mid; }
+        const uint32_t vb = mesh_table[lo].y;
+        idx_global[3 * (size_t)t] = idx_local[3 * (size_t)t] + vb;
+        idx_global[3 * (size_t)t + 1] = idx_local[3 * (size_t)t + 1] + vb;
+        idx_global[3 * (size_t)t + 2] = idx_local[3 * (size_t)t + 2] + vb;
+        tri_mesh[t] = lo;
+    }
+}
+void launch_rebase_indices(cudaStream_t st, const uint32_t* idx_local, const uint2* mesh_table, uint32_t n_meshes, uint32_t ntri,
+                           uint32_t* idx_global, uint32_t* tri_mesh)
+{
+    k_rebase_indices<<<148 * 8, 256, 0, st>>>(idx_local, mesh_table, n_meshes, ntri, idx_global, tri_mesh);
+}
+
 // ------------------------------------------------------------------ host orchestration
-// Every temporary of one build; freed when the build returns, on the error paths too.
+// Every temporary of one build; freed when the build returns, on the error paths too.  Scratch arrays are carved out of ONE
+// slab (a 10 M-triangle build used to spend 60 of its 70 ms in ~40 cudaMalloc / cudaFree calls, 12 ms in kernels); what the
+// caller keeps (own = true) gets an allocation of its own.
 struct Temps {
     std::vector<void*> ptrs;
-    ~Temps() { for (void* p : ptrs) cudaFree(p); }
-    template <typename T> cudaError_t alloc(T** p, size_t n)
+    unsigned char* slab = nullptr; size_t slab_size = 0, slab_used = 0;
+    ~Temps() { for (void* p : ptrs) cudaFree(p); cudaFree(slab); }
+    void reserve(size_t bytes) { if (cudaMalloc((void**)&slab, bytes) == cudaSuccess) slab_size = bytes; else { slab = nullptr; cudaGetLastError(); } }
+    template <typename T> cudaError_t alloc(T** p, size_t n, bool own = false)
     {
+        const size_t bytes = (n * sizeof(T) + 32 + 255) & ~(size_t)255;
+        if (!own && slab && slab_used + bytes <= slab_size) { *p = (T*)(slab + slab_used); slab_used += bytes; return cudaSuccess; }
         cudaError_t e = cudaMalloc((void**)p, n * sizeof(T) + 32);
         if (e == cudaSuccess) ptrs.push_back((void*)*p); else *p = nullptr;
         return e;
@@ -554,10 +580,12 @@ cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, const uint32_t*
     uint32_t* lvl_counts = nullptr;
     const uint32_t nblocks = (ntri + RS_TILE - 1) / RS_TILE;
     const uint32_t ninner = ntri > 1 ? ntri - 1 : 1;
-    CK(tmp.alloc(&tri_rec, 3 * (size_t)ntri)); CK(tmp.alloc(&box_lo, ntri)); CK(tmp.alloc(&box_hi, ntri));
+    // scratch per triangle: boxes 32, keys 16, ids 8, clusters 72, nn/alive/pos 12, binary nodes 44, wide nodes 64, work items 32
+    tmp.reserve((size_t)ntri * 288 + 256 * (size_t)nblocks * 4 + ((size_t)ntri / SC_TILE + 64) * 8 + (1u << 20));
+    CK(tmp.alloc(&tri_rec, 3 * (size_t)ntri, true)); CK(tmp.alloc(&box_lo, ntri)); CK(tmp.alloc(&box_hi, ntri));
     CK(tmp.alloc(&bounds, 8)); CK(tmp.alloc(&keys[0], ntri)); CK(tmp.alloc(&keys[1], ntri));
     CK(tmp.alloc(&vals[0], ntri)); CK(tmp.alloc(&vals[1], ntri)); CK(tmp.alloc(&hist, 256 * (size_t)nblocks));
-    CK(tmp.alloc(&scal, 8)); CK(tmp.alloc(&sorted, ntri));
+    CK(tmp.alloc(&scal, 8)); CK(tmp.alloc(&sorted, ntri, true));
     uint32_t* tile_sums = nullptr;
     CK(tmp.alloc(&tile_sums, std::max<size_t>(ntri, 256 * (size_t)nblocks) / SC_TILE + 2));
     CK(cudaMemsetAsync(scal, 0, 8 * sizeof(uint32_t), st));
@@ -593,9 +621,9 @@ cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, const uint32_t*
     out->pad = pad;
 
     float4* tri_sorted = nullptr; uint4* nodes = nullptr;
-    CK(tmp.alloc(&tri_sorted, 3 * (size_t)ntri));
+    CK(tmp.alloc(&tri_sorted, 3 * (size_t)ntri, true));
     if ((int)ntri <= leaf_max) {
-        CK(tmp.alloc(&nodes, nstride));
+        CK(tmp.alloc(&nodes, nstride, true));
         k_emit_single4<<<1, 32, 0, st>>>((int)ntri, bounds, pad, nodes);
         CK(cudaMemcpyAsync(sorted, vals[cur], ntri * sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
         *launches += 1;
@@ -656,9 +684,9 @@ cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, const uint32_t*
             if (depth4 <= kMaxWideDepth) break;
             out->balanced_fallback = 1;
         }
-        if (out->n_nodes < cap) {                            // shrink to fit
+        {                                                    // the node array the caller keeps, sized to fit
             uint4* exact = nullptr;
-            CK(tmp.alloc(&exact, nstride * (size_t)out->n_nodes));
+            CK(tmp.alloc(&exact, nstride * (size_t)out->n_nodes, true));
             CK(cudaMemcpyAsync(exact, nodes, nstride * (size_t)out->n_nodes * sizeof(uint4), cudaMemcpyDeviceToDevice, st));
             CK(cudaStreamSynchronize(st));
             nodes = exact;

@@ -25,5 +25,9 @@ struct BuiltBvh {
 cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, const uint32_t* d_tri_mesh, uint32_t ntri, int leaf_max, int wide, cudaStream_t st,
                       BuiltBvh* out, uint64_t* launches);
 void free_bvh(BuiltBvh* b);
+// scene assembly (fovpt_scene_commit): idx_global[3t+k] = idx_local[3t+k] + vertex base of t's mesh, tri_mesh[t] = that mesh;
+// mesh_table[m] = (first triangle, first vertex) of mesh m, ascending
+void launch_rebase_indices(cudaStream_t st, const uint32_t* idx_local, const uint2* mesh_table, uint32_t n_meshes, uint32_t ntri,
+                           uint32_t* idx_global, uint32_t* tri_mesh);
 
 }  // namespace fovpt

@@ -203,6 +203,9 @@ __device__ __forceinline__ void shadow_resolve(const PathState& ps, const Shadow
 #ifndef FOVPT_TRACE_BLOCKS
 #define FOVPT_TRACE_BLOCKS 9
 #endif
+#ifndef FOVPT_NODE_REPEAT
+#define FOVPT_NODE_REPEAT 1   // node steps per vote: lanes still at an inner node after a node step take the next one without a new vote
+#endif
 #ifndef FOVPT_LEAF_NUM
 #define FOVPT_LEAF_NUM 2      // run the leaf phase when LEAF_NUM * lanes_at_leaf > LEAF_DEN * lanes_at_node (leaves are cheap:
 #define FOVPT_LEAF_DEN 1      // <= 2 triangles; measured best at 2:1 on C3)
@@ -265,7 +268,15 @@ __device__ __forceinline__ void trace_loop(const SceneDev& S, const PathState& p
 #endif
                 // when every lane that takes the step is a shadow ray the children need no distance order (warp-uniform flag)
                 const bool all_any = __ballot_sync(FULL, node && !T.any) == 0u;
-                if (node) T.node_step(S.bvh, stack, all_any);
+                if (node) {
+                    T.node_step(S.bvh, stack, all_any);
+#if FOVPT_NODE_REPEAT > 1
+                    // consecutive node steps only ever lose lanes to the leaf phase, so the vote between them decides nothing but
+                    // when the leaf phase starts: take the next step(s) right away and save the loop bookkeeping (~19 instructions)
+#pragma unroll 1
+                    for (int rep = 1; rep < FOVPT_NODE_REPEAT; ++rep) if (T.at_node()) T.node_step(S.bvh, stack, all_any);
+#endif
+                }
                 stepped = node;
             } else {
                 const uint32_t nmax = __reduce_max_sync(FULL, leaf ? T.leaf_work() : 0u);

@@ -253,7 +253,7 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const uint64_t* __
 // ------------------------------------------------------------------ PLOC
 // node ids: >= 0 inner binary node, < 0 leaf = ~(global triangle id)
 #ifndef FOVPT_PLOC_RADIUS
-#define FOVPT_PLOC_RADIUS 16
+#define FOVPT_PLOC_RADIUS 32
 #endif
 constexpr int kPlocRadius = FOVPT_PLOC_RADIUS;
 constexpr int kPlocThreads = 256;

@@ -204,7 +204,10 @@ __device__ __forceinline__ void shadow_resolve(const PathState& ps, const Shadow
 #define FOVPT_TRACE_BLOCKS 9
 #endif
 #ifndef FOVPT_NODE_REPEAT
-#define FOVPT_NODE_REPEAT 1   // node steps per vote: lanes still at an inner node after a node step take the next one without a new vote
+#define FOVPT_NODE_REPEAT 2   // node steps per vote: lanes still at an inner node after a node step take the next one without a new vote
+#endif
+#ifndef FOVPT_NODE_ADAPT
+#define FOVPT_NODE_ADAPT 0    // > 0: repeat only while this many eighths of the first step's lanes are still at inner nodes
 #endif
 #ifndef FOVPT_LEAF_NUM
 #define FOVPT_LEAF_NUM 2      // run the leaf phase when LEAF_NUM * lanes_at_leaf > LEAF_DEN * lanes_at_node (leaves are cheap:
@@ -273,8 +276,19 @@ __device__ __forceinline__ void trace_loop(const SceneDev& S, const PathState& p
 #if FOVPT_NODE_REPEAT > 1
                     // consecutive node steps only ever lose lanes to the leaf phase, so the vote between them decides nothing but
                     // when the leaf phase starts: take the next step(s) right away and save the loop bookkeeping (~19 instructions)
+#if FOVPT_NODE_ADAPT
+                    // keep stepping while at least ADAPT/8 of the lanes that took the first step are still at an inner node
+                    const int first = __popc(mn);
+#pragma unroll 1
+                    for (int rep = 1; rep < FOVPT_NODE_REPEAT; ++rep) {
+                        const bool again = T.at_node();
+                        if (8 * __popc(__ballot_sync(__activemask(), again)) < FOVPT_NODE_ADAPT * first) break;
+                        if (again) T.node_step(S.bvh, stack, all_any);
+                    }
+#else
 #pragma unroll 1
                     for (int rep = 1; rep < FOVPT_NODE_REPEAT; ++rep) if (T.at_node()) T.node_step(S.bvh, stack, all_any);
+#endif
 #endif
                 }
                 stepped = node;

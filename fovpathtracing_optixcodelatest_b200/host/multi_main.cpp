@@ -86,6 +86,7 @@ int run_rank(int rank, int world, int handle_fd, const std::vector<int>& publish
             if (fovpt_sync(sample.context()) != 0) throw std::runtime_error(fovpt_last_error(sample.context()));
         }
         delete model;
+        std::fflush(stdout);                                       // the ranks leave through _exit()
         return 0;
     } catch (const std::exception& e) {
         std::cerr << "FATAL ERROR (rank " << rank << "): " << e.what() << std::endl;

@@ -301,7 +301,11 @@ def test_fovpt_demo_renders_writes_and_rereads_a_ppm(H, tmp_path):
     assert H.fovpth_decode_image(str(out).encode(), C.byref(ww), C.byref(hh), p(px), px.size) == 0, H.fovpth_last_error()
     assert (ww.value, hh.value) == (w, h)
     # the same frame through the python binding (main.cpp's camera: bounding box centre, 1.4 extents back along +z)
-    sc = scenes.cornell_box()
+    m = H.fovpth_load_obj(os.path.join(ROOT, "assets", "cornell.obj").encode())      # the scene as the OBJ file holds it (rounded decimals)
+    sc = scenes.Scene()
+    for x in model_meshes(H, m):
+        sc.add(x["vtx"], x["idx"], x["material"], x["texcoord"], x["texture_id"])
+    H.fovpth_model_free(m)
     v = np.concatenate([m.vtx for m in sc.meshes]); lo, hi = v.min(0), v.max(0)
     centre = (0.5 * (lo + hi)).astype(np.float32); extent = np.float32((hi - lo).max())
     cam = scenes.CameraSpec(eye=(centre[0], centre[1], np.float32(centre[2] + np.float32(1.4) * extent)), lookat=tuple(centre), up=(0.0, 1.0, 0.0), fovy=45.0)

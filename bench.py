@@ -501,6 +501,26 @@ def native_arm(args):
         e2e_pageable_ms = p0.elapsed_time(p1)
         assert int(pageable.astype(np.uint64).sum()) == checksum
 
+    # the reference's own build flag (--use_fast_math, CMakeLists.txt:181) as an extra data point: the same timed loop with
+    # fovpt_config.fast_math = 1 (SFU sin / cos / pow / log / reciprocal in shading; parity bar 1e-3 instead of 1e-6)
+    fast = None
+    if world == 1:
+        cfg_fast = wl.apply(native.default_config()); cfg_fast.fast_math = 1
+        r.ctx.set_config(cfg_fast)
+        lp.frame.subframe_index = 0; step_no[0] = 0
+        for _ in range(2):
+            step()
+        barrier()
+        lp.frame.subframe_index = 0; step_no[0] = 0
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for k in range(args.steps):
+            step()
+        f1.record()
+        barrier()
+        fast = f0.elapsed_time(f1)
+        r.ctx.set_config(cfg)
+
     if rank == 0:
         hbm, peak_src = load_peaks()
         traced_samples = samples                               # sum over ranks, incl. tile-edge duplicates
@@ -524,6 +544,9 @@ def native_arm(args):
                     "pageable_destination": None if e2e_pageable_ms is None else
                     {"value": samples / (e2e_pageable_ms * 1e-3) / 1e6, "ms_per_step": e2e_pageable_ms / args.steps}},
             "ingest": ingest,
+            "use_fast_math": None if fast is None else
+            {"value": samples / (fast * 1e-3) / 1e6, "ms_per_step": fast / args.steps,
+             "note": "fovpt_config.fast_math = 1, the reference's --use_fast_math build (CMakeLists.txt:181); not the headline: `value` is IEEE shading"},
             "clocks": clk, "wall_s_timed_region": t_wall, "step_ms": step_ms, "per_rank": per_rank,
         }
         if parity is not None:

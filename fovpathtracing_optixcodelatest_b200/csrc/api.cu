@@ -374,13 +374,16 @@ int run_frame(fovpt_ctx* c, const LaunchParamsBlob& lp, const std::vector<PassHo
         // k_shade(i-1) emitted (counter slot alternates 2 / 5), k_shade(i) consumes the hits.
         for (int it = 0; it <= iters; ++it) {
             const int slot_prev = (it & 1) ? 2 : 5, slot_new = (it & 1) ? 5 : 2;
+            char range[32]; snprintf(range, sizeof(range), "fovpt bounce %d", it);
+            nvtx_push(range);
             mark(c, K_EXTEND);
             launch_trace(c->L, c->scene, ps, c->q, slot_prev, c->cfg.tmin, c->cfg.tmax, c->d_stats); c->launches++; c->trace_launches++;
-            if (it == iters) break;                      // the last launch only drains the final shadow rays
+            if (it == iters) { nvtx_pop(); break; }      // the last launch only drains the final shadow rays
             if (feat && it == 0) { launch_features(c->L, c->scene, ps, c->q, c->cfg.fast_math != 0); c->launches++; }
             mark(c, K_SHADE);
             launch_shade(c->L, F, c->scene, ps, c->q, slot_new, c->cfg.fast_math != 0); c->launches++;
             std::swap(c->q.cur, c->q.next);                // the device-side counters are swapped by k_shade's last CTA
+            nvtx_pop();
         }
         mark(c, K_RESOLVE);
         launch_resolve_li(c->L, F, g.res, c->needed, c->ps, c->li_backplate, c->li_color, feat ? c->li_normal : nullptr, feat ? c->li_albedo : nullptr); c->launches++;

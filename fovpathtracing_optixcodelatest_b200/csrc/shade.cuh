@@ -112,43 +112,70 @@ __device__ __forceinline__ float fresnel_dielectric(float vdn, float eta_i, floa
     return 0.5f * (sq(r1) + sq(r2));
 }
 
+// Terms of the BSDF that depend on the material, the normal and the VIEW direction only.  One hit evaluates the BSDF for two
+// light directions (the probe sample of the next-event estimate and the sampled continuation) and its pdf for both; the
+// reference recomputes these terms in every call (Disney.cuh:152-193, :318-427), here they are computed once per hit.
+// Every term keeps the reference's expression, so the values are the ones the separate calls produced.
+struct BsdfView {
+    float ndv, a;          // dot(n, v); max(0.001, roughness)
+    float F;               // fresnel_dielectric(ndv, eta_i, eta_o)
+    float Gv, FV;          // smith_ggx(ndv, a); schlick_weight(ndv)
+    float3 spec0;
+};
+
 template <bool FAST>
-__device__ __forceinline__ float bsdf_pdf(const BsdfParams& m, float eta_i, float eta_o, float3 n, float3 v, float3 l)
+__device__ __forceinline__ void bsdf_view_terms(const BsdfParams& m, float3 albedo, BsdfView& w)
 {
-    const float ldn = dot3(l, n);
-    if (ldn <= 0.f) return mixf(FOVPT_INV_2PI * m.subsurface * 0.5f, 0.f, m.transmission);
-    const float F = fresnel_dielectric(dot3(n, v), eta_i, eta_o);
-    const float a = fmaxf(0.001f, m.roughness);
+    const float lum = 0.3f * albedo.x + 0.6f * albedo.y + 0.1f * albedo.z;
+    const float3 tint = lum > 0.f ? albedo * Mth<FAST>::rcp(lum) : f3(1.f);
+    w.spec0 = mix3((m.specular * 0.08f) * mix3(f3(1.f), tint, m.specularTint), albedo, m.metallic);
+    w.Gv = smith_ggx(w.ndv, w.a);
+    w.FV = schlick_weight(w.ndv);
+}
+
+// ... and the terms that depend on one light direction, shared by its pdf and its value: the half vector's cosines and the
+// GGX distribution at it (BSDFPdf and BSDFEval both normalise l + v and both evaluate GTR2 there, Disney.cuh:168-178, :330-352)
+struct BsdfDir { float ndl, ndh, ldh, D; };
+
+template <bool FAST>
+__device__ __forceinline__ void bsdf_dir_terms(const BsdfView& w, float3 n, float3 v, float3 l, BsdfDir& d)
+{
+    d.ndl = dot3(n, l);
     float3 h = l + v;
     const float hl = dot3(h, h);
     h = hl > 0.f ? h * Mth<FAST>::rsqrt(hl) : f3(0.f);
-    const float cth = fabsf(dot3(h, n));
-    const float pdf_half = gtr2(cth, a) * cth;
-    const float pdf_spec = 0.25f * pdf_half / fmaxf(1.e-6f, dot3(l, h));
-    const float pdf_diff = fabsf(ldn) * FOVPT_INV_PI * (1.f - m.subsurface);
-    return mixf(mixf(pdf_diff, pdf_spec, 0.5f), pdf_spec * F, m.transmission);
+    d.ndh = dot3(n, h); d.ldh = dot3(l, h);
+    d.D = d.ndl > 0.f ? gtr2(d.ndh, w.a) : 0.f;           // only the upper hemisphere branches read it
 }
 
 template <bool FAST>
-__device__ __forceinline__ float3 bsdf_eval(const BsdfParams& m, float3 albedo, float eta_i, float eta_o, float3 n, float3 v, float3 l)
+__device__ __forceinline__ float bsdf_pdf(const BsdfParams& m, const BsdfView& w, const BsdfDir& d)
 {
-    const float ndl = dot3(n, l), ndv = dot3(n, v);
-    const float3 h = unit3<FAST>(l + v);
-    const float ndh = dot3(n, h), ldh = dot3(l, h);
-    const float lum = 0.3f * albedo.x + 0.6f * albedo.y + 0.1f * albedo.z;
-    const float3 tint = lum > 0.f ? albedo * Mth<FAST>::rcp(lum) : f3(1.f);
-    const float3 spec0 = mix3((m.specular * 0.08f) * mix3(f3(1.f), tint, m.specularTint), albedo, m.metallic);
+    const float ldn = d.ndl;
+    if (ldn <= 0.f) return mixf(FOVPT_INV_2PI * m.subsurface * 0.5f, 0.f, m.transmission);
+    const float cth = fabsf(d.ndh);
+    const float pdf_half = d.D * cth;
+    const float pdf_spec = 0.25f * pdf_half / fmaxf(1.e-6f, d.ldh);
+    const float pdf_diff = fabsf(ldn) * FOVPT_INV_PI * (1.f - m.subsurface);
+    return mixf(mixf(pdf_diff, pdf_spec, 0.5f), pdf_spec * w.F, m.transmission);
+}
+
+template <bool FAST>
+__device__ __forceinline__ float3 bsdf_eval(const BsdfParams& m, const BsdfView& w, const BsdfDir& d, float3 albedo, float eta_i, float eta_o)
+{
+    const float ndl = d.ndl, ndv = w.ndv;
+    const float ndh = d.ndh, ldh = d.ldh;
+    const float3 spec0 = w.spec0;
     float3 bsdf = f3(0.f), brdf = f3(0.f);
-    const float a = fmaxf(0.001f, m.roughness);
+    const float a = w.a;
     if (m.transmission > 0.f) {
         if (ndl <= 0.f) {
-            const float F = fresnel_dielectric(ndv, eta_i, eta_o);
-            bsdf = f3(m.transmission * (1.f - F) / fabsf(ndl) * (1.f - m.metallic));
+            bsdf = f3(m.transmission * (1.f - w.F) / fabsf(ndl) * (1.f - m.metallic));
         } else {
-            const float Ds = gtr2(ndh, a);
+            const float Ds = d.D;
             const float FH = fresnel_dielectric(ldh, eta_i, eta_o);
             const float3 Fs = mix3(spec0, f3(1.f), FH);
-            const float Gs = smith_ggx(ndv, a) * smith_ggx(ndl, a);
+            const float Gs = w.Gv * smith_ggx(ndl, a);
             bsdf = Gs * Fs * Ds;
         }
     }
@@ -157,22 +184,29 @@ __device__ __forceinline__ float3 bsdf_eval(const BsdfParams& m, float3 albedo, 
             if (m.subsurface > 0.f) {
                 // uses the material colour, not the textured albedo (Disney.cuh:374)
                 const float3 s = f3(sqrtf(m.color.x), sqrtf(m.color.y), sqrtf(m.color.z));
-                const float FL = schlick_weight(fabsf(ndl)), FV = schlick_weight(ndv);
-                const float Fd = (1.f - 0.5f * FL) * (1.f - 0.5f * FV);
+                const float FL = schlick_weight(fabsf(ndl));
+                const float Fd = (1.f - 0.5f * FL) * (1.f - 0.5f * w.FV);
                 brdf = FOVPT_INV_PI * s * m.subsurface * Fd * (1.f - m.metallic);
             }
         } else {
-            const float Ds = gtr2(ndh, a);
+            const float Ds = d.D;
             const float FH = schlick_weight(ldh);
             const float3 Fs = mix3(spec0, f3(1.f), FH);
-            const float Gs = smith_ggx(ndv, a) * smith_ggx(ndl, a);
-            const float FL = schlick_weight(ndl), FV = schlick_weight(ndv);
+            const float Gs = w.Gv * smith_ggx(ndl, a);
+            const float FL = schlick_weight(ndl);
             const float Fd90 = 0.5f + 2.f * ldh * ldh * m.roughness;
-            const float Fd = mixf(1.f, Fd90, FL) * mixf(1.f, Fd90, FV);
-            const float Dr = gtr1<FAST>(ndh, mixf(.1f, .001f, m.clearcoatGloss));
-            const float Fc = mixf(.04f, 1.f, FH);
-            const float Gr = smith_ggx(ndl, .25f) * smith_ggx(ndv, .25f);
-            brdf = FOVPT_INV_PI * Fd * albedo * (1.f - m.metallic) * (1.f - m.subsurface) + Gs * Fs * Ds + f3(m.clearcoat * Gr * Fc * Dr);
+            const float Fd = mixf(1.f, Fd90, FL) * mixf(1.f, Fd90, w.FV);
+            // clearcoat lobe (Disney.cuh:411-417): the reference evaluates it for every material and multiplies by m.clearcoat;
+            // with clearcoat == 0 (the constructor default, Material.h:31) the product is an exact zero, so the log, the two
+            // Smith terms and their divisions are skipped without changing a bit of the result
+            float cc = 0.f;
+            if (m.clearcoat != 0.f) {
+                const float Dr = gtr1<FAST>(ndh, mixf(.1f, .001f, m.clearcoatGloss));
+                const float Fc = mixf(.04f, 1.f, FH);
+                const float Gr = smith_ggx(ndl, .25f) * smith_ggx(ndv, .25f);
+                cc = m.clearcoat * Gr * Fc * Dr;
+            }
+            brdf = FOVPT_INV_PI * Fd * albedo * (1.f - m.metallic) * (1.f - m.subsurface) + Gs * Fs * Ds + f3(cc);
         }
     }
     return mix3(brdf, bsdf, m.transmission);
@@ -180,9 +214,8 @@ __device__ __forceinline__ float3 bsdf_eval(const BsdfParams& m, float3 albedo, 
 
 // GGX half-vector sample shared by the two specular branches (Disney.cuh:211-219 and :287-301)
 template <bool FAST>
-__device__ __forceinline__ float3 ggx_reflect(const BsdfParams& m, float3 tu, float3 tv, float3 n, float3 view, float r1, float r2)
+__device__ __forceinline__ float3 ggx_reflect(float a, float3 tu, float3 tv, float3 n, float3 view, float r1, float r2)
 {
-    const float a = fmaxf(0.001f, m.roughness);
     const float cth = sqrtf((1.f - r2) / (1.f + (sq(a) - 1.f) * r2));
     const float sth = sqrtf(fmaxf(0.f, 1.f - sq(cth)));
     float sp, cp;
@@ -192,35 +225,36 @@ __device__ __forceinline__ float3 ggx_reflect(const BsdfParams& m, float3 tu, fl
     return 2.f * dot3(view, h) * h - view;
 }
 
-// returns pdf (<= 0: path ends).  Consumes 2, 4, 5 or 7 uniform draws depending on the branch.
+// Draws the continuation direction (Disney.cuh:197-315 up to its closing BSDFPdf call).  Returns < 0 when the pdf of `light` is
+// still to be evaluated with bsdf_pdf (every branch but smooth refraction), else the final pdf (<= 0: path ends).
+// Consumes 2, 4, 5 or 7 uniform draws depending on the branch.  w.ndv, w.a and w.F must be set.
 template <bool FAST>
-__device__ __forceinline__ float bsdf_sample(const BsdfParams& m, float eta_i, float eta_o, float3 tu, float3 tv, float3 n, float3 view,
-                                             fx_rng& rng, float3& light)
+__device__ __forceinline__ float bsdf_sample_dir(const BsdfParams& m, const BsdfView& w, float eta_i, float eta_o, float3 tu, float3 tv, float3 n,
+                                                 float3 view, fx_rng& rng, float3& light)
 {
     if (fx_rng_f(&rng) < m.transmission) {
-        const float F = fresnel_dielectric(dot3(n, view), eta_i, eta_o);
-        if (fx_rng_f(&rng) < F) {
+        if (fx_rng_f(&rng) < w.F) {
             const float r1 = fx_rng_f(&rng), r2 = fx_rng_f(&rng);
-            light = ggx_reflect<FAST>(m, tu, tv, n, view, r1, r2);
+            light = ggx_reflect<FAST>(w.a, tu, tv, n, view, r1, r2);
         } else {
             // smooth refraction (Disney.cuh:36-49,231-247)
             const float eta = eta_i / eta_o;
-            const float ci = dot3(n, view);
+            const float ci = w.ndv;
             const float s2t = eta * eta * fmaxf(0.f, 1.f - ci * ci);
             if (s2t >= 1.f) return 0.f;
             const float ct = sqrtf(1.f - s2t);
             light = eta * (-view) + (eta * ci - ct) * n;
-            return (1.f - F) * m.transmission;
+            return (1.f - w.F) * m.transmission;
         }
     } else {
         const float r1 = fx_rng_f(&rng), r2 = fx_rng_f(&rng);
         if (fx_rng_f(&rng) < 0.5f) {
             if (fx_rng_f(&rng) < m.subsurface) {
                 const float z = fx_rng_f(&rng);
-                const float w = sqrtf(1.f - z * z);
+                const float wz = sqrtf(1.f - z * z);
                 float s, c;
                 Mth<FAST>::sincos(FOVPT_2PI * fx_rng_f(&rng), &s, &c);
-                light = tu * (c * w) + tv * (s * w) - n * z;
+                light = tu * (c * wz) + tv * (s * wz) - n * z;
             } else {
                 const float r = sqrtf(r1);
                 float s, c;
@@ -230,10 +264,10 @@ __device__ __forceinline__ float bsdf_sample(const BsdfParams& m, float eta_i, f
                 light = tu * dx + tv * dy + n * dz;
             }
         } else {
-            light = ggx_reflect<FAST>(m, tu, tv, n, view, r1, r2);
+            light = ggx_reflect<FAST>(w.a, tu, tv, n, view, r1, r2);
         }
     }
-    return bsdf_pdf<FAST>(m, eta_i, eta_o, n, view, light);
+    return -1.f;
 }
 
 // ---------------------------------------------------------------- probe

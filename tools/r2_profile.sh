@@ -21,3 +21,4 @@ full-c5)   # per step (one subframe = 265 M samples): 6 row-chunk groups x 6 k_t
   python tools/ncu_summary.py gpurun_out/prof_${TAG}_c5.ncu-rep gpurun_out/ncu_${TAG}_c5.json "tools/r2_profile.sh $TAG full c5: ncu --set full --clock-control none -k regex:k_trace -s 144 -c 6; $CMD (the 6 k_trace launches of the first row-chunk group of the timed step: 48 Mi paths of the 10 M-triangle scene, tree larger than L2)" > /dev/null
   rm -f gpurun_out/prof_${TAG}_c5.ncu-rep ;;
 esac
+cp gpurun_out/plain.log gpurun_out/plain_${TAG}_${MODE}_$WL.log 2>/dev/null

@@ -554,7 +554,7 @@ int fovpt_scene_add_texture(fovpt_ctx* c, const uint32_t* rgba8, int w, int h)
 int fovpt_scene_add_mesh(fovpt_ctx* c, const float* vtx, size_t nvtx, const uint32_t* idx, size_t ntri,
                          const float* tc, const void* material104, int texture_id)
 {
-    if (!c || !vtx || !idx || !material104) { fail(c, "null mesh argument"); return -1; }
+    if (!c || (!vtx && nvtx) || (!idx && ntri) || !material104) { fail(c, "null mesh argument"); return -1; }
     // validation as two branch-free reductions (they vectorise; an early-exit loop over 30 M indices does not)
     uint32_t max_idx = 0;
     for (size_t i = 0; i < 3 * ntri; ++i) max_idx = std::max(max_idx, idx[i]);

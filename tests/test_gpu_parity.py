@@ -719,6 +719,61 @@ def test_api_contract_and_errors(gpu):
     ctx.close(); r.close()
 
 
+def test_scene_ingest_is_independent_of_how_the_meshes_arrive(gpu):
+    """fovpt_scene_add_mesh copies geometry straight into growing device arenas and fovpt_scene_commit rebases the indices on
+    the device: the textured atrium handed over (a) as its meshes, (b) one triangle per mesh with unshared vertices --
+    thousands of add_mesh calls, so the arenas grow by doubling many times -- with empty meshes and a NaN / out-of-range
+    rejection in between, and (c) committed twice, must give the same frame bit for bit (triangle order, hence every
+    tie-break, is preserved); also ragged input: meshes without texcoords next to meshes with them"""
+    w, h, ri, ro = 240, 136, 20, 60
+    sc = scenes.atrium(detail=0.08)
+    cam, probe = scenes.SPONZA_CAMERA, scenes.sky_probe(64, 32, 3)
+
+    def render(ctx_fill):
+        r = gpu.SampleRenderer(scenes.Scene(), 0)
+        cfg = gpu.native.default_config(); cfg.inner_radius, cfg.outer_radius = ri, ro; r.setConfig(cfg)
+        ctx_fill(r.ctx)
+        r.resize((w, h)); r.setCamera(cam); r.setProbe(gpu.ProbeData(probe).BuildCDF())
+        r.launchParams.frame.c_x, r.launchParams.frame.c_y = w // 2, h // 2
+        r.render()
+        out = (r.downloadPixels().copy(), r.downloadAccum().copy(), r.stats()["bvh_tris"])
+        r.close()
+        return out
+
+    def whole(ctx):
+        ctx.upload_scene(sc)
+
+    def shredded(ctx):
+        ctx.scene_begin()
+        for t in sc.textures:
+            ctx.add_texture(t)
+        empty_v, empty_i = np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32)
+        for k, m in enumerate(sc.meshes):
+            ctx.add_mesh(empty_v, empty_i, m.material)                       # an empty mesh between the real ones
+            if k == 1:
+                bad = m.vtx[:3].copy(); bad[1, 2] = np.nan
+                with pytest.raises(RuntimeError, match="finite"):
+                    ctx.add_mesh(bad, [[0, 1, 2]], m.material)                # refused; the arenas stay as they were
+                with pytest.raises(RuntimeError, match="index"):
+                    ctx.add_mesh(m.vtx[:3], [[0, 1, 3]], m.material)
+            step = 1 if len(m.idx) < 400 else 97                              # small meshes: one triangle per add_mesh call
+            for a in range(0, len(m.idx), step):
+                tri = m.idx[a:a + step].astype(np.int64)
+                v = m.vtx[tri.reshape(-1)]
+                tc = None if m.texcoord is None else m.texcoord[tri.reshape(-1)]
+                ctx.add_mesh(v, np.arange(len(v), dtype=np.uint32).reshape(-1, 3), m.material, tc, m.texture_id)
+        ctx.commit()
+
+    def twice(ctx):
+        ctx.upload_scene(sc)
+        ctx.commit()                                                          # a second commit rebuilds from the same arenas
+
+    a, b, c = render(whole), render(shredded), render(twice)
+    assert a[2] == b[2] == c[2] == sc.n_tris
+    assert (a[0] == b[0]).all() and (bits(a[1]) == bits(b[1])).all()
+    assert (a[0] == c[0]).all() and (bits(a[1]) == bits(c[1])).all()
+
+
 def test_c_program_drives_the_abi(gpu, tmp_path):
     """tests/c/abi_smoke.c: a C99 program builds a scene and traces rays through include/fovpt.h"""
     import subprocess

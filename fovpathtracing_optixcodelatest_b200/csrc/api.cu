@@ -566,6 +566,10 @@ int fovpt_scene_add_mesh(fovpt_ctx* c, const float* vtx, size_t nvtx, const uint
     // Straight from the caller's arrays into the device arenas: no host-side copy of the geometry exists.  (cudaMemcpy from
     // pageable memory returns when the source has been consumed, so the caller may free its arrays right away.)
     cudaSetDevice(c->device);
+    if (c->committed) {                                   // the committed scene reads the arenas (texcoords): growing them invalidates it
+        cudaStreamSynchronize(c->stream);
+        c->committed = false;                             // frames fail with "scene not committed" until fovpt_scene_commit runs again
+    }
     cudaError_t e = arena_reserve(c->a_vtx, c->a_vtx.used + 3 * nvtx, c->stream);
     if (e == cudaSuccess) e = arena_reserve(c->a_idx, c->a_idx.used + 3 * ntri, c->stream);
     if (e == cudaSuccess) e = arena_reserve(c->a_tc, c->a_tc.used + nvtx, c->stream);

@@ -79,7 +79,10 @@ int         fovpt_get_config(fovpt_ctx*, fovpt_config*);
 
 /* -- scene: SampleRenderer::buildAccel + createTextures + buildSBT, SimplePathtracer.cpp:602-746,
  *    748-799, 534-599.  Host pointers.  mesh = one (shape, material) group of loadOBJ; returns the
- *    mesh / texture id (>= 0) or a negative error.  Indices are bounds-checked. */
+ *    mesh / texture id (>= 0) or a negative error.  Indices are bounds-checked, vertices must be finite.
+ *    fovpt_scene_add_mesh copies the arrays straight into device memory before it returns (no host-side copy is kept; the
+ *    caller may free them at once); vtx / idx may be NULL for an empty mesh.  Adding a mesh after a commit invalidates the
+ *    committed scene until fovpt_scene_commit is called again; a second commit without changes rebuilds the same scene. */
 int fovpt_scene_begin(fovpt_ctx*);
 int fovpt_scene_add_texture(fovpt_ctx*, const uint32_t* rgba8, int w, int h);
 int fovpt_scene_add_mesh(fovpt_ctx*, const float* vtx, size_t nvtx, const uint32_t* idx, size_t ntri,

@@ -778,6 +778,11 @@ def test_scene_ingest_is_independent_of_how_the_meshes_arrive(gpu):
     def twice(ctx):
         ctx.upload_scene(sc)
         ctx.commit()                                                          # a second commit rebuilds from the same arenas
+        m0 = sc.meshes[0]
+        ctx.add_mesh(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.uint32), m0.material)
+        with pytest.raises(RuntimeError, match="not committed"):              # adding a mesh invalidates the committed scene ...
+            ctx.trace(np.zeros((1, 8), np.float32), 0)
+        ctx.commit()                                                          # ... until the next commit
 
     a, b, c = render(whole), render(shredded), render(twice)
     assert a[2] == b[2] == c[2] == sc.n_tris

@@ -34,11 +34,14 @@ struct Bytes {
     unsigned be32() { unsigned a = be16(); return (a << 16) | be16(); }
     unsigned le16() { unsigned a = u8(); return a | (u8() << 8); }
     unsigned le32() { unsigned a = le16(); return a | (le16() << 16); }
-    void skip(size_t k) { if (k > n - pos) fail("file is truncated"); pos += k; }
-    const uint8_t* take(size_t k) { if (k > n - pos) fail("file is truncated"); const uint8_t* q = p + pos; pos += k; return q; }
+    void skip(size_t k) { if (pos > n || k > n - pos) fail("file is truncated"); pos += k; }
+    const uint8_t* take(size_t k) { if (pos > n || k > n - pos) fail("file is truncated"); const uint8_t* q = p + pos; pos += k; return q; }
 };
 
 inline uint32_t rgba(unsigned r, unsigned g, unsigned b, unsigned a) { return r | (g << 8) | (b << 16) | (a << 24); }
+
+// a corrupt header must not turn into a multi-gigabyte allocation: 2^28 texels (1 GiB of RGBA8) is far beyond any texture
+inline void check_size(long long w, long long h) { if (w <= 0 || h <= 0 || w * h > (1ll << 28)) fail("image dimensions out of range"); }
 
 // ---------------------------------------------------------------- inflate
 // Canonical prefix code: a 10-bit first-level table (symbol | length << 9) and, for longer codes, the
@@ -197,6 +200,7 @@ void decode_png(const uint8_t* d, size_t n, int& w, int& h, std::vector<uint32_t
             w = (int)in.be32(); h = (int)in.be32(); depth = in.u8(); ctype = in.u8();
             const unsigned comp = in.u8(), filt = in.u8(); interlace = in.u8();
             if (w <= 0 || h <= 0 || w > (1 << 24) || h > (1 << 24)) fail("PNG: bad image size");
+            check_size(w, h);
             if (comp || filt || interlace > 1) fail("PNG: unknown compression / filter / interlace method");
             const bool ok = (ctype == 0 && (depth == 1 || depth == 2 || depth == 4 || depth == 8 || depth == 16)) ||
                             ((ctype == 2 || ctype == 4 || ctype == 6) && (depth == 8 || depth == 16)) ||
@@ -330,6 +334,8 @@ void decode_tga(const uint8_t* d, size_t n, int& w, int& h, std::vector<uint32_t
     if (!read_tga_header(d, n, t)) fail("TGA: bad header");
     Bytes in(d, n); in.skip(18 + t.idlen);
     const bool indexed = t.cmap_type == 1, rle = t.type >= 8, grey = (t.type & 7) == 3;
+    if (indexed && t.cmap_len == 0) fail("TGA: colour-mapped image without a palette");
+    check_size(t.w, t.h);
     const unsigned cbits = indexed ? t.cmap_bits : t.bpp;
     if (grey && cbits != 8 && cbits != 16) fail("TGA: unsupported grey depth");
     const unsigned cbytes = (cbits + 7) / 8;
@@ -390,6 +396,7 @@ struct JHuff {
         unsigned code = 0; int k = 0;
         for (int l = 1; l <= 16; ++l) {
             delta[l] = k - (int)code;
+            if (code + counts[l - 1] > (1u << l)) fail("JPEG: bad Huffman table");      // over-subscribed: would index past the tables
             for (int i = 0; i < counts[l - 1]; ++i, ++k, ++code) {
                 if (l <= 9) { const unsigned lo = code << (9 - l); for (unsigned j = 0; j < (1u << (9 - l)); ++j) look[lo + j] = (uint16_t)(vals[k] | (l << 8)); }
             }
@@ -551,26 +558,28 @@ struct Jpeg {
     }
 
     // ---- inverse DCT: 8x8 coefficients -> 8x8 samples at out (row stride given)
-    static inline uint8_t clamp8(int v) { return (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v); }
-    struct Lines { int e0, e1, e2, e3, o0, o1, o2, o3; };
-    static inline Lines idct_1d(int s0, int s1, int s2, int s3, int s4, int s5, int s6, int s7)
+    // (64-bit intermediates: a valid stream stays far inside 32 bits and gets the same values; a corrupt one cannot overflow)
+    typedef long long wide;
+    static inline uint8_t clamp8(wide v) { return (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v); }
+    struct Lines { wide e0, e1, e2, e3, o0, o1, o2, o3; };
+    static inline Lines idct_1d(wide s0, wide s1, wide s2, wide s3, wide s4, wide s5, wide s6, wide s7)
     {
-        constexpr int c0_541 = 2217, c1_847 = -7567, c0_765 = 3135, c1_175 = 4816, c0_298 = 1223, c2_053 = 8410, c3_072 = 12586,
+        constexpr wide c0_541 = 2217, c1_847 = -7567, c0_765 = 3135, c1_175 = 4816, c0_298 = 1223, c2_053 = 8410, c3_072 = 12586,
                       c1_501 = 6149, c0_899 = -3685, c2_562 = -10497, c1_961 = -8034, c0_390 = -1597;        // round(x * 4096)
         // even part
-        const int z = (s2 + s6) * c0_541, a2 = z + s6 * c1_847, a3 = z + s2 * c0_765;
-        const int a0 = (s0 + s4) * 4096, a1 = (s0 - s4) * 4096;
+        const wide z = (s2 + s6) * c0_541, a2 = z + s6 * c1_847, a3 = z + s2 * c0_765;
+        const wide a0 = (s0 + s4) * 4096, a1 = (s0 - s4) * 4096;
         Lines L;
         L.e0 = a0 + a3; L.e3 = a0 - a3; L.e1 = a1 + a2; L.e2 = a1 - a2;
         // odd part
-        const int p3 = s7 + s3, p4 = s5 + s1, p1 = s7 + s1, p2 = s5 + s3, p5 = (p3 + p4) * c1_175;
-        const int q1 = p5 + p1 * c0_899, q2 = p5 + p2 * c2_562, q3 = p3 * c1_961, q4 = p4 * c0_390;
+        const wide p3 = s7 + s3, p4 = s5 + s1, p1 = s7 + s1, p2 = s5 + s3, p5 = (p3 + p4) * c1_175;
+        const wide q1 = p5 + p1 * c0_899, q2 = p5 + p2 * c2_562, q3 = p3 * c1_961, q4 = p4 * c0_390;
         L.o3 = s1 * c1_501 + q1 + q4; L.o2 = s3 * c3_072 + q2 + q3; L.o1 = s5 * c2_053 + q2 + q4; L.o0 = s7 * c0_298 + q1 + q3;
         return L;
     }
     static void idct(uint8_t* out, int stride, const int16_t d[64])
     {
-        int tmp[64];
+        wide tmp[64];
         for (int i = 0; i < 8; ++i) {                                // columns, 10 bits dropped
             Lines L = idct_1d(d[i], d[8 + i], d[16 + i], d[24 + i], d[32 + i], d[40 + i], d[48 + i], d[56 + i]);
             L.e0 += 512; L.e1 += 512; L.e2 += 512; L.e3 += 512;
@@ -580,9 +589,9 @@ struct Jpeg {
             tmp[24 + i] = (L.e3 + L.o0) >> 10; tmp[32 + i] = (L.e3 - L.o0) >> 10;
         }
         for (int i = 0; i < 8; ++i, out += stride) {                 // rows, 17 bits dropped, +128 folded into the rounding term
-            const int* v = tmp + 8 * i;
+            const wide* v = tmp + 8 * i;
             Lines L = idct_1d(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
-            const int bias = 65536 + (128 << 17);
+            const wide bias = 65536 + (128 << 17);
             L.e0 += bias; L.e1 += bias; L.e2 += bias; L.e3 += bias;
             out[0] = clamp8((L.e0 + L.o3) >> 17); out[7] = clamp8((L.e0 - L.o3) >> 17);
             out[1] = clamp8((L.e1 + L.o2) >> 17); out[6] = clamp8((L.e1 - L.o2) >> 17);
@@ -624,6 +633,7 @@ struct Jpeg {
         if (in.u8() != 8) fail("JPEG: only 8-bit samples are supported");
         h = (int)in.be16(); w = (int)in.be16(); ncomp = (int)in.u8();
         if (h <= 0 || w <= 0) fail("JPEG: bad image size");
+        check_size(w, h);
         if (ncomp == 4) fail("JPEG: CMYK / YCCK images are not supported");
         if (ncomp != 1 && ncomp != 3) fail("JPEG: bad component count");
         if (len != 8u + 3u * ncomp) fail("JPEG: bad SOF length");
@@ -853,6 +863,7 @@ void decode_bmp(const uint8_t* d, size_t n, int& w, int& h, std::vector<uint32_t
     const unsigned bpp = in.le16(), comp = in.le32();
     const bool top_down = hh < 0; h = top_down ? -hh : hh;
     if ((bpp != 24 && bpp != 32) || comp != 0 || w <= 0 || h <= 0) fail("BMP: only uncompressed 24 / 32 bit images are supported");
+    check_size(w, h);
     const size_t stride = ((size_t)w * (bpp / 8) + 3) & ~(size_t)3;
     in.pos = off;
     px.resize((size_t)w * h);
@@ -887,6 +898,7 @@ void decode_ppm(const uint8_t* d, size_t n, int& w, int& h, std::vector<uint32_t
     };
     w = next_int(); h = next_int();
     if (next_int() != 255 || w <= 0 || h <= 0) fail("PPM: only 8-bit P6 files are supported");
+    check_size(w, h);
     const uint8_t* q = in.take((size_t)w * h * 3);
     px.resize((size_t)w * h);
     for (size_t i = 0; i < px.size(); ++i) px[i] = rgba(q[3 * i], q[3 * i + 1], q[3 * i + 2], 255);

@@ -159,6 +159,42 @@ def test_texture_decoders_match_reference_loader(H):
     assert b"PNG" in H.fovpth_last_error() or b"truncated" in H.fovpth_last_error()
 
 
+def test_texture_decoders_survive_damaged_files(H, tmp_path):
+    """textures come from disk: every fixture truncated at a dozen places and with random bytes overwritten must be either
+    refused with a message or decoded to an image of the size the header states -- never crash, hang or allocate without bound"""
+    rng = np.random.default_rng(7)
+    tex = os.path.join(GOLDEN, "textures")
+    files = sorted(f for f in os.listdir(tex) if f.rsplit(".", 1)[-1] in ("png", "tga", "jpg", "bmp", "ppm"))
+    assert len(files) >= 50
+    path = str(tmp_path / "damaged.bin").encode()
+    w, h = C.c_int(), C.c_int()
+    out = np.zeros(1 << 18, np.uint32)
+    refused = decoded = 0
+    for f in files:
+        data = open(os.path.join(tex, f), "rb").read()
+        variants = [data[:k] for k in sorted(set(int(x) for x in np.linspace(0, len(data) - 1, 8)))]
+        for _ in range(24):
+            d = bytearray(data)
+            for _ in range(int(rng.integers(1, 4))):
+                d[int(rng.integers(0, len(d)))] = int(rng.integers(0, 256))
+            variants.append(bytes(d))
+        big = bytearray(data)                                         # blow the size fields up
+        if f.endswith(".png"): big[16:24] = b"\x7f\xff\xff\xff\x7f\xff\xff\xff"
+        elif f.endswith(".tga"): big[12:16] = b"\xff\xff\xff\xff"
+        elif f.endswith(".bmp"): big[18:26] = b"\xff\xff\xff\x7f\xff\xff\xff\x7f"
+        variants.append(bytes(big))
+        for v in variants:
+            open(path, "wb").write(v)
+            rc = H.fovpth_decode_image(path, C.byref(w), C.byref(h), p(out), out.size)
+            if rc != 0:
+                assert H.fovpth_last_error(), f
+                refused += 1
+            else:
+                assert 0 < w.value * h.value <= (1 << 28), f
+                decoded += 1
+    assert refused > 300 and decoded > 300                            # both outcomes occur (a flipped pixel byte still decodes)
+
+
 def test_cpp_tile_partition_is_the_python_partition(H):
     """host/MultiGpu.cpp (what a C++ application links) against partition.py (what bench.py uses): byte-identical owner tables
     and equal per-rank loads, for the density-weighted and the interleaved assignment, several frame sizes / gaze points / ranks"""

@@ -35,6 +35,7 @@
 
 #include "bvh.cuh"
 #include "bvh_build.h"
+#include "top_sah.h"
 
 namespace fovpt {
 
@@ -365,90 +366,7 @@ __global__ void k_cluster_counts(uint32_t n, const int* __restrict__ cid, const 
     if (i < n) out[i] = cid[i] < 0 ? 1u : cnt[cid[i]];
 }
 
-namespace {
-struct TopCluster { int cid; float lo[3], hi[3]; uint32_t cnt; };
-struct TopNode { int left, right; float lo[3], hi[3]; uint32_t cnt; };
-
-inline float half_area(const float lo[3], const float hi[3])
-{
-    const float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
-    return dx * dy + dy * dz + dz * dx;
-}
-
-// Builds the subtree over c[b, e) (reordering that range) into nodes[base, base + (e - b) - 1) and returns its id (first_id +
-// index; a single cluster is its own subtree).  A subtree over m clusters has exactly m - 1 inner nodes, so every range of
-// the node array belongs to one call: ids do not depend on which thread runs what.
-int top_sah(TopCluster* c, size_t b, size_t e, int first_id, TopNode* nodes, size_t base, int depth)
-{
-    if (e - b == 1) return c[b].cid;
-    float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f}, clo[3] = {3e38f, 3e38f, 3e38f}, chi[3] = {-3e38f, -3e38f, -3e38f};
-    uint32_t total = 0;
-    for (size_t i = b; i < e; ++i) {
-        for (int a = 0; a < 3; ++a) {
-            lo[a] = std::min(lo[a], c[i].lo[a]); hi[a] = std::max(hi[a], c[i].hi[a]);
-            const float m = 0.5f * (c[i].lo[a] + c[i].hi[a]);
-            clo[a] = std::min(clo[a], m); chi[a] = std::max(chi[a], m);
-        }
-        total += c[i].cnt;
-    }
-    constexpr int kBins = 32;
-    struct Bin { float lo[3], hi[3]; uint32_t n; };
-    float best_cost = 3e38f; int best_axis = -1, best_bin = 0;
-    float sc[3]; bool use[3];
-    for (int a = 0; a < 3; ++a) { use[a] = depth < 48 && chi[a] - clo[a] > 0.f; sc[a] = use[a] ? kBins / (chi[a] - clo[a]) : 0.f; }
-    if (use[0] || use[1] || use[2]) {                      // deeper than 48 levels (adversarial input): halve the list
-        Bin bins[3][kBins];
-        for (int a = 0; a < 3; ++a) for (int k = 0; k < kBins; ++k) { bins[a][k].n = 0; for (int d = 0; d < 3; ++d) { bins[a][k].lo[d] = 3e38f; bins[a][k].hi[d] = -3e38f; } }
-        for (size_t i = b; i < e; ++i)                      // one pass over the clusters fills the bins of all three axes
-            for (int a = 0; a < 3; ++a) {
-                if (!use[a]) continue;
-                Bin& B = bins[a][std::min(kBins - 1, std::max(0, (int)((0.5f * (c[i].lo[a] + c[i].hi[a]) - clo[a]) * sc[a])))];
-                B.n += c[i].cnt;
-                for (int d = 0; d < 3; ++d) { B.lo[d] = std::min(B.lo[d], c[i].lo[d]); B.hi[d] = std::max(B.hi[d], c[i].hi[d]); }
-            }
-        for (int a = 0; a < 3; ++a) {
-            if (!use[a]) continue;
-            float rl[kBins][3], rh[kBins][3]; uint32_t rn[kBins];           // suffix boxes
-            float l3[3] = {3e38f, 3e38f, 3e38f}, h3[3] = {-3e38f, -3e38f, -3e38f}; uint32_t nn = 0;
-            for (int k = kBins - 1; k >= 0; --k) {
-                for (int d = 0; d < 3; ++d) { l3[d] = std::min(l3[d], bins[a][k].lo[d]); h3[d] = std::max(h3[d], bins[a][k].hi[d]); rl[k][d] = l3[d]; rh[k][d] = h3[d]; }
-                nn += bins[a][k].n; rn[k] = nn;
-            }
-            for (int d = 0; d < 3; ++d) { l3[d] = 3e38f; h3[d] = -3e38f; }
-            nn = 0;
-            for (int k = 0; k + 1 < kBins; ++k) {                           // split after bin k
-                for (int d = 0; d < 3; ++d) { l3[d] = std::min(l3[d], bins[a][k].lo[d]); h3[d] = std::max(h3[d], bins[a][k].hi[d]); }
-                nn += bins[a][k].n;
-                if (nn == 0 || rn[k + 1] == 0) continue;
-                const float cost = half_area(l3, h3) * (float)nn + half_area(rl[k + 1], rh[k + 1]) * (float)rn[k + 1];
-                if (cost < best_cost) { best_cost = cost; best_axis = a; best_bin = k; }
-            }
-        }
-    }
-    size_t mid = b;
-    if (best_axis >= 0) {
-        const int a = best_axis;
-        TopCluster* it = std::partition(c + b, c + e, [&](const TopCluster& x) {
-            return std::min(kBins - 1, std::max(0, (int)((0.5f * (x.lo[a] + x.hi[a]) - clo[a]) * sc[a]))) <= best_bin; });
-        mid = (size_t)(it - c);
-    }
-    if (mid == b || mid == e) mid = b + (e - b) / 2;                        // coincident centroids: split the list in half
-    const size_t ml = mid - b;
-    int l, r;
-    if (e - b > 16384 && depth < 6) {                                       // big subtrees: left half on a thread of its own
-        std::thread t([&]() { l = top_sah(c, b, mid, first_id, nodes, base + 1, depth + 1); });
-        r = top_sah(c, mid, e, first_id, nodes, base + ml, depth + 1);
-        t.join();
-    } else {
-        l = top_sah(c, b, mid, first_id, nodes, base + 1, depth + 1);
-        r = top_sah(c, mid, e, first_id, nodes, base + ml, depth + 1);
-    }
-    TopNode& nd = nodes[base];
-    nd.left = l; nd.right = r; nd.cnt = total;
-    for (int d = 0; d < 3; ++d) { nd.lo[d] = lo[d]; nd.hi[d] = hi[d]; }
-    return first_id + (int)base;
-}
-}  // namespace
+using topsah::TopCluster; using topsah::TopNode; using topsah::top_sah;
 
 // ------------------------------------------------------------------ 4-wide collapse
 struct CollapseItem { int bvh2; int node4; uint32_t first; uint32_t pad_; };   // first = slot of the subtree's first triangle in the final order
@@ -783,7 +701,7 @@ cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, const uint32_t*
                 CK(cudaStreamSynchronize(st));
                 std::vector<TopCluster> tc(n);
                 for (uint32_t i = 0; i < n; ++i)
-                    tc[i] = TopCluster{h_cid[i], {h_lo[i].x, h_lo[i].y, h_lo[i].z}, {h_hi[i].x, h_hi[i].y, h_hi[i].z}, h_cnt[i]};
+                    tc[i] = TopCluster{{h_lo[i].x, h_lo[i].y, h_lo[i].z}, h_cid[i], {h_hi[i].x, h_hi[i].y, h_hi[i].z}, h_cnt[i]};
                 std::vector<TopNode> tn(n - 1);              // n - 1 new binary nodes, ids next_id ..
                 const int root = top_sah(tc.data(), 0, n, (int)next_id, tn.data(), 0, 0);
                 const size_t m = tn.size();

@@ -38,6 +38,18 @@ def test_header_is_plain_c_and_library_links_from_c(tmp_path):
     assert out.returncode == 0, out.stdout + out.stderr
 
 
+def test_bvh_top_level_sah_builder(tmp_path):
+    """the BVH builder's host stage (csrc/top_sah.h: binned SAH over the clusters the device-side PLOC phase leaves) as a CPU
+    program: every cluster a leaf exactly once, node boxes / counts consistent, result independent of thread timing, separated
+    groups split first, coincident boxes balanced (tests/c/top_sah_test.cpp)"""
+    import subprocess
+    exe = str(tmp_path / "top_sah_test")
+    subprocess.run(["g++", "-std=c++17", "-O2", "-Wall", "-Werror", "-pthread", "-I", os.path.join(ROOT, "fovpathtracing_optixcodelatest_b200", "csrc"),
+                    os.path.join(ROOT, "tests", "c", "top_sah_test.cpp"), "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "top_sah ok" in out.stdout, out.stdout + out.stderr
+
+
 def test_no_gpu_fails_loudly():
     import torch
     if torch.cuda.is_available():

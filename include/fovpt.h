@@ -87,7 +87,8 @@ int fovpt_scene_begin(fovpt_ctx*);
 int fovpt_scene_add_texture(fovpt_ctx*, const uint32_t* rgba8, int w, int h);
 int fovpt_scene_add_mesh(fovpt_ctx*, const float* vtx, size_t nvtx, const uint32_t* idx, size_t ntri,
                          const float* texcoord_or_null, const void* material104, int texture_id);
-/* builds the BVH on the device (Morton codes, radix sort, PLOC clustering, collapse into compressed wide nodes);
+/* builds the BVH (on the device: Morton codes, radix sort, PLOC clustering, collapse into compressed wide nodes; on the host:
+ * the top of the tree by binned SAH over the last <= 1 M clusters, a few tens of ms on the machine's cores);
  * *traversable_out is what LaunchParams.traversable (offset 160) must carry. */
 int fovpt_scene_commit(fovpt_ctx*, uint64_t* traversable_out);
 

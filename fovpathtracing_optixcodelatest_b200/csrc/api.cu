@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <string>
 #include <vector>
 
@@ -546,8 +547,10 @@ int fovpt_scene_begin(fovpt_ctx* c)
 int fovpt_scene_add_texture(fovpt_ctx* c, const uint32_t* rgba8, int w, int h)
 {
     if (!c || !rgba8 || w <= 0 || h <= 0) { fail(c, "bad texture"); return -1; }
-    HostTex t; t.w = w; t.h = h; t.px.assign(rgba8, rgba8 + (size_t)w * h);
-    c->textures.push_back(std::move(t));
+    try {
+        HostTex t; t.w = w; t.h = h; t.px.assign(rgba8, rgba8 + (size_t)w * h);
+        c->textures.push_back(std::move(t));
+    } catch (const std::exception& e) { fail(c, std::string("fovpt_scene_add_texture: ") + e.what()); return -1; }
     return (int)c->textures.size() - 1;
 }
 
@@ -586,9 +589,15 @@ int fovpt_scene_add_mesh(fovpt_ctx* c, const float* vtx, size_t nvtx, const uint
     return (int)c->meshes.size() - 1;
 }
 
+static int scene_commit(fovpt_ctx* c, uint64_t* traversable_out);
 int fovpt_scene_commit(fovpt_ctx* c, uint64_t* traversable_out)
 {
     if (!c) return 1;
+    try { return scene_commit(c, traversable_out); }
+    catch (const std::exception& e) { return fail(c, std::string("fovpt_scene_commit: ") + e.what()); }      // no exception crosses the C ABI
+}
+static int scene_commit(fovpt_ctx* c, uint64_t* traversable_out)
+{
     cudaSetDevice(c->device);
     const bool trace = getenv("FOVPT_BUILD_TRACE") != nullptr;
     auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
@@ -734,15 +743,23 @@ int fovpt_launch(fovpt_ctx* c, const void* lp248, size_t size, unsigned lw, unsi
     if (lp.frame.size_x <= 0 || lp.frame.size_y <= 0) return fail(c, "frame.size not set");
     if (lp.frame.factor_x != lp.frame.factor_y) return fail(c, "anisotropic factor not supported");
     if (lw == 0 || lh == 0) return 0;
-    std::vector<PassHost> p;
-    p.push_back({lw, lh, lp.frame.factor_x, lp.frame.fillSize, lp.frame.r_inner, lp.frame.r_outer, lp.samples_per_launch,
-                 lp.frame.offset_x, lp.frame.offset_y, lp.frame.redraw, lp.frame.subframe_index, 0u});
-    return run_frame(c, lp, p);
+    try {
+        std::vector<PassHost> p;
+        p.push_back({lw, lh, lp.frame.factor_x, lp.frame.fillSize, lp.frame.r_inner, lp.frame.r_outer, lp.samples_per_launch,
+                     lp.frame.offset_x, lp.frame.offset_y, lp.frame.redraw, lp.frame.subframe_index, 0u});
+        return run_frame(c, lp, p);
+    } catch (const std::exception& e) { return fail(c, std::string("fovpt_launch: ") + e.what()); }
 }
 
+static int render_frames(fovpt_ctx* c, void* lp248, int n_subframes);
 int fovpt_render_frames(fovpt_ctx* c, void* lp248, int n_subframes)
 {
     if (!c) return 1;
+    try { return render_frames(c, lp248, n_subframes); }
+    catch (const std::exception& e) { return fail(c, std::string("fovpt_render_frames: ") + e.what()); }
+}
+static int render_frames(fovpt_ctx* c, void* lp248, int n_subframes)
+{
     if (!lp248) return fail(c, "null launch params");
     if (n_subframes < 1 || n_subframes > 65536) return fail(c, "n_subframes out of range");
     LaunchParamsBlob* lp = (LaunchParamsBlob*)lp248;

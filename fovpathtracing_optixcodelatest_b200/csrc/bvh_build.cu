@@ -34,6 +34,7 @@
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <exception>
 #include <thread>
 #include <vector>
 
@@ -692,7 +693,7 @@ cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, const uint32_t*
             }
             out->ploc_rounds = rounds;
             phase("PLOC rounds");
-            if (n > 1) {                                     // the tree above the remaining clusters: top-down SAH on the host
+            if (n > 1) try {                                 // the tree above the remaining clusters: top-down SAH on the host
                 std::vector<int> h_cid(n); std::vector<float4> h_lo(n), h_hi(n); std::vector<uint32_t> h_cnt(n);
                 uint32_t next_id = 0;
                 k_cluster_counts<<<(n + 255) / 256, 256, 0, st>>>(n, cid[cb], cnt, pos);
@@ -722,7 +723,7 @@ cudaError_t build_bvh(const float* d_vtx, const uint32_t* d_idx, const uint32_t*
                 CK(cudaMemcpyAsync(cid[cb], &root, sizeof(int), cudaMemcpyHostToDevice, st));
                 CK(cudaStreamSynchronize(st));               // the host vectors go out of scope
                 phase("top-level SAH (host)");
-            }
+            } catch (const std::exception&) { return cudaErrorMemoryAllocation; }       // host memory for the cluster list
             // ---- 4-wide collapse, one launch per level of the wide tree, until a level comes up empty
             CK(cudaMemsetAsync(lvl_counts, 0, ((size_t)max_levels + 2) * sizeof(uint32_t), st));
             k_seed_collapse<<<1, 32, 0, st>>>(items[0], lvl_counts, scal + 2, cid[cb]);

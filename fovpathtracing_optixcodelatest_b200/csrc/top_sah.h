@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstddef>
 #include <cstdint>
+#include <system_error>
 #include <thread>
 #include <vector>
 #if defined(__SSE2__)
@@ -137,9 +138,12 @@ inline int top_sah(TopCluster* c, size_t b, size_t e, int first_id, TopNode* nod
     const size_t ml = mid - b;
     int l, r;
     if (e - b > 16384 && depth < 6) {                                       // big subtrees: left half on a thread of its own
-        std::thread t([&]() { l = top_sah(c, b, mid, first_id, nodes, base + 1, depth + 1); });
+        std::thread t;
+        bool spawned = true;
+        try { t = std::thread([&]() { l = top_sah(c, b, mid, first_id, nodes, base + 1, depth + 1); }); }
+        catch (const std::system_error&) { spawned = false; }              // no thread to be had: do the left half here as well
         r = top_sah(c, mid, e, first_id, nodes, base + ml, depth + 1);
-        t.join();
+        if (spawned) t.join(); else l = top_sah(c, b, mid, first_id, nodes, base + 1, depth + 1);
     } else {
         l = top_sah(c, b, mid, first_id, nodes, base + 1, depth + 1);
         r = top_sah(c, mid, e, first_id, nodes, base + ml, depth + 1);

@@ -576,8 +576,8 @@ def native_arm(args):
                                     "avg_launch_ms": ext_ms / n_trace_launches,
                                     "rays_per_s_in_kernel": rays_in_kernel,
                                     "note": "algorithmic bytes = oracle canonical-BVH node visits*64 + triangle tests*48 + 48 per ray "
-                                            "(DESIGN.md section 5).  Measured DRAM traffic is 59 B/ray on C3 (tree L2-resident) and 147 B/ray on C5 "
-                                            "(10 M triangles, tree > L2; ncu, profiles/ncu_r02f_*): L1/L2 absorb > 90 % of the algorithmic bytes on every "
+                                            "(DESIGN.md section 5).  Measured DRAM traffic is 58 B/ray on C3 (tree L2-resident) and 109 B/ray on C5 "
+                                            "(10 M triangles, tree > L2; ncu, profiles/ncu_r03c_*): L1/L2 absorb > 90 % of the algorithmic bytes on every "
                                             "workload, so HBM is not what binds k_trace -- issue slots are, see roofline_issue"}
                 if ip and clk and clk.get("sm_mhz"):
                     # issue-slot roofline: one warp instruction per SM sub-partition and clock.  warp_inst_per_ray is an ncu constant of this

@@ -5,7 +5,8 @@
 //   OBJ : v, vn, vt, f (v, v/vt, v//vn, v/vt/vn; negative indices; polygons), o, g, usemtl, mtllib
 //   MTL : newmtl, Kd, Ke, map_Kd
 //   textures : PNG, TGA, JPEG, BMP, PPM through host/ImageDecode.cpp (own decoders, texel-identical to the
-//              reference's); undecodable files are reported and skipped (diffuseTextureID = -1) as in the reference
+//              reference's); undecodable files are reported and skipped (diffuseTextureID = -1) as in the reference;
+//              all files the used materials name are decoded up front on all cores, ids are assigned in the reference's order
 // Resulting Model, as the reference produces it (Model.cpp:138-217):
 //   * a new shape starts at every `o` / `g`; one TriangleMesh per (shape, material id), shapes in file
 //     order, material ids ascending inside a shape; meshes without faces are dropped;
@@ -19,6 +20,7 @@
 #include "ImageDecode.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -27,6 +29,8 @@
 #include <set>
 #include <sstream>
 #include <stdexcept>
+#include <system_error>
+#include <thread>
 #include <tuple>
 
 // ---- ownership (the containers hold raw pointers, as the reference's callers expect)
@@ -113,19 +117,48 @@ Corner parse_corner(const std::string& tok, int nv, int nvt, int nvn)
     return c;
 }
 
-// returns the texture id in model->textures, or -1 (reference loadTexture, Model.cpp:87-136)
-int load_texture(Model* model, std::map<std::string, int>& known, const std::string& name, const std::string& model_dir)
+// One decoded image file; loadOBJ decodes every file its used materials name up front, on all cores (a Sponza-class scene
+// names dozens of multi-megabyte PNG / TGA files: seconds of decoding when done one after the other in the mesh loop).
+struct Decoded { bool ok = false; int w = 0, h = 0; std::vector<uint32_t> px; std::string why; };
+
+std::string texture_path(const std::string& name, const std::string& model_dir)
+{
+    std::string file = name;
+    std::replace(file.begin(), file.end(), '\\', '/');                 // "first, fix backspaces" (Model.cpp:99-102)
+    return model_dir + file;
+}
+
+void decode_all(std::map<std::string, Decoded>& cache)
+{
+    std::vector<std::pair<const std::string, Decoded>*> jobs;
+    for (auto& kv : cache) jobs.push_back(&kv);
+    std::atomic<size_t> next{0};
+    auto worker = [&]() {
+        for (size_t i; (i = next.fetch_add(1)) < jobs.size();) {
+            Decoded& d = jobs[i]->second;
+            d.ok = fovpt_image::decode_file(jobs[i]->first, d.w, d.h, d.px, &d.why);
+        }
+    };
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t nthreads = std::min<size_t>(std::min<size_t>(hw, 32), jobs.size());
+    std::vector<std::thread> pool;
+    try { for (size_t t = 1; t < nthreads; ++t) pool.emplace_back(worker); } catch (const std::system_error&) {}
+    worker();
+    for (auto& t : pool) t.join();
+}
+
+// returns the texture id in model->textures, or -1 (reference loadTexture, Model.cpp:87-136); pixels come from the cache
+int load_texture(Model* model, std::map<std::string, int>& known, const std::string& name, const std::string& model_dir,
+                 const std::map<std::string, Decoded>& cache)
 {
     if (name.empty()) return -1;
     auto it = known.find(name);
     if (it != known.end()) return it->second;
-    std::string file = name;
-    std::replace(file.begin(), file.end(), '\\', '/');
-    file = model_dir + file;
-    int w = 0, h = 0; std::vector<uint32_t> px;
+    const std::string file = texture_path(name, model_dir);
     int id = -1;
-    std::string why;
-    if (fovpt_image::decode_file(file, w, h, px, &why)) {
+    const Decoded& d = cache.at(file);
+    const int w = d.w, h = d.h; const std::vector<uint32_t>& px = d.px; const std::string& why = d.why;
+    if (d.ok) {
         Texture* t = new Texture;
         t->resolution = make_int2(w, h);
         t->pixel = new uint32_t[(size_t)w * h];
@@ -186,6 +219,13 @@ Model* loadOBJ(const std::string& objFile)
     if (shapes.back().faces.empty()) shapes.pop_back();
     std::cout << "Done loading obj file - found " << shapes.size() << " shapes with " << materials.size() << " materials" << std::endl;
 
+    // every texture file a used material names, decoded in parallel before the meshes are assembled
+    std::map<std::string, Decoded> decoded;
+    for (const Shape& shape : shapes)
+        for (const Face& f : shape.faces)
+            if (f.material >= 0 && !materials[(size_t)f.material].map_kd.empty()) decoded[texture_path(materials[(size_t)f.material].map_kd, model_dir)];
+    decode_all(decoded);
+
     Model* model = new Model;
     for (const Shape& shape : shapes) {
         std::set<int> ids;
@@ -215,7 +255,7 @@ Model* loadOBJ(const std::string& objFile)
             if (id >= 0) {
                 mesh->material.color = materials[id].kd;               // :190-191
                 mesh->material.emission = materials[id].ke;
-                mesh->diffuseTextureID = load_texture(model, known_textures, materials[id].map_kd, model_dir);
+                mesh->diffuseTextureID = load_texture(model, known_textures, materials[id].map_kd, model_dir, decoded);
             }
             if (mesh->vertex.empty()) delete mesh; else model->meshes.push_back(mesh);
         }

@@ -848,6 +848,16 @@ int fovpt_download_accum(fovpt_ctx* c, float* dst, size_t npix)
     return 0;
 }
 
+int fovpt_upload_accum(fovpt_ctx* c, const float* src, size_t npix)
+{
+    if (!c || !src) return 1;
+    if (!c->fb_accum || npix != (size_t)c->fb_w * c->fb_h) return fail(c, "fovpt_upload_accum: size differs from the accumulation buffer of fovpt_resize");
+    cudaSetDevice(c->device);
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemcpy(c->fb_accum, src, npix * 16, cudaMemcpyHostToDevice));
+    return 0;
+}
+
 int fovpt_trace(fovpt_ctx* c, const float* rays, size_t n, int mode, int32_t* tri, float* tuv)
 {
     if (!c || !rays || !tri) return 1;

@@ -1,8 +1,10 @@
 // SimplePathtracer.cpp -- SampleRenderer on top of the libfovpt C ABI (see SimplePathtracer.h).
 #include "SimplePathtracer.h"
 
+#include <cstdio>
 #include <cstring>
 #include <iostream>
+#include <vector>
 #include <stdexcept>
 
 void SampleRenderer::check(int rc)
@@ -106,6 +108,35 @@ void SampleRenderer::downloadPixels(uint32_t h_pixels[])
 void SampleRenderer::downloadAccum(float4 h_accum[])
 {
     check(fovpt_download_accum(ctx, &h_accum[0].x, (size_t)launchParams.frame.size.x * launchParams.frame.size.y));
+}
+
+void SampleRenderer::saveCheckpoint(const std::string& path)
+{
+    const int w = launchParams.frame.size.x, h = launchParams.frame.size.y;
+    std::vector<float4> accum((size_t)w * h);
+    downloadAccum(accum.data());
+    FILE* f = std::fopen(path.c_str(), "wb");
+    if (!f) throw std::runtime_error("cannot write checkpoint " + path);
+    const int32_t head[3] = {w, h, (int32_t)launchParams.frame.subframe_index};
+    const bool ok = std::fwrite("FOVPTCK1", 1, 8, f) == 8 && std::fwrite(head, sizeof(head), 1, f) == 1 &&
+                    std::fwrite(accum.data(), sizeof(float4), accum.size(), f) == accum.size();
+    std::fclose(f);
+    if (!ok) throw std::runtime_error("short write to checkpoint " + path);
+}
+
+void SampleRenderer::loadCheckpoint(const std::string& path)
+{
+    FILE* f = std::fopen(path.c_str(), "rb");
+    if (!f) throw std::runtime_error("cannot read checkpoint " + path);
+    char magic[8]; int32_t head[3] = {0, 0, 0};
+    bool ok = std::fread(magic, 1, 8, f) == 8 && std::memcmp(magic, "FOVPTCK1", 8) == 0 && std::fread(head, sizeof(head), 1, f) == 1;
+    if (ok && (head[0] != launchParams.frame.size.x || head[1] != launchParams.frame.size.y)) { std::fclose(f); throw std::runtime_error("checkpoint was written for another frame size"); }
+    std::vector<float4> accum(ok ? (size_t)head[0] * head[1] : 0);
+    ok = ok && std::fread(accum.data(), sizeof(float4), accum.size(), f) == accum.size();
+    std::fclose(f);
+    if (!ok) throw std::runtime_error("not a checkpoint file: " + path);
+    check(fovpt_upload_accum(ctx, &accum[0].x, accum.size()));
+    launchParams.frame.subframe_index = (unsigned)head[2];
 }
 
 void SampleRenderer::setCamera(const sutil::Camera& camera)

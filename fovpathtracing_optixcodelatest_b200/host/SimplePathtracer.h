@@ -10,6 +10,7 @@
 // (sutil::Exception derives from it, sutil/Exception.h:93-194).
 #pragma once
 #include <cuda_runtime.h>
+#include <string>
 
 #include "../../include/fovpt.h"
 #include "CUDAOutputBuffer.h"
@@ -44,6 +45,11 @@ public:
     void downloadPixels(uint32_t h_pixels[]);
     /*! float4 accumulation buffer (extension, for parity tests) */
     void downloadAccum(float4 h_accum[]);
+    /*! extension: checkpoint / resume of a progressive render.  The accumulation buffer and frame.subframe_index are the only
+        persistent state of the path (the reference never saves them); a run that loads a checkpoint continues
+        bit-identically.  File: "FOVPTCK1", width, height, subframe_index (int32 each), then width*height float4. */
+    void saveCheckpoint(const std::string& path);
+    void loadCheckpoint(const std::string& path);
     /*! aspect ratio is taken from frame.size, so call after resize (SimplePathtracer.cpp:282-289) */
     void setCamera(const sutil::Camera& camera);
     /*! uploads data + CDF tables; throws "Probe Data is not valid" before BuildCDF (Probe.h:102-124) */

@@ -149,5 +149,7 @@ int fovpth_render_to_output_buffer(SampleRenderer* r, int type, uint32_t* host_o
 }
 int fovpth_download_pixels(SampleRenderer* r, uint32_t* out) { GUARD(r->downloadPixels(out)); }
 int fovpth_download_accum(SampleRenderer* r, float* out) { GUARD(r->downloadAccum((float4*)out)); }
+int fovpth_save_checkpoint(SampleRenderer* r, const char* path) { GUARD(r->saveCheckpoint(path)); }
+int fovpth_load_checkpoint(SampleRenderer* r, const char* path) { GUARD(r->loadCheckpoint(path)); }
 
 }  // extern "C"

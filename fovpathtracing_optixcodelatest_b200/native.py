@@ -47,7 +47,7 @@ EXPORTS = [
     "fovpt_peer_frame_create", "fovpt_peer_frame_open", "fovpt_peer_frame_signal", "fovpt_peer_frame_wait",
     "fovpt_peer_frame_release", "fovpt_peer_frame_close", "fovpt_set_kernel_timing",
     "fovpt_render_frames", "fovpt_peer_frame_accum", "fovpt_forget_frame", "fovpt_texture_check",
-    "fovpt_feature_buffers", "fovpt_download_features",
+    "fovpt_feature_buffers", "fovpt_download_features", "fovpt_upload_accum",
 ]
 
 _lib = None
@@ -88,6 +88,7 @@ def load_library():
     L.fovpt_sync.argtypes = [vp]
     L.fovpt_download.argtypes = [vp, vp, C.c_size_t]
     L.fovpt_download_accum.argtypes = [vp, vp, C.c_size_t]
+    L.fovpt_upload_accum.argtypes = [vp, vp, C.c_size_t]
     L.fovpt_trace.argtypes = [vp, vp, C.c_size_t, i32, vp, vp]
     L.fovpt_primary_hits.argtypes = [vp, vp, C.c_uint, C.c_uint, vp, vp, vp]
     L.fovpt_set_tile_owner.argtypes = [vp, i32, i32, i32, vp, i32]
@@ -228,6 +229,10 @@ class Context:
         out = np.empty((h, w, 4), np.float32)
         self._chk(self.L.fovpt_download_accum(self.h, _p(out), w * h))
         return out
+
+    def upload_accum(self, accum):
+        a = np.ascontiguousarray(accum, dtype=np.float32)
+        self._chk(self.L.fovpt_upload_accum(self.h, _p(a), a.size // 4))
 
     def feature_buffers(self):
         """device pointers (color, normal, albedo) of the denoiser buffers at the size of the last resize"""

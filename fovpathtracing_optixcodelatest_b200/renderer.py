@@ -134,6 +134,20 @@ class SampleRenderer:
         lp = self.launchParams
         return self.ctx.download_accum(lp.frame.size_x, lp.frame.size_y)
 
+    # -- checkpoint / resume of a progressive render (the reference has none): the accumulation buffer and
+    #    frame.subframe_index are the only persistent state of the path
+    def saveCheckpoint(self, path):
+        lp = self.launchParams
+        np.savez(path, accum=self.downloadAccum(), subframe_index=np.uint32(lp.frame.subframe_index), size=np.array([lp.frame.size_x, lp.frame.size_y]))
+
+    def loadCheckpoint(self, path):
+        lp = self.launchParams
+        d = np.load(path)
+        if tuple(int(v) for v in d["size"]) != (lp.frame.size_x, lp.frame.size_y):
+            raise RuntimeError("checkpoint was written for another frame size")
+        self.ctx.upload_accum(d["accum"])
+        lp.frame.subframe_index = int(d["subframe_index"])
+
     def downloadFeatures(self):
         """dict(color, normal, albedo) of (h, w, 4) float32: LaunchParams.frame.{color,normal,albedo}_buffer (config.features = 1)"""
         lp = self.launchParams

@@ -133,6 +133,11 @@ int fovpt_download(fovpt_ctx*, uint32_t* dst, size_t npix);
  * to go away: fovpt_download falls back to the buffers of fovpt_resize instead of reading freed memory. */
 int fovpt_forget_frame(fovpt_ctx*);
 int fovpt_download_accum(fovpt_ctx*, float* dst_rgba, size_t npix);
+/* checkpoint / resume of a progressive render (the accumulation buffer and frame.subframe_index are the only
+ * persistent state of the path; the reference never saves them): blocking H2D of npix float4 values into the accumulation
+ * buffer of fovpt_resize.  Together with fovpt_download_accum and the caller's own frame.subframe_index a run continues
+ * bit-identically where it stopped (SampleRenderer::saveCheckpoint / loadCheckpoint). */
+int fovpt_upload_accum(fovpt_ctx*, const float* src_rgba, size_t npix);
 
 /* -- ray queries (optixTrace equivalents, deviceProgram.cu:196-248), for parity tests and tools.
  *    rays: n x {ox,oy,oz,tmin, dx,dy,dz,tmax} host floats (a negative tmin counts as 0).  mode 0: closest hit -> tri = global

@@ -790,6 +790,42 @@ def test_scene_ingest_is_independent_of_how_the_meshes_arrive(gpu):
     assert (a[0] == c[0]).all() and (bits(a[1]) == bits(c[1])).all()
 
 
+def test_checkpoint_resume_continues_bit_identically(gpu, tmp_path):
+    """SURVEY section 5 (checkpoint / resume; the reference has none): the accumulation buffer + frame.subframe_index are the
+    path's only persistent state.  4 subframes, checkpoint, 4 more  ==  a NEW renderer that loads the checkpoint and renders
+    4 more, bit for bit (python binding and the C++ SampleRenderer::saveCheckpoint / loadCheckpoint)"""
+    w, h, ri, ro = 240, 136, 20, 60
+    sc, cam, probe = scenes.atrium(detail=0.1), scenes.SPONZA_CAMERA, scenes.sky_probe(64, 32, 4)
+
+    def make():
+        cfg = gpu.native.default_config(); cfg.inner_radius, cfg.outer_radius = ri, ro
+        cfg.accumulate = 1; cfg.seed_all_passes_with_subframe = 1; cfg.max_depth = 6
+        r = gpu.SampleRenderer(sc, 0, cfg)
+        r.resize((w, h)); r.setCamera(cam); r.setProbe(gpu.ProbeData(probe).BuildCDF())
+        r.launchParams.frame.c_x, r.launchParams.frame.c_y = w // 2, h // 2
+        return r
+    a = make()
+    a.renderSubframes(4)
+    ck = str(tmp_path / "run.npz")
+    a.saveCheckpoint(ck)
+    a.renderSubframes(4)
+    want_px, want_acc = a.downloadPixels().copy(), a.downloadAccum().copy()
+    a.close()
+    b = make()
+    b.loadCheckpoint(ck)
+    assert b.launchParams.frame.subframe_index == 4
+    b.renderSubframes(4)
+    assert (b.downloadPixels() == want_px).all() and (bits(b.downloadAccum()) == bits(want_acc)).all()
+    with pytest.raises(RuntimeError):
+        b.resize((w // 2, h // 2)); b.loadCheckpoint(ck)                    # written for another frame size
+    b.close()
+    c = make()                                                           # without the checkpoint the same 4 subframes differ
+    c.launchParams.frame.subframe_index = 4
+    c.renderSubframes(4)
+    assert (bits(c.downloadAccum()) != bits(want_acc)).any()
+    c.close()
+
+
 def test_c_program_drives_the_abi(gpu, tmp_path):
     """tests/c/abi_smoke.c: a C99 program builds a scene and traces rays through include/fovpt.h"""
     import subprocess

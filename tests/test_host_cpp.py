@@ -53,6 +53,9 @@ def H():
     L.fovpth_render_to_output_buffer.argtypes = [vp, C.c_int, vp]
     L.fovpth_download_pixels.argtypes = [vp, vp]
     L.fovpth_download_accum.argtypes = [vp, vp]
+    L.fovpth_save_checkpoint.argtypes = [vp, C.c_char_p]
+    L.fovpth_load_checkpoint.argtypes = [vp, C.c_char_p]
+    L.fovpth_render_subframes.argtypes = [vp, C.c_int]
     return L
 
 
@@ -314,6 +317,27 @@ def test_cpp_samplerenderer_matches_oracle_and_python_binding(H, port):
     assert H.fovpth_render(r) == 0
     px2 = np.zeros((h, w), np.uint32); H.fovpth_download_pixels(r, p(px2))
     assert (px2 == px).all()
+    # (4) saveCheckpoint / loadCheckpoint: a second C++ renderer continues the progressive run of the first, bit for bit
+    import tempfile
+    cfg2 = native.default_config(); cfg2.inner_radius, cfg2.outer_radius = ri, ro; cfg2.accumulate = 1; cfg2.seed_all_passes_with_subframe = 1
+    def cpp_renderer():
+        q = H.fovpth_renderer_new(m, 0, C.byref(cfg2))
+        assert H.fovpth_resize(q, w, h) == 0 and H.fovpth_set_camera(q, p(eye), p(look), p(up), cam.fovy) == 0 and H.fovpth_set_probe(q, 16, 8, p(probe), 1) == 0
+        qlp = LaunchParams.from_address(H.fovpth_launch_params(q)); qlp.frame.c_x, qlp.frame.c_y = w // 2, h // 2
+        return q, qlp
+    with tempfile.TemporaryDirectory() as td:
+        ck = os.path.join(td, "run.ck").encode()
+        r1, lp1 = cpp_renderer()
+        assert H.fovpth_render_subframes(r1, 3) == 0 and H.fovpth_save_checkpoint(r1, ck) == 0 and H.fovpth_render_subframes(r1, 2) == 0
+        a1 = np.zeros((h, w, 4), np.float32); H.fovpth_download_accum(r1, p(a1))
+        r2, lp2 = cpp_renderer()
+        assert H.fovpth_load_checkpoint(r2, ck) == 0, H.fovpth_last_error()
+        assert lp2.frame.subframe_index == 3
+        assert H.fovpth_render_subframes(r2, 2) == 0
+        a2 = np.zeros((h, w, 4), np.float32); H.fovpth_download_accum(r2, p(a2))
+        assert (bits(a1) == bits(a2)).all() and lp2.frame.subframe_index == 5
+        assert H.fovpth_load_checkpoint(r2, os.path.join(td, "missing.ck").encode()) != 0 and b"checkpoint" in H.fovpth_last_error()
+        H.fovpth_renderer_free(r1); H.fovpth_renderer_free(r2)
     H.fovpth_renderer_free(r); H.fovpth_model_free(m)
 
 

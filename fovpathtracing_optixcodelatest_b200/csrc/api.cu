@@ -362,6 +362,7 @@ int run_frame(fovpt_ctx* c, const LaunchParamsBlob& lp, const std::vector<PassHo
     for (auto& g : groups) max_paths = std::max(max_paths, g.paths);
     if (max_paths >= 0xff000000ull) return fail(c, "path batch exceeds 32-bit ids");
     if (ensure_paths(c, max_paths)) return 1;
+    F.path_cap = (unsigned)std::min<size_t>(c->path_cap, 0xffffffffu);
 
     const bool feat = c->cfg.features != 0;
     PathState ps = c->ps;
@@ -653,6 +654,7 @@ static int scene_commit(fovpt_ctx* c, uint64_t* traversable_out)
     c->scene.tri_mesh = c->d_tri_mesh; c->scene.tri_vidx = c->d_idx; c->scene.texcoords = c->a_tc.p;
     c->scene.materials = c->d_mat; c->scene.mesh_tex = c->d_mesh_tex; c->scene.tex_info = c->d_tex_info; c->scene.texels = c->d_texels;
     c->scene.any_catcher = any_catcher;
+    c->scene.n_meshes = (uint32_t)mats.size(); c->scene.n_textures = (uint32_t)tex_info.size(); c->scene.n_vertices = (uint32_t)nv;
     c->committed = true;
     if (traversable_out) *traversable_out = (uint64_t)(uintptr_t)c->bvh.nodes | 1ull;
     return 0;
@@ -794,6 +796,7 @@ int fovpt_sync(fovpt_ctx* c)
     CU(cudaStreamSynchronize(c->stream));
     CU(cudaGetLastError());
     collect_times(c);
+    if (const unsigned site = read_check_failure()) return fail(c, "bounds check " + std::to_string(site) + " failed in a kernel (FOVPT_CHECKED build, sites in csrc/bvh.cuh / wavefront.cu)");
     if (c->peer.open) {                       // a wait on the shared frame that timed out left the number of the missing rank + 1
         uint32_t* where = c->peer.owner ? c->peer.flags + kPeerError : c->peer.d_err;
         uint32_t e = 0;

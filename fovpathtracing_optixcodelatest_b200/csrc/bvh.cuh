@@ -24,6 +24,20 @@
 
 #include "../../include/fovpt_exact.h"
 
+// Bounds-checked build (make -C csrc checked -> libfovpt_checked.so; compute-sanitizer is not available on the B200 pool, so the
+// memory-safety evidence is this: every index the kernels derive from device data is tested before use, a violation latches its
+// site number in a device word that fovpt_sync reports, and the GPU test suite runs against that build through FOVPT_LIB).
+// In the product build the macro expands to nothing.
+#ifndef FOVPT_CHECKED
+#define FOVPT_CHECKED 0
+#endif
+#if FOVPT_CHECKED
+static __device__ unsigned int g_fovpt_check_site = 0;
+#define FOVPT_CHECK(cond, site) do { if (!(cond)) atomicCAS(&g_fovpt_check_site, 0u, (unsigned)(site)); } while (0)
+#else
+#define FOVPT_CHECK(cond, site) do { } while (0)
+#endif
+
 namespace fovpt {
 
 constexpr int kBvhWide = 4;   // branching factor of the device BVH (an 8-wide compressed layout was built and measured in round 1:
@@ -59,7 +73,11 @@ struct RayStack {
     int2* local;          // kStackSize entries
     int2* shared;         // this thread's column: entry e at shared[e * stride]
     int   n_shared, stride;
-    __device__ __forceinline__ void put(int i, int2 v) const { if (i < n_shared) shared[i * stride] = v; else local[i - n_shared] = v; }
+    __device__ __forceinline__ void put(int i, int2 v) const
+    {
+        FOVPT_CHECK(i >= 0 && i - n_shared < kStackSize, 3);
+        if (i < n_shared) shared[i * stride] = v; else local[i - n_shared] = v;
+    }
     __device__ __forceinline__ int2 get(int i) const { return i < n_shared ? shared[i * stride] : local[i - n_shared]; }
     // store under a predicate, meant to compile to predicated STS / STL without a branch (i may be out of range when !p)
     __device__ __forceinline__ void put_if(bool p, int i, int2 v) const
@@ -210,6 +228,7 @@ struct Traversal {
     // matter -- skip the distance keys and the sorting network
     __device__ __forceinline__ void node_step(const DeviceBvh& bvh, const RayStack& stack, bool unordered = false)
     {
+        FOVPT_CHECK((uint32_t)cur < bvh.n_nodes, 1);
         const uint4* np = bvh.nodes + 4 * (size_t)cur;
         const u8x A = ldg256(np), B = ldg256(np + 2);           // A = (n0, n1), B = (n2, n3)
         const float tlimit = is_any() ? tmax : fminf(tmax, best_t);
@@ -283,6 +302,7 @@ struct Traversal {
     __device__ __forceinline__ void leaf_step(const DeviceBvh& bvh, const RayStack& stack, const RayRows& rows, uint32_t nmax)
     {
         const uint32_t first = leaf_first(cur), count = leaf_count(cur);
+        FOVPT_CHECK(first + count <= bvh.n_tris, 2);
         bool occluded = false;
         for (uint32_t i = 0; i < nmax; ++i) {
             if (i < count) {

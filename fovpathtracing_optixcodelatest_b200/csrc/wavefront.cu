@@ -53,6 +53,7 @@ __device__ __forceinline__ bool tile_is_mine(const FrameDev& F, int X, int Y)
 {
     if (!F.tile_owner) return true;
     const int tx = X / F.tile_size, ty = Y / F.tile_size;
+    FOVPT_CHECK(tx >= 0 && tx < F.tiles_x && ty >= 0 && ty < F.tiles_y, 6);
     return F.tile_owner[ty * F.tiles_x + tx] == (uint8_t)F.rank;
 }
 
@@ -139,6 +140,7 @@ __global__ void k_raygen(FrameDev F, ChunkTable T, const uint8_t* __restrict__ n
             const PassDev& P = F.pass[pass];
             uint32_t slot = s_base + __popc(m & ((1u << lane) - 1u));
             for (unsigned w = 0; w < wib; ++w) slot += s_cnt[w];
+            FOVPT_CHECK(slot < F.path_cap && pid < F.path_cap && P.li_base + li < F.li_total, 7);
             uint32_t px, py;
             fx_launch_to_pixel(lx, ly, P.factor, P.factor, P.uoff_x, P.uoff_y, &px, &py);
             uint32_t seed = fx_tea4(ly * (unsigned)F.w + lx, P.subframe + layer * P.sub_step);   // :411
@@ -384,9 +386,11 @@ __device__ __forceinline__ void shade_path(const FrameDev& F, const SceneDev& S,
     const uint32_t slot = (uint32_t)__float_as_int(h4.w);
     if (slot == kNoHit) return;                               // __miss__radiance: DONE, adds nothing (:253-282)
     const float3 ro = f3(ro4.x, ro4.y, ro4.z), rd = f3(rd4.x, rd4.y, rd4.z);
+    FOVPT_CHECK(slot < S.bvh.n_tris && pid < F.path_cap, 5);
     const float4* tp = S.bvh.tris + 3 * (size_t)slot;
     const float4 ta = __ldg(tp), tb = __ldg(tp + 1), tc = __ldg(tp + 2);
     const uint32_t gid = (uint32_t)__float_as_int(ta.w);
+    FOVPT_CHECK(gid < S.bvh.n_tris && (uint32_t)__float_as_int(tb.w) < S.n_meshes, 5);
     // geometric normal, flipped toward the viewer (:632-634)
     const float3 v0 = f3(ta.x, ta.y, ta.z);
     const float3 n0 = unit3<FAST>(cross3(f3(tb.x, tb.y, tb.z) - v0, f3(tc.x, tc.y, tc.z) - v0));
@@ -421,6 +425,7 @@ __device__ __forceinline__ void shade_path(const FrameDev& F, const SceneDev& S,
     float3 albedo = bp.color;
     if (mt.x >= 0 && mt.y) {                                 // :655-665
         const uint32_t* vi = S.tri_vidx + 3 * (size_t)gid;
+        FOVPT_CHECK((uint32_t)mt.x < S.n_textures && vi[0] < S.n_vertices && vi[1] < S.n_vertices && vi[2] < S.n_vertices, 8);
         const float2 t0 = __ldg(&S.texcoords[vi[0]]), t1 = __ldg(&S.texcoords[vi[1]]), t2 = __ldg(&S.texcoords[vi[2]]);
         const float u = h4.y, v = h4.z, w0 = 1.f - u - v;
         const int4 ti = __ldg(&S.tex_info[mt.x]);
@@ -575,10 +580,12 @@ __global__ void __launch_bounds__(128, FOVPT_SHADE_BLOCKS) k_shade(FrameDev F, S
         const unsigned lt = (1u << lane) - 1u;
         if (out.push_next) {
             const uint32_t j = on + __popc(mn & lt);
+            FOVPT_CHECK(j < F.path_cap, 9);
             q.next.o[j] = out.o; q.next.d[j] = out.d; q.next.thr[j] = out.thr; q.next.rng[j] = out.rng; q.next.meta[j] = out.meta;
         }
         if (out.push_shadow) {
             const uint32_t k = os + __popc(ms & lt);
+            FOVPT_CHECK(k < F.path_cap, 9);
             q.shadow.o[k] = out.o; q.shadow.d[k] = out.s_d; q.shadow.pend[k] = out.s_pend; q.shadow.pid[k] = out.meta.x;
         }
     }
@@ -679,6 +686,7 @@ __global__ void k_resolve_px(FrameDev F, const uint32_t* __restrict__ owner_map,
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
         const uint32_t own = owner_map[i];
         if (own == kNoOwner) continue;
+        FOVPT_CHECK((int)(own >> 28) < F.npass && (own & 0x0fffffffu) < F.pass[own >> 28].lw * F.pass[own >> 28].lh, 10);
         const PassDev& P = F.pass[own >> 28];
         const bool lerps = F.accumulate && !P.redraw;
         float3 acc = f3(0.f);
@@ -908,6 +916,19 @@ void launch_primary_hits(const LaunchCfg& L, const FrameDev& F, const SceneDev& 
 void launch_trace_query(const LaunchCfg& L, const SceneDev& S, const float* rays, size_t n, int mode, int32_t* tri, float* tuv)
 {
     k_trace_query<<<L.grid_trace, 128, 0, L.stream>>>(S, rays, n, mode, tri, tuv);
+}
+
+// bounds-checked build: the site number of the first failed check since the last call (0 = none); always 0 in the product build
+unsigned read_check_failure()
+{
+#if FOVPT_CHECKED
+    unsigned v = 0, zero = 0;
+    cudaMemcpyFromSymbol(&v, g_fovpt_check_site, sizeof(v));
+    if (v) cudaMemcpyToSymbol(g_fovpt_check_site, &zero, sizeof(zero));
+    return v;
+#else
+    return 0u;
+#endif
 }
 
 void query_occupancy(int* extend_blocks_per_sm, int* shade_blocks_per_sm)

@@ -65,6 +65,7 @@ struct SceneDev {
     const int4*         tex_info;     // per texture: (texel offset, w, h, 0)
     const uint32_t*     texels;
     int                 any_catcher;
+    uint32_t            n_meshes, n_textures, n_vertices;     // table sizes (bounds-checked build)
 };
 
 struct PassDev {
@@ -91,6 +92,7 @@ struct FrameDev {
     // nsub layers of li_total entries, k_resolve_px replays the per-frame accumulation over the layers in order
     int       nsub;
     unsigned  li_total;
+    unsigned  path_cap;         // slots of the per-path / per-ray buffers (bounds-checked build)
     // config
     int   max_depth;
     float tmin, tmax, exposure;

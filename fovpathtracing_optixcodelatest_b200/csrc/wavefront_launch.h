@@ -38,5 +38,6 @@ void launch_trace_query(const LaunchCfg&, const SceneDev&, const float* rays, si
 void launch_texture_probe(const LaunchCfg&, cudaTextureObject_t tex, const uint32_t* texels, int w, int h, const float2* uv, size_t n, int mode,
                           float4* sw, float4* hw);
 void query_occupancy(int* extend_blocks_per_sm, int* shade_blocks_per_sm);
+unsigned read_check_failure();      // FOVPT_CHECKED builds: site of the first failed bounds check (bvh.cuh), else 0
 
 }  // namespace fovpt

@@ -10,9 +10,12 @@ Bars (BASELINE.json north_star):
   * RGBA8 frame                                                      -> >= 99 % of pixels identical
 """
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
+
+from conftest import ROOT
 
 from fovpathtracing_optixcodelatest_b200 import partition, scenes, workloads
 from fovpathtracing_optixcodelatest_b200.structs import LaunchParams, Material
@@ -824,6 +827,37 @@ def test_checkpoint_resume_continues_bit_identically(gpu, tmp_path):
     c.renderSubframes(4)
     assert (bits(c.downloadAccum()) != bits(want_acc)).any()
     c.close()
+
+
+def test_bounds_checked_build_finds_no_violation():
+    """libfovpt_checked.so (make -C csrc checked: every index the kernels derive from device data is tested before use, the
+    first violation is reported by fovpt_sync) renders the smoke frame, a textured depth-8 batch with features and filter on and
+    traces random rays without a report.  The pool has no compute-sanitizer; the full parity suite was also run against this
+    build (profiles/pytest_r03g_checked_build.log: FOVPT_LIB=.../libfovpt_checked.so pytest tests/test_gpu_parity.py -m gpu)."""
+    import subprocess, sys
+    lib = os.path.join(ROOT, "fovpathtracing_optixcodelatest_b200", "libfovpt_checked.so")
+    if not os.path.exists(lib):
+        pytest.skip("libfovpt_checked.so not built (make -C fovpathtracing_optixcodelatest_b200/csrc checked)")
+    code = (
+        "import numpy as np\n"
+        "import __graft_entry__ as g\n"
+        "g.smoke()\n"
+        "from fovpathtracing_optixcodelatest_b200 import native, scenes\n"
+        "from fovpathtracing_optixcodelatest_b200.renderer import ProbeData, SampleRenderer\n"
+        "assert native.LIB_PATH != native.os.environ['FOVPT_LIB']\n"
+        "cfg = native.default_config(); cfg.inner_radius, cfg.outer_radius, cfg.max_depth = 30, 90, 8\n"
+        "cfg.accumulate = cfg.seed_all_passes_with_subframe = cfg.features = cfg.filter = 1\n"
+        "r = SampleRenderer(scenes.atrium(detail=0.2), 0, cfg)\n"
+        "r.resize((400, 224)); r.setCamera(scenes.SPONZA_CAMERA); r.setProbe(ProbeData(scenes.sky_probe(64, 32, 2)).BuildCDF())\n"
+        "r.launchParams.frame.c_x, r.launchParams.frame.c_y = 20, 200\n"
+        "r.renderSubframes(3); r.render()\n"
+        "rays = np.random.default_rng(1).normal(size=(20000, 8)).astype(np.float32); rays[:, 3] = 0.0; rays[:, 7] = 1e9\n"
+        "rays[:, :3] *= 300\n"
+        "r.ctx.trace(rays, 0); r.ctx.trace(rays, 1); r.ctx.sync(); r.close()\n"
+        "print('checked build ok')\n")
+    env = dict(os.environ, FOVPT_LIB=lib, PYTHONPATH=ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd=ROOT, timeout=600)
+    assert out.returncode == 0 and "checked build ok" in out.stdout, out.stdout + out.stderr
 
 
 def test_c_program_drives_the_abi(gpu, tmp_path):
